@@ -1,0 +1,147 @@
+"""Synthetic Visual-Genome-shaped inputs and weights.
+
+There is no dataset / checkpoint access, so every test, fixture and benchmark
+uses inputs generated here from a numpy ``default_rng`` seed.  The same
+generator is used by the golden-fixture script (which feeds the reference), the
+oracle tests and ``bench.py``, so "identical inputs" is by construction.
+
+Shapes follow the reference: boxes are pixel xyxy in the 592-px frame
+(config.py:32 IM_SCALE), classes 1..150, predicates 1..50, edges are ordered
+pairs (i != j) of same-image objects sorted by (img, subj, obj) exactly as
+lib/proposal_assignments_gtbox.py:74-77 leaves them.
+"""
+import hashlib
+import numpy as np
+
+IM_SCALE = 592
+NUM_CLASSES = 151
+NUM_RELS = 51
+
+
+def synth_graph(B, n_box, n_edge, seed, ragged=False, all_pairs=False):
+    """Returns a dict with
+    boxes [N,4] f32, gt_classes [N,2] i64 (img, cls), im_inds [N] i64,
+    rel_inds [E,3] i64 (img, subj_global, obj_global) sorted,
+    gt_rels [R,4] i64 (img, subj_local, obj_local, pred), rel_labels [E,4] i64.
+    """
+    rng = np.random.default_rng(seed)
+    boxes, classes, rel_inds, gt_rels, rel_labels = [], [], [], [], []
+    base = 0
+    for b in range(B):
+        nb = n_box
+        if ragged:
+            nb = int(np.clip(np.rint(rng.normal(n_box, 0.2 * n_box)), 2, 62))
+        xy = rng.random((nb, 2), dtype=np.float32) * np.float32(0.6 * IM_SCALE)
+        wh = rng.random((nb, 2), dtype=np.float32) * np.float32(0.4 * IM_SCALE - 16) + np.float32(16)
+        boxes.append(np.concatenate((xy, xy + wh), 1).astype(np.float32))
+        cls = rng.integers(1, NUM_CLASSES, nb)
+        classes.append(np.stack((np.full(nb, b), cls), 1))
+        ii, jj = np.nonzero(~np.eye(nb, dtype=bool))
+        ncand = ii.shape[0]
+        if all_pairs or n_edge >= ncand:
+            sel = np.arange(ncand)
+        else:
+            sel = np.sort(rng.choice(ncand, n_edge, replace=False))
+        si, oi = ii[sel], jj[sel]
+        pred = np.zeros(sel.shape[0], np.int64)
+        nfg = min(5, sel.shape[0])
+        fg = rng.choice(sel.shape[0], nfg, replace=False)
+        pred[fg] = rng.integers(1, NUM_RELS, nfg)
+        rel_inds.append(np.stack((np.full_like(si, b), si + base, oi + base), 1))
+        rel_labels.append(np.stack((np.full_like(si, b), si + base, oi + base, pred), 1))
+        gt_rels.append(np.stack((np.full(nfg, b), si[fg], oi[fg], pred[fg]), 1))
+        base += nb
+    g = dict(boxes=np.concatenate(boxes), gt_classes=np.concatenate(classes).astype(np.int64),
+             rel_inds=np.concatenate(rel_inds).astype(np.int64),
+             gt_rels=np.concatenate(gt_rels).astype(np.int64),
+             rel_labels=np.concatenate(rel_labels).astype(np.int64))
+    g['im_inds'] = g['gt_classes'][:, 0].copy()
+    g['rois'] = np.concatenate((g['im_inds'][:, None].astype(np.float32), g['boxes']), 1)
+    return g
+
+
+def synth_l1_feats(N, E, seed, D=4096):
+    """Precomputed-feature inputs at the L1 boundary: node head ends in ReLU
+    (rel_model_base.py:111), edge head ends linear (:110)."""
+    rng = np.random.default_rng(seed + 7919)
+    obj = np.maximum(rng.standard_normal((N, D), dtype=np.float32), 0)
+    edge = rng.standard_normal((E, D), dtype=np.float32)
+    return obj, edge
+
+
+def synth_l0_states(N, E, seed, H=512):
+    """message_pass inputs: obj_rep (obj_unary output, linear) and rel_rep (post-ReLU)."""
+    rng = np.random.default_rng(seed + 104729)
+    obj = rng.standard_normal((N, H), dtype=np.float32) * np.float32(0.5)
+    rel = np.maximum(rng.standard_normal((E, H), dtype=np.float32) * np.float32(0.5), 0)
+    return obj, rel
+
+
+def synth_pooled(N, E, seed, C=512, P=7):
+    """L2 inputs: RoIAlign outputs of a post-ReLU feature map are non-negative."""
+    rng = np.random.default_rng(seed + 15485863)
+    node = np.maximum(rng.standard_normal((N, C, P, P), dtype=np.float32), 0)
+    edge = np.maximum(rng.standard_normal((E, C, P, P), dtype=np.float32), 0)
+    return node, edge
+
+
+def synth_fmap(B, seed, C=512, S=38):
+    rng = np.random.default_rng(seed + 32452843)
+    return np.maximum(rng.standard_normal((B, C, S, S), dtype=np.float32), 0)
+
+
+def _u(rng, shape, bound):
+    return ((rng.random(shape, dtype=np.float32) * 2 - 1) * np.float32(bound)).astype(np.float32)
+
+
+def synth_params(seed, H=512, D=4096, scale=1.0, level='l1', C=512, P=7):
+    """State-dict-keyed weights (names/shapes of SURVEY.md §8a), U(-s/sqrt(fan_in), s/sqrt(fan_in))
+    like torch's default Linear/GRUCell init, ``scale`` > 1 emulates trained logit magnitudes.
+
+    level: 'l0' message-passing only; 'l1' + unary/heads; 'l2' + union_boxes.conv and roi_fmap*.
+    """
+    rng = np.random.default_rng(seed + 611953)
+    p = {}
+    s = float(scale)
+    for gname in ('edge_gru', 'node_gru'):
+        b = s / np.sqrt(H)
+        p[gname + '.weight_ih'] = _u(rng, (3 * H, H), b)
+        p[gname + '.weight_hh'] = _u(rng, (3 * H, H), b)
+        p[gname + '.bias_ih'] = _u(rng, (3 * H,), b)
+        p[gname + '.bias_hh'] = _u(rng, (3 * H,), b)
+    for k in ('sub_vert', 'obj_vert', 'out_edge', 'in_edge'):
+        b = s / np.sqrt(2 * H)
+        p[k + '_w_fc.0.weight'] = _u(rng, (1, 2 * H), b)
+        p[k + '_w_fc.0.bias'] = _u(rng, (1,), b)
+    if level in ('l1', 'l2'):
+        for k, (o, i) in (('obj_unary', (H, D)), ('edge_unary', (H, D)),
+                          ('obj_fc', (NUM_CLASSES, H)), ('rel_fc', (NUM_RELS, H))):
+            b = s / np.sqrt(i)
+            p[k + '.weight'] = _u(rng, (o, i), b)
+            p[k + '.bias'] = _u(rng, (o,), b)
+    if level == 'l2':
+        half = C // 2
+        p['union_boxes.conv.0.weight'] = _u(rng, (half, 2, 7, 7), s / np.sqrt(2 * 49))
+        p['union_boxes.conv.0.bias'] = _u(rng, (half,), s / np.sqrt(2 * 49))
+        p['union_boxes.conv.4.weight'] = _u(rng, (C, half, 3, 3), s / np.sqrt(half * 9))
+        p['union_boxes.conv.4.bias'] = _u(rng, (C,), s / np.sqrt(half * 9))
+        for idx, ch in (('2', half), ('6', C)):
+            p['union_boxes.conv.%s.weight' % idx] = (rng.random(ch, dtype=np.float32) + np.float32(0.5))
+            p['union_boxes.conv.%s.bias' % idx] = _u(rng, (ch,), 0.2)
+            p['union_boxes.conv.%s.running_mean' % idx] = _u(rng, (ch,), 0.2)
+            p['union_boxes.conv.%s.running_var' % idx] = (rng.random(ch, dtype=np.float32) + np.float32(0.5))
+        fin = C * P * P
+        for pre in ('roi_fmap.1.', 'roi_fmap_obj.'):
+            p[pre + '0.weight'] = _u(rng, (D, fin), s / np.sqrt(fin))
+            p[pre + '0.bias'] = _u(rng, (D,), s / np.sqrt(fin))
+            p[pre + '3.weight'] = _u(rng, (D, D), s / np.sqrt(D))
+            p[pre + '3.bias'] = _u(rng, (D,), s / np.sqrt(D))
+    return p
+
+
+def digest(*arrays):
+    """Short content hash used by fixtures to detect generator drift."""
+    h = hashlib.sha256()
+    for a in arrays:
+        h.update(np.ascontiguousarray(a).tobytes())
+    return h.hexdigest()[:16]

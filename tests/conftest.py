@@ -1,0 +1,17 @@
+import os, sys
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def built_lib():
+    """Path of the in-tree C-ABI library; builds it (nvcc cross-compile) if missing."""
+    from sgg_b200 import _build
+    return _build.ensure_built()
