@@ -1,0 +1,379 @@
+#!/usr/bin/env python
+"""Benchmark of the IMP relation-model hot path (BASELINE.json metric: images/sec, PredCls,
+3 MP iterations; MP/L1-kernel HBM GB/s vs measured peak).
+
+  python bench.py --gpus 1 --steps 50 --warmup 5            # this repo's CUDA path
+  python bench.py --impl reference --steps 3 --warmup 1     # reference's CPU path (oracle port)
+  python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+Workload at N=1 = BASELINE.json configs[1]: PredCls batch=8, 30 boxes/img, 300 candidate
+edges/img, 4096-d features (the L1 boundary: rel_model_stanford.py:103-107 without roi_fmap*),
+3 MP iterations.  A "step" = one L1 forward over one batch of 8 synthetic images.  N>1: every
+rank runs the same-sized independent batch (images shard naturally; no data-path collective),
+weak scaling, value = images of all ranks / max-over-ranks time.
+
+One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from sgg_b200 import synth  # noqa: E402
+
+L2_BYTES_FALLBACK = 126 * 1024 * 1024
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=50)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='native', choices=['native', 'reference'])
+    ap.add_argument('--batch', type=int, default=8)
+    ap.add_argument('--boxes', type=int, default=30)
+    ap.add_argument('--edges', type=int, default=300)
+    ap.add_argument('--iters', type=int, default=3)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-graph', action='store_true', help='do not replay the step from a CUDA graph')
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d['hbm_gbs']), float(d.get('bf16_tflops', 0)), 'measured (MEASURED_PEAKS.json)'
+    return 6650.0, 1590.0, 'fallback (B200_PROFILING.md)'
+
+
+def alg_bytes_l1(N, E, H, D, T, n_cls=151, n_rel=51, idx_bytes=8):
+    """SURVEY.md §8d 'L1 per forward' minimum: feature read + logits out + weights once (states
+    assumed L2-resident across iterations) + the int64 rel_inds the boundary receives."""
+    w_mp = 4 * (2 * (2 * 3 * H * H + 2 * 3 * H) + 4 * (2 * H + 1))
+    w_unary = 2 * 4 * (H * D + H)
+    w_heads = 4 * (n_cls * H + n_cls + n_rel * H + n_rel)
+    return 4 * D * (N + E) + 4 * (n_cls * N + n_rel * E) + idx_bytes * 2 * E + w_mp + w_unary + w_heads
+
+
+def alg_flops_l1(N, E, H, D, T, n_cls=151, n_rel=51):
+    """SURVEY.md §8d canonical flop count (no linearity shortcut)."""
+    gru = 2 * (H * 3 * H) * 2
+    return (2 * D * H * (N + E) + (gru // 2) * (N + E) + T * (gru * (N + E) + 8 * H * 2 * E)
+            + 2 * H * (n_cls * N + n_rel * E))
+
+
+class ClockSampler(object):
+    """nvidia-smi sampler (B200_PROFILING.md 'clocks line') running during the timed region."""
+
+    def __init__(self, index=0):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+             'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+             'clocks_event_reasons.sw_power_cap')
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.12)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(',')]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(n)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': mx, 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+def make_case(args, rank, slot):
+    seed = 1234 + 2 + 1000 * rank + slot
+    g = synth.synth_graph(args.batch, args.boxes, args.edges, seed)
+    N, E = g['boxes'].shape[0], g['rel_inds'].shape[0]
+    of, ef = synth.synth_l1_feats(N, E, seed)
+    return dict(N=N, E=E, obj=of, edge=ef, rel=np.ascontiguousarray(g['rel_inds'][:, 1:3]))
+
+
+def cpu_reference_run(args, cases, params, steps, warmup, threads):
+    """The reference's PyTorch-CPU path (oracle/imp_torch_cpu.py port: same op sequence incl. the dense
+    [N,E] incidence matmuls), eval mode, no_grad, all host threads."""
+    from oracle.imp_torch_cpu import ImpCpu
+    torch.set_num_threads(threads)
+    m = ImpCpu(mp_iter=args.iters).load_numpy(params).eval()
+    ins = [(torch.from_numpy(c['obj']), torch.from_numpy(c['edge']), torch.from_numpy(c['rel'])) for c in cases]
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            o, e, r = ins[i % len(ins)]
+            t0 = time.perf_counter()
+            m.l1_forward(o, e, r)
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+    return times
+
+
+def main():
+    args = parse()
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    H, D = 512, 4096
+    workload = ('PredCls L1 batch=%d, %d boxes/img, %d edges/img, 4096-d feats, %d MP iters'
+                % (args.batch, args.boxes, args.edges, args.iters))
+    config = {'workload': workload, 'batch_per_gpu': args.batch, 'boxes_per_img': args.boxes,
+              'edges_per_img': args.edges, 'mp_iter': args.iters, 'boundary': 'L1 (4096-d features -> dists)',
+              'parallelism': 'dp%d (independent image shards, no data-path collective)' % max(world, 1)}
+    params = synth.synth_params(111, level='l1')
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == 'reference':
+        if rank != 0:
+            return 0
+        threads = os.cpu_count() or 1
+        cases = [make_case(args, 0, s) for s in range(2)]
+        times = cpu_reference_run(args, cases, params, args.steps, args.warmup, threads)
+        ms = float(np.mean(times) * 1e3)
+        val = args.batch / (ms / 1e3)
+        line = {'impl': 'reference', 'metric': 'images/sec (PredCls, 3 MP iters)', 'value': val, 'unit': 'images/s',
+                'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms,
+                'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+                'data': 'synthetic', 'config': config,
+                'cpu_baseline': {'value': val, 'unit': 'images/s', 'cores': threads, 'kind': 'port',
+                                 'sample': '%d steps of the full workload (one batch of %d images each)'
+                                           % (args.steps, args.batch)},
+                'e2e': {'value': val, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ native arm (CUDA)
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py --impl native needs a CUDA device (no CPU fallback)')
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=dev)
+    from sgg_b200 import ops, _lib
+    from sgg_b200.runner import ImpL1Runner
+    lib = _lib.load()
+
+    info = (torch.cuda.get_device_properties(dev))
+    l2 = getattr(info, 'L2_cache_size', L2_BYTES_FALLBACK) or L2_BYTES_FALLBACK
+    c0 = make_case(args, rank, 0)
+    N, E = c0['N'], c0['E']
+    in_bytes = (N + E) * D * 4
+    ring = max(2, int(np.ceil(1.5 * l2 / in_bytes)))          # input ring > L2 so features come from HBM
+    cases = [c0] + [make_case(args, rank, s) for s in range(1, ring)]
+    config['l2_policy'] = 'input ring of %d x %.1f MB > %.0f MB L2 (features read from HBM every step)' % (
+        ring, in_bytes / 1e6, l2 / 1e6)
+
+    dparams = {k: torch.from_numpy(v).to(dev) for k, v in params.items()}
+    d_in = [(torch.from_numpy(c['obj']).to(dev), torch.from_numpy(c['edge']).to(dev),
+             torch.from_numpy(c['rel']).to(dev)) for c in cases]
+    plan = ops.L1Plan(dparams, N, E, D, args.iters, dev)
+    graphs_ws = [None] * ring
+
+    def step_eager(i):
+        o, e, r = d_in[i % ring]
+        g = ops.build_graph(r, N)
+        graphs_ws[i % ring] = g
+        plan.run(o, e, g)
+
+    # CUDA graphs: one captured step per ring slot (static shapes), replayed in the loop.
+    launches_per_step = None
+    cuda_graphs = None
+    if not args.no_graph:
+        try:
+            for i in range(ring):
+                step_eager(i)
+            torch.cuda.synchronize()
+            cuda_graphs = []
+            side = torch.cuda.Stream()
+            for i in range(ring):
+                gr = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gr, stream=side):
+                    n0 = lib.sgg_launch_count()
+                    step_eager(i)
+                    launches_per_step = lib.sgg_launch_count() - n0
+                cuda_graphs.append(gr)
+            config['launch'] = 'cuda-graph replay (1 graph/step, %d kernels)' % launches_per_step
+        except Exception as ex:   # capture unsupported: fall back to eager launches (still the CUDA path)
+            cuda_graphs = None
+            config['launch'] = 'eager (graph capture failed: %s)' % str(ex)[:80]
+    if cuda_graphs is None:
+        n0 = lib.sgg_launch_count(); step_eager(0); launches_per_step = lib.sgg_launch_count() - n0
+        config.setdefault('launch', 'eager')
+
+    def step(i):
+        if cuda_graphs is not None:
+            cuda_graphs[i % ring].replay()
+        else:
+            step_eager(i)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput ("value")
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local_rank).start() if rank == 0 else None
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(args.steps):
+        step(i)
+    ev1.record()
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    if dist is not None:
+        t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+
+    # ---- end-to-end through the host-buffer API ("e2e"): pinned host inputs, H2D + D2H inside the timed region
+    runner = ImpL1Runner(dparams, N, E, args.iters, slots=3, device=dev)
+    h_in = [(torch.from_numpy(c['obj']).pin_memory(), torch.from_numpy(c['edge']).pin_memory(),
+             torch.from_numpy(c['rel']).pin_memory()) for c in cases[:max(2, min(ring, 4))]]
+    for i in range(max(args.warmup, 3)):
+        runner.wait(runner.submit(*h_in[i % len(h_in)]))
+    barrier()
+    t0 = time.perf_counter()
+    pending = []
+    for i in range(args.steps):
+        pending.append(runner.submit(*h_in[i % len(h_in)]))
+        if len(pending) >= 3:
+            runner.wait(pending.pop(0))
+    while pending:
+        runner.wait(pending.pop(0))
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    clocks = sampler.stop() if sampler is not None else None
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant stage, timed live with CUDA events on the launching stream
+    hbm_peak, tf_peak, peak_src = peaks()
+    g0 = ops.build_graph(d_in[0][2], N)
+    stages = {}
+
+    def time_stage(name, fn, reps=20):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record(); torch.cuda.synchronize()
+        stages[name] = a.elapsed_time(b) / reps
+
+    obj_rep = ops.linear(d_in[0][0], dparams['obj_unary.weight'], dparams['obj_unary.bias'])
+    rel_rep = ops.linear(d_in[0][1], dparams['edge_unary.weight'], dparams['edge_unary.bias'], relu=True)
+    k = [0]
+
+    def unary():
+        k[0] += 1
+        o, e, _ = d_in[k[0] % ring]
+        ops.linear(e, dparams['edge_unary.weight'], dparams['edge_unary.bias'], relu=True)
+
+    time_stage('edge_unary_linear', unary)
+    time_stage('message_pass_T%d' % args.iters, lambda: ops.message_pass(rel_rep, obj_rep, g0, dparams, args.iters))
+    time_stage('graph_build', lambda: ops.build_graph(d_in[0][2], N))
+    w_mp = 4 * (2 * (2 * 3 * H * H + 2 * 3 * H) + 4 * (2 * H + 1))
+    mp_bytes_iter = 4 * H * 2 * (N + E) + 8 * 2 * E      # SURVEY §8d bytes_iter without weights
+    mp_bytes = args.iters * mp_bytes_iter + w_mp + 4 * H * 2 * (N + E)   # + initial-step read/write
+    unary_bytes = 4 * D * E + 4 * (H * D + H) + 4 * H * E
+    dom = max(('edge_unary_linear', 'message_pass_T%d' % args.iters), key=lambda n: stages[n])
+    dom_bytes = unary_bytes if dom == 'edge_unary_linear' else mp_bytes
+    ach = dom_bytes / (stages[dom] * 1e-3) / 1e9
+    gru_flops = 2 * (H * 3 * H) * 2
+    mp_flops = (gru_flops // 2) * (N + E) + args.iters * (gru_flops * (N + E) + 8 * H * 2 * E)
+    unary_flops = 2 * D * H * E
+    roofline = {'bound': 'hbm', 'kernel': dom, 'achieved': ach, 'peak': hbm_peak, 'unit': 'GB/s',
+                'frac': ach / hbm_peak, 'traffic': None, 'peak_source': peak_src,
+                'algorithmic_bytes': dom_bytes,
+                'note': 'fp32 SIMT tile GEMMs in round 1: the binding term is fp32 FMA issue, not HBM (DESIGN.md §5)',
+                'stage_ms': stages,
+                'tflops_fp32': {'edge_unary_linear': unary_flops / (stages['edge_unary_linear'] * 1e-3) / 1e12,
+                                'message_pass': mp_flops / (stages['message_pass_T%d' % args.iters] * 1e-3) / 1e12},
+                'whole_step': {'algorithmic_bytes': alg_bytes_l1(N, E, H, D, args.iters),
+                               'achieved_gbs': alg_bytes_l1(N, E, H, D, args.iters) / (ms_step * 1e-3) / 1e9,
+                               'algorithmic_flops': alg_flops_l1(N, E, H, D, args.iters)}}
+
+    # ---- CPU baseline: the reference's CPU path (oracle port), bounded sample, rank 0 only at N=1
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        tms = cpu_reference_run(args, cases[:2], params, 5, 1, threads)
+        cpu = {'value': args.batch / float(np.median(tms)), 'unit': 'images/s', 'cores': threads, 'kind': 'port',
+               'sample': '5 steps (+1 warm-up) of the same workload, median; oracle/imp_torch_cpu.py'}
+
+    images = args.batch * world
+    line = {'metric': 'images/sec (PredCls, 3 MP iters)', 'value': images / (ms_step * 1e-3), 'unit': 'images/s',
+            'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_step,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': config, 'clocks': clocks,
+            'e2e': {'value': images * args.steps / e2e_s, 'unit': 'images/s', 'h2d_bytes_per_step': runner.h2d_bytes,
+                    'd2h_bytes_per_step': runner.d2h_bytes, 'ms_per_step': e2e_s * 1e3 / args.steps,
+                    'api': 'sgg_b200.runner.ImpL1Runner.submit/wait (3 in-flight slots, pinned host buffers)'},
+            'gpu_launches': int(launches_per_step) * args.steps,
+            'gpu_launches_per_step': int(launches_per_step),
+            'roofline': roofline, 'cpu_baseline': cpu}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == '__main__':
+    sys.exit(main())

@@ -1,0 +1,146 @@
+/* sgg_b200 — C-ABI of the B200-native IMP relation-model hot path.
+ *
+ * Drop-in boundary for the message-passing relation model of bknyaz/sgg
+ * (sgg_models/rel_model_stanford.py, lib/get_union_boxes.py,
+ * lib/draw_rectangles/draw_rectangles.pyx, sgg_models/rel_model_base.py).
+ * The reference is pure Python/PyTorch (+ one Cython op); the binding a
+ * maintainer adds is a ctypes stub or the mirror classes in
+ * sgg_b200/rel_model_stanford.py.
+ *
+ * Conventions (all entry points):
+ *  - plain C: pointers + sizes only, no torch / C++ types;
+ *  - every pointer is a DEVICE pointer to row-major contiguous memory owned by
+ *    the caller (torch), unless documented as "host";
+ *  - work is enqueued on `stream` (a cudaStream_t passed as void*); nothing
+ *    synchronises, nothing allocates — the caller passes workspaces sized by
+ *    the matching *_workspace_bytes function;
+ *  - return value: 0 = ok, otherwise a cudaError_t (or SGG_E_* below); the
+ *    text is available from sgg_last_error(); nothing throws;
+ *  - fp32 data, int64 indices at the boundary (what the reference holds),
+ *    int32 internally.
+ */
+#ifndef SGG_B200_H
+#define SGG_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define SGG_API __attribute__((visibility("default")))
+#else
+#define SGG_API
+#endif
+
+#define SGG_ABI_VERSION 1
+#define SGG_E_BADARG 10001   /* shape / alignment / null pointer          */
+#define SGG_E_WORKSPACE 10002 /* workspace too small                      */
+#define SGG_E_INDEX 10003    /* rel_inds out of [0, N) (reported by sgg_graph_check) */
+
+SGG_API int sgg_abi_version(void);
+SGG_API const char *sgg_last_error(void);
+/* sm count etc. of the current device: {sm_count, cc_major, cc_minor, l2_bytes} */
+SGG_API int sgg_device_info(int out[4]);
+/* number of kernels this library has launched in this process (bench.py gpu_launches) */
+SGG_API unsigned long long sgg_launch_count(void);
+
+/* ---- message-passing weights: rel_model_stanford.py:36-45 ------------------
+ * edge_gru / node_gru: nn.GRUCell(H, H): weight_ih, weight_hh [3H,H] (r,z,n),
+ * bias_ih, bias_hh [3H].  gate_w[k]: Linear(2H,1).weight [2H] = [vertex half |
+ * edge half]; gate_b[k]: [1].  k = 0 sub_vert_w_fc, 1 obj_vert_w_fc,
+ * 2 out_edge_w_fc, 3 in_edge_w_fc. */
+typedef struct {
+  const float *edge_w_ih, *edge_w_hh, *edge_b_ih, *edge_b_hh;
+  const float *node_w_ih, *node_w_hh, *node_b_ih, *node_b_hh;
+  const float *gate_w[4];
+  const float *gate_b[4];
+} sgg_mp_weights;
+
+/* ---- ragged graph index (replaces the dense [N,E] incidence matrices of
+ * rel_model_stanford.py:58-66) -----------------------------------------------
+ * rel_inds: int64 rows with stride `row_stride` elements; columns col_subj /
+ * col_obj hold GLOBAL object ids (rel_model_stanford.py:76-77).  Writes into
+ * graph_ws: subj32[E], obj32[E], CSR by subject (out_ptr[N+1], out_idx[E]) and
+ * by object (in_ptr[N+1], in_idx[E]); per-node lists are sorted by edge id so
+ * every reduction order is deterministic.  Edges need not be sorted; duplicate
+ * edges are kept (they add, as in the reference). */
+SGG_API size_t sgg_graph_workspace_bytes(int N, int E);
+SGG_API int sgg_graph_build(const int64_t *rel_inds, int64_t row_stride, int col_subj, int col_obj,
+                    int N, int E, void *graph_ws, size_t graph_ws_bytes, void *stream);
+/* host-synchronising validation helper (debug / tests): returns SGG_E_INDEX if any id
+ * was out of range during the last sgg_graph_build on this workspace. */
+SGG_API int sgg_graph_check(const void *graph_ws, int N, int E, void *stream);
+
+/* ---- a1-a3: RelModelStanford.message_pass (rel_model_stanford.py:48-94) -----
+ * obj_rep [N,H], rel_rep [E,H] -> V_out [N,H], E_out [E,H] after T iterations.
+ * saved (nullable): (T+1) * (N+E) * H floats, states V_0,E_0 ... V_T,E_T for backward.
+ * H must be a multiple of 64. */
+SGG_API size_t sgg_mp_workspace_bytes(int N, int E, int H, int T);
+SGG_API int sgg_mp_forward(const float *obj_rep, const float *rel_rep, const void *graph_ws,
+                   const sgg_mp_weights *w, int N, int E, int H, int T,
+                   float *V_out, float *E_out, float *saved,
+                   void *ws, size_t ws_bytes, void *stream);
+
+/* ---- a5/a6: nn.Linear (+ReLU): y[M,Nout] = act(x[M,K] @ w[Nout,K]^T + b) ----
+ * (obj_unary / edge_unary / obj_fc / rel_fc rel_model_stanford.py:29-33,
+ *  roi_fmap / roi_fmap_obj rel_model_base.py:110-111).  b nullable. K % 16 == 0. */
+SGG_API int sgg_linear_forward(const float *x, const float *w, const float *b, float *y,
+                       int M, int Nout, int K, int relu, void *stream);
+
+/* ---- L1: 4096-d features -> obj_dists / rel_dists (rel_model_stanford.py:103-107
+ * without roi_fmap*): obj_unary, relu(edge_unary), message_pass, obj_fc, rel_fc. */
+typedef struct {
+  const float *obj_unary_w, *obj_unary_b;   /* [H,D],[H] */
+  const float *edge_unary_w, *edge_unary_b; /* [H,D],[H] */
+  const float *obj_fc_w, *obj_fc_b;         /* [n_cls,H],[n_cls] */
+  const float *rel_fc_w, *rel_fc_b;         /* [n_rel,H],[n_rel] */
+} sgg_head_weights;
+SGG_API size_t sgg_l1_workspace_bytes(int N, int E, int H, int T);
+SGG_API int sgg_l1_forward(const float *obj_feat, const float *edge_feat, const void *graph_ws,
+                   const sgg_head_weights *hw, const sgg_mp_weights *w,
+                   int N, int E, int D, int H, int T, int n_cls, int n_rel,
+                   float *obj_dists, float *rel_dists,
+                   void *ws, size_t ws_bytes, void *stream);
+
+/* ---- a8: draw_union_boxes (lib/draw_rectangles/draw_rectangles.pyx:12-67) ----
+ * rois [N,5] (img,x1,y1,x2,y2) as in rel_model_base.py:147; union_inds int64
+ * rows (stride row_stride) cols (col_subj,col_obj); out [E,2,P,P] f32.
+ * `sub_half` != 0 subtracts 0.5 (lib/get_union_boxes.py:67). */
+SGG_API int sgg_draw_union_boxes(const float *rois, const int64_t *union_inds, int64_t row_stride,
+                         int col_subj, int col_obj, int E, int P, int sub_half,
+                         float *out, void *stream);
+
+/* ---- a7: UnionBoxesAndFeats geometry branch (lib/get_union_boxes.py:51-59,101)
+ * geom[E,C] = BN2(ReLU(conv3s16(maxpool(BN1(ReLU(conv7s16(rects))))))) computed
+ * straight from the boxes (the 27x27 masks never reach HBM); eval-mode BN
+ * (running statistics).  C = 512 output channels, C/2 hidden.
+ * If union_pools != NULL: out[E,C,7,7] = union_pools + geom (broadcast add, :101);
+ * else out = geom [E,C]. */
+typedef struct {
+  const float *conv1_w, *conv1_b;              /* [C/2,2,7,7],[C/2] */
+  const float *bn1_w, *bn1_b, *bn1_rm, *bn1_rv; /* [C/2] */
+  const float *conv2_w, *conv2_b;              /* [C,C/2,3,3],[C] */
+  const float *bn2_w, *bn2_b, *bn2_rm, *bn2_rv; /* [C] */
+} sgg_geom_weights;
+SGG_API size_t sgg_union_geom_workspace_bytes(int E, int C);
+SGG_API int sgg_union_geom_forward(const float *rois, const int64_t *union_inds, int64_t row_stride,
+                           int col_subj, int col_obj, int E, int C,
+                           const sgg_geom_weights *gw, const float *union_pools,
+                           float *out, void *ws, size_t ws_bytes, void *stream);
+
+/* ---- a9: node_edge_features (rel_model_base.py:245-260): torchvision
+ * roi_align(aligned=False, sampling_ratio=2, 7x7, scale 1/16) for objects and
+ * for union boxes computed on the fly from (rois, union_inds).
+ * fmap [B,C,Hf,Wf]; node_feat [N,C,7,7]; edge_feat [E,C,7,7] (either may be NULL). */
+SGG_API int sgg_node_edge_features(const float *fmap, int B, int C, int Hf, int Wf,
+                           const float *rois, int N,
+                           const int64_t *union_inds, int64_t row_stride, int col_subj, int col_obj, int E,
+                           float spatial_scale, int pool, int sampling_ratio,
+                           float *node_feat, float *edge_feat, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SGG_B200_H */

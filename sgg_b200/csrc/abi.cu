@@ -1,0 +1,40 @@
+// Error reporting / device info for the C-ABI.
+#include "common.cuh"
+#include <stdarg.h>
+#include <stdio.h>
+
+#include <atomic>
+static thread_local char g_err[512] = "";
+static std::atomic<unsigned long long> g_launches{0};
+void sgg_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+extern "C" unsigned long long sgg_launch_count(void) { return g_launches.load(); }
+
+int sgg_set_err(int code, const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int sgg_num_sms() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+extern "C" int sgg_abi_version(void) { return SGG_ABI_VERSION; }
+extern "C" const char *sgg_last_error(void) { return g_err; }
+extern "C" int sgg_device_info(int out[4]) {
+  int dev = 0;
+  SGG_CUDA_TRY(cudaGetDevice(&dev));
+  SGG_CUDA_TRY(cudaDeviceGetAttribute(&out[0], cudaDevAttrMultiProcessorCount, dev));
+  SGG_CUDA_TRY(cudaDeviceGetAttribute(&out[1], cudaDevAttrComputeCapabilityMajor, dev));
+  SGG_CUDA_TRY(cudaDeviceGetAttribute(&out[2], cudaDevAttrComputeCapabilityMinor, dev));
+  SGG_CUDA_TRY(cudaDeviceGetAttribute(&out[3], cudaDevAttrL2CacheSize, dev));
+  return 0;
+}

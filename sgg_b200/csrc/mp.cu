@@ -1,0 +1,423 @@
+// Iterative message passing (IMP) forward — RelModelStanford.message_pass,
+// sgg_models/rel_model_stanford.py:48-94 — on ragged CSR graphs.
+//
+// Algebra (exact up to fp32 reassociation):
+//   x_e = g_s * V[s] + g_o * V[o]           (:78-81)
+//   W_ih x_e = g_s * (W_ih V[s]) + g_o * (W_ih V[o])   ("linearity shortcut")
+//   w . [v ; e] = w_v . v + w_e . e                    (gate logits split per half)
+// so per iteration the E-row input-side GEMM of the edge GRU collapses into one
+// N-row GEMM  P = V W_ih_e^T  whose rows are gathered (and scaled by the scalar
+// gates) in the epilogue of the E-row hidden-side GEMM  R = Eh W_hh_e^T.
+//
+// Per iteration i (all reads are iteration-i states, Jacobi, :74-92):
+//   k_gate_node   a[n,4]   = V[n] . w_k[:H]                       warp-shuffle dots
+//   k_gate_edge   g[e,4]   = sigmoid(a[s|o,k] + Eh[e] . w_k[H:] + b_k)
+//   linear        P[N,3H]  = V W_ih_e^T
+//   k_ctx         ctx[n]   = sum_out g_out[e] Eh[e] + sum_in g_in[e] Eh[e]   (CSR, fixed order)
+//   k_gru<EDGE>   Eh'      = GRU(gi = g_s P[s] + g_o P[o] + b_ih, gh = Eh W_hh_e^T + b_hh, h = Eh)
+//   k_gru<NODE>   V'       = GRU(gi = ctx W_ih_n^T + b_ih, gh = V W_hh_n^T + b_hh, h = V)
+// The GRU non-linearity runs in the GEMM epilogue: a tile covers hidden units
+// [j0, j0+64) of all three gates (weight rows j0, H+j0, 2H+j0).
+#include "gemm_core.cuh"
+#include "kernels.h"
+
+namespace sgg {
+
+enum { GRU_INIT = 0, GRU_NODE = 1, GRU_EDGE = 2 };
+
+struct GruArgs {
+  // GEMM operands
+  const float *x;      // INIT: input rows [M,H]; NODE: ctx [M,H]; EDGE: unused
+  const float *h;      // NODE/EDGE: previous state [M,H]; INIT: null (h = 0)
+  const float *w_ih, *w_hh, *b_ih, *b_hh;
+  // EDGE only
+  const float *P;      // [N,3H] = V W_ih^T
+  const float *gates;  // [M,4]  (g_sub, g_obj, g_out, g_in)
+  const int *subj, *obj;
+  float *out;          // [M,H]
+  int M, H;
+};
+
+template <int BM, int MODE>
+__global__ void __launch_bounds__(NTHREADS, (BM == 64 ? 2 : 1))
+k_gru(GruArgs p) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int TM = BM / 16;
+  constexpr int NACC = (MODE == GRU_NODE) ? 4 : 3;   // r, z, n_i [, n_h]
+  const int H = p.H;
+  const int m0 = blockIdx.y * BM;
+  const int j0 = blockIdx.x * BN;
+  float acc[TM][NACC][4];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int b = 0; b < NACC; ++b)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[i][b][c] = 0.f;
+
+  WBlocks<3> Wb;
+  Wb.ldw = H;
+#pragma unroll
+  for (int g = 0; g < 3; ++g) { Wb.rowbase[g] = g * H + j0; Wb.nvalid[g] = BN; }
+
+  if (MODE == GRU_INIT || MODE == GRU_NODE) {
+    ARows A{p.x, H, p.M, m0};
+    Wb.W = p.w_ih;
+    gemm_segment<BM, NACC, 3, AccMap<0, 1, 2>>(acc, A, Wb, H, smem);
+  }
+  if (MODE == GRU_NODE) {
+    ARows A{p.h, H, p.M, m0};
+    Wb.W = p.w_hh;
+    gemm_segment<BM, NACC, 3, AccMap<0, 1, 3>>(acc, A, Wb, H, smem);
+  }
+  if (MODE == GRU_EDGE) {
+    ARows A{p.h, H, p.M, m0};
+    Wb.W = p.w_hh;
+    gemm_segment<BM, NACC, 3, AccMap<0, 1, 2>>(acc, A, Wb, H, smem);
+  }
+
+  // ---- epilogue: GRUCell pointwise (torch.nn.GRUCell semantics) ----
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int j = j0 + tx * 4;
+  const float4 bir = __ldg(reinterpret_cast<const float4 *>(p.b_ih + j));
+  const float4 biz = __ldg(reinterpret_cast<const float4 *>(p.b_ih + H + j));
+  const float4 bin = __ldg(reinterpret_cast<const float4 *>(p.b_ih + 2 * H + j));
+  const float4 bhr = __ldg(reinterpret_cast<const float4 *>(p.b_hh + j));
+  const float4 bhz = __ldg(reinterpret_cast<const float4 *>(p.b_hh + H + j));
+  const float4 bhn = __ldg(reinterpret_cast<const float4 *>(p.b_hh + 2 * H + j));
+  const float bi_r[4] = {bir.x, bir.y, bir.z, bir.w}, bi_z[4] = {biz.x, biz.y, biz.z, biz.w},
+              bi_n[4] = {bin.x, bin.y, bin.z, bin.w};
+  const float bh_r[4] = {bhr.x, bhr.y, bhr.z, bhr.w}, bh_z[4] = {bhz.x, bhz.y, bhz.z, bhz.w},
+              bh_n[4] = {bhn.x, bhn.y, bhn.z, bhn.w};
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    const int m = m0 + ty * TM + i;
+    if (m >= p.M) continue;
+    float hv[4] = {0.f, 0.f, 0.f, 0.f};
+    if (MODE != GRU_INIT) {
+      float4 t = *reinterpret_cast<const float4 *>(p.h + (size_t)m * H + j);
+      hv[0] = t.x; hv[1] = t.y; hv[2] = t.z; hv[3] = t.w;
+    }
+    float gi_r[4], gi_z[4], gi_n[4], gh_r[4], gh_z[4], gh_n[4];
+    if (MODE == GRU_EDGE) {
+      const int s = p.subj[m], o = p.obj[m];
+      const float4 g4 = *reinterpret_cast<const float4 *>(p.gates + (size_t)m * 4);
+      const float gs = g4.x, go = g4.y;
+      const float *ps = p.P + (size_t)s * 3 * H + j, *po = p.P + (size_t)o * 3 * H + j;
+      const float4 sr = *reinterpret_cast<const float4 *>(ps), orr = *reinterpret_cast<const float4 *>(po);
+      const float4 sz = *reinterpret_cast<const float4 *>(ps + H), oz = *reinterpret_cast<const float4 *>(po + H);
+      const float4 sn = *reinterpret_cast<const float4 *>(ps + 2 * H), on = *reinterpret_cast<const float4 *>(po + 2 * H);
+      const float a_sr[4] = {sr.x, sr.y, sr.z, sr.w}, a_or[4] = {orr.x, orr.y, orr.z, orr.w};
+      const float a_sz[4] = {sz.x, sz.y, sz.z, sz.w}, a_oz[4] = {oz.x, oz.y, oz.z, oz.w};
+      const float a_sn[4] = {sn.x, sn.y, sn.z, sn.w}, a_on[4] = {on.x, on.y, on.z, on.w};
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        gi_r[c] = fmaf(gs, a_sr[c], go * a_or[c]) + bi_r[c];
+        gi_z[c] = fmaf(gs, a_sz[c], go * a_oz[c]) + bi_z[c];
+        gi_n[c] = fmaf(gs, a_sn[c], go * a_on[c]) + bi_n[c];
+        gh_r[c] = acc[i][0][c] + bh_r[c];
+        gh_z[c] = acc[i][1][c] + bh_z[c];
+        gh_n[c] = acc[i][2][c] + bh_n[c];
+      }
+    } else if (MODE == GRU_NODE) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {   // acc0/acc1 already hold gi+gh for r and z
+        gi_r[c] = acc[i][0][c] + bi_r[c]; gh_r[c] = bh_r[c];
+        gi_z[c] = acc[i][1][c] + bi_z[c]; gh_z[c] = bh_z[c];
+        gi_n[c] = acc[i][2][c] + bi_n[c];
+        gh_n[c] = acc[i][NACC - 1][c] + bh_n[c];
+      }
+    } else {  // INIT: h = 0 => gh = b_hh
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        gi_r[c] = acc[i][0][c] + bi_r[c]; gh_r[c] = bh_r[c];
+        gi_z[c] = acc[i][1][c] + bi_z[c]; gh_z[c] = bh_z[c];
+        gi_n[c] = acc[i][2][c] + bi_n[c]; gh_n[c] = bh_n[c];
+      }
+    }
+    float o4[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float r = sgg_sigmoid(gi_r[c] + gh_r[c]);
+      const float z = sgg_sigmoid(gi_z[c] + gh_z[c]);
+      const float n = tanhf(gi_n[c] + r * gh_n[c]);
+      o4[c] = (1.0f - z) * n + z * hv[c];
+    }
+    *reinterpret_cast<float4 *>(p.out + (size_t)m * H + j) = make_float4(o4[0], o4[1], o4[2], o4[3]);
+  }
+}
+
+// a[n,k] = V[n] . gate_w[k][:H]   — one warp per node, warp-shuffle reduction.
+__global__ void k_gate_node(const float *__restrict__ V, int N, int H, const float *w0, const float *w1,
+                            const float *w2, const float *w3, float *__restrict__ a) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= N) return;
+  const float *row = V + (size_t)warp * H;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  for (int k = lane * 4; k < H; k += 128) {
+    const float4 v = *reinterpret_cast<const float4 *>(row + k);
+    const float4 a0 = __ldg(reinterpret_cast<const float4 *>(w0 + k));
+    const float4 a1 = __ldg(reinterpret_cast<const float4 *>(w1 + k));
+    const float4 a2 = __ldg(reinterpret_cast<const float4 *>(w2 + k));
+    const float4 a3 = __ldg(reinterpret_cast<const float4 *>(w3 + k));
+    s0 += v.x * a0.x + v.y * a0.y + v.z * a0.z + v.w * a0.w;
+    s1 += v.x * a1.x + v.y * a1.y + v.z * a1.z + v.w * a1.w;
+    s2 += v.x * a2.x + v.y * a2.y + v.z * a2.z + v.w * a2.w;
+    s3 += v.x * a3.x + v.y * a3.y + v.z * a3.z + v.w * a3.w;
+  }
+  s0 = sgg_warp_sum(s0); s1 = sgg_warp_sum(s1); s2 = sgg_warp_sum(s2); s3 = sgg_warp_sum(s3);
+  if (lane == 0) *reinterpret_cast<float4 *>(a + (size_t)warp * 4) = make_float4(s0, s1, s2, s3);
+}
+
+// g[e,k] = sigmoid(a[s or o, k] + Eh[e] . gate_w[k][H:] + b[k])   (rel_model_stanford.py:78-81,86-89)
+__global__ void k_gate_edge(const float *__restrict__ Eh, int E, int H, const float *w0, const float *w1,
+                            const float *w2, const float *w3, const float *b0, const float *b1, const float *b2,
+                            const float *b3, const float *__restrict__ a, const int *__restrict__ subj,
+                            const int *__restrict__ obj, float *__restrict__ g) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= E) return;
+  const float *row = Eh + (size_t)warp * H;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  for (int k = lane * 4; k < H; k += 128) {
+    const float4 v = *reinterpret_cast<const float4 *>(row + k);
+    const float4 a0 = __ldg(reinterpret_cast<const float4 *>(w0 + H + k));
+    const float4 a1 = __ldg(reinterpret_cast<const float4 *>(w1 + H + k));
+    const float4 a2 = __ldg(reinterpret_cast<const float4 *>(w2 + H + k));
+    const float4 a3 = __ldg(reinterpret_cast<const float4 *>(w3 + H + k));
+    s0 += v.x * a0.x + v.y * a0.y + v.z * a0.z + v.w * a0.w;
+    s1 += v.x * a1.x + v.y * a1.y + v.z * a1.z + v.w * a1.w;
+    s2 += v.x * a2.x + v.y * a2.y + v.z * a2.z + v.w * a2.w;
+    s3 += v.x * a3.x + v.y * a3.y + v.z * a3.z + v.w * a3.w;
+  }
+  s0 = sgg_warp_sum(s0); s1 = sgg_warp_sum(s1); s2 = sgg_warp_sum(s2); s3 = sgg_warp_sum(s3);
+  if (lane == 0) {
+    const int s = subj[warp], o = obj[warp];
+    const float4 as = *reinterpret_cast<const float4 *>(a + (size_t)s * 4);
+    const float4 ao = *reinterpret_cast<const float4 *>(a + (size_t)o * 4);
+    float4 r;
+    r.x = sgg_sigmoid(as.x + s0 + __ldg(b0));   // sub_vert: subject vertex
+    r.y = sgg_sigmoid(ao.y + s1 + __ldg(b1));   // obj_vert: object vertex
+    r.z = sgg_sigmoid(as.z + s2 + __ldg(b2));   // out_edge: uses the subject vertex (:86)
+    r.w = sgg_sigmoid(ao.w + s3 + __ldg(b3));   // in_edge:  uses the object vertex  (:88)
+    *reinterpret_cast<float4 *>(g + (size_t)warp * 4) = r;
+  }
+}
+
+// ctx[n] = sum_{e in out(n)} g_out[e] Eh[e] + sum_{e in in(n)} g_in[e] Eh[e]   (:86-91)
+// One CTA per node, one float4 column group per thread; CSR lists are in ascending edge id.
+__global__ void k_ctx(const float *__restrict__ Eh, const float *__restrict__ g, const int *__restrict__ out_ptr,
+                      const int *__restrict__ out_idx, const int *__restrict__ in_ptr, const int *__restrict__ in_idx,
+                      int H, float *__restrict__ ctx) {
+  const int n = blockIdx.x;
+  for (int j = threadIdx.x * 4; j < H; j += blockDim.x * 4) {
+    float4 so = make_float4(0.f, 0.f, 0.f, 0.f), si = so;
+    int b = out_ptr[n], e = out_ptr[n + 1];
+    int k = b;
+    for (; k + 4 <= e; k += 4) {
+      int e0 = out_idx[k], e1 = out_idx[k + 1], e2 = out_idx[k + 2], e3 = out_idx[k + 3];
+      float g0 = g[(size_t)e0 * 4 + 2], g1 = g[(size_t)e1 * 4 + 2], g2 = g[(size_t)e2 * 4 + 2], g3 = g[(size_t)e3 * 4 + 2];
+      float4 v0 = *reinterpret_cast<const float4 *>(Eh + (size_t)e0 * H + j);
+      float4 v1 = *reinterpret_cast<const float4 *>(Eh + (size_t)e1 * H + j);
+      float4 v2 = *reinterpret_cast<const float4 *>(Eh + (size_t)e2 * H + j);
+      float4 v3 = *reinterpret_cast<const float4 *>(Eh + (size_t)e3 * H + j);
+      so.x += g0 * v0.x; so.y += g0 * v0.y; so.z += g0 * v0.z; so.w += g0 * v0.w;
+      so.x += g1 * v1.x; so.y += g1 * v1.y; so.z += g1 * v1.z; so.w += g1 * v1.w;
+      so.x += g2 * v2.x; so.y += g2 * v2.y; so.z += g2 * v2.z; so.w += g2 * v2.w;
+      so.x += g3 * v3.x; so.y += g3 * v3.y; so.z += g3 * v3.z; so.w += g3 * v3.w;
+    }
+    for (; k < e; ++k) {
+      int e0 = out_idx[k];
+      float g0 = g[(size_t)e0 * 4 + 2];
+      float4 v0 = *reinterpret_cast<const float4 *>(Eh + (size_t)e0 * H + j);
+      so.x += g0 * v0.x; so.y += g0 * v0.y; so.z += g0 * v0.z; so.w += g0 * v0.w;
+    }
+    b = in_ptr[n]; e = in_ptr[n + 1];
+    k = b;
+    for (; k + 4 <= e; k += 4) {
+      int e0 = in_idx[k], e1 = in_idx[k + 1], e2 = in_idx[k + 2], e3 = in_idx[k + 3];
+      float g0 = g[(size_t)e0 * 4 + 3], g1 = g[(size_t)e1 * 4 + 3], g2 = g[(size_t)e2 * 4 + 3], g3 = g[(size_t)e3 * 4 + 3];
+      float4 v0 = *reinterpret_cast<const float4 *>(Eh + (size_t)e0 * H + j);
+      float4 v1 = *reinterpret_cast<const float4 *>(Eh + (size_t)e1 * H + j);
+      float4 v2 = *reinterpret_cast<const float4 *>(Eh + (size_t)e2 * H + j);
+      float4 v3 = *reinterpret_cast<const float4 *>(Eh + (size_t)e3 * H + j);
+      si.x += g0 * v0.x; si.y += g0 * v0.y; si.z += g0 * v0.z; si.w += g0 * v0.w;
+      si.x += g1 * v1.x; si.y += g1 * v1.y; si.z += g1 * v1.z; si.w += g1 * v1.w;
+      si.x += g2 * v2.x; si.y += g2 * v2.y; si.z += g2 * v2.z; si.w += g2 * v2.w;
+      si.x += g3 * v3.x; si.y += g3 * v3.y; si.z += g3 * v3.z; si.w += g3 * v3.w;
+    }
+    for (; k < e; ++k) {
+      int e0 = in_idx[k];
+      float g0 = g[(size_t)e0 * 4 + 3];
+      float4 v0 = *reinterpret_cast<const float4 *>(Eh + (size_t)e0 * H + j);
+      si.x += g0 * v0.x; si.y += g0 * v0.y; si.z += g0 * v0.z; si.w += g0 * v0.w;
+    }
+    *reinterpret_cast<float4 *>(ctx + (size_t)n * H + j) = make_float4(so.x + si.x, so.y + si.y, so.z + si.z, so.w + si.w);
+  }
+}
+
+template <int BM, int MODE>
+static int launch_gru_t(const GruArgs &a, cudaStream_t st) {
+  static bool attr_done = false;
+  const size_t smem = TileSmem<BM, 3>::bytes;
+  if (!attr_done) {
+    SGG_CUDA_TRY(cudaFuncSetAttribute(k_gru<BM, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
+  }
+  dim3 grid(a.H / BN, (a.M + BM - 1) / BM);
+  k_gru<BM, MODE><<<grid, NTHREADS, smem, st>>>(a);
+  SGG_RETURN_IF_LAUNCH_FAILED("k_gru");
+  return 0;
+}
+
+template <int MODE>
+static int launch_gru(const GruArgs &a, cudaStream_t st) {
+  if (a.M <= 0) return 0;
+  const int sms = sgg_num_sms();
+  const long t128 = (long)(a.H / BN) * ((a.M + 127) / 128), t64 = (long)(a.H / BN) * ((a.M + 63) / 64);
+  const double c128 = (double)((t128 + sms - 1) / sms) * 2.0;
+  const double c64 = (double)((t64 + 2L * sms - 1) / (2L * sms)) * 2.0 * 1.08;   // 2 CTAs/SM, slightly less efficient
+  if (c64 < c128) return launch_gru_t<64, MODE>(a, st);
+  return launch_gru_t<128, MODE>(a, st);
+}
+
+struct MpScratch {
+  float *V[2], *Eh[2], *P, *a, *g, *ctx;
+};
+
+static size_t mp_layout(MpScratch *s, void *ws, int N, int E, int H) {
+  SggArena ar(ws, (size_t)-1);
+  const size_t n1 = N > 0 ? N : 1, e1 = E > 0 ? E : 1;
+  for (int i = 0; i < 2; ++i) { s->V[i] = ar.take<float>(n1 * H); s->Eh[i] = ar.take<float>(e1 * H); }
+  s->P = ar.take<float>(n1 * 3 * H);
+  s->a = ar.take<float>(n1 * 4);
+  s->g = ar.take<float>(e1 * 4);
+  s->ctx = ar.take<float>(n1 * H);
+  return ar.off;
+}
+
+int mp_forward(const float *obj_rep, const float *rel_rep, const void *graph_ws, const sgg_mp_weights *w, int N,
+               int E, int H, int T, float *V_out, float *E_out, float *saved, void *ws, size_t ws_bytes,
+               cudaStream_t st) {
+  if (N < 0 || E < 0 || T < 0 || H <= 0 || (H % BN) != 0)
+    return sgg_set_err(SGG_E_BADARG, "mp_forward: N=%d E=%d H=%d T=%d (H must be a multiple of %d)", N, E, H, T, BN);
+  if (!w || !graph_ws || (N > 0 && (!obj_rep || !V_out)) || (E > 0 && (!rel_rep || !E_out)))
+    return sgg_set_err(SGG_E_BADARG, "mp_forward: null pointer");
+  MpScratch s;
+  const size_t need = mp_layout(&s, ws, N, E, H);
+  if (need > ws_bytes || !ws) return sgg_set_err(SGG_E_WORKSPACE, "mp_forward: workspace %zu < %zu", ws_bytes, need);
+  SggGraphView g = sgg_graph_view(graph_ws, N, E);
+  const size_t vN = (size_t)N * H, eN = (size_t)E * H;
+  // State buffers: with `saved` every iteration writes into its own slot (no ping-pong copy);
+  // otherwise ping-pong in the workspace and write the last iteration straight to the outputs.
+  auto vbuf = [&](int it) -> float * {
+    if (saved) return saved + (size_t)it * (vN + eN);
+    return it == T ? V_out : s.V[it & 1];
+  };
+  auto ebuf = [&](int it) -> float * {
+    if (saved) return saved + (size_t)it * (vN + eN) + vN;
+    return it == T ? E_out : s.Eh[it & 1];
+  };
+  int rc;
+  {  // hx = 0 initial step (:68-72)
+    GruArgs a{}; a.x = obj_rep; a.h = nullptr; a.w_ih = w->node_w_ih; a.w_hh = w->node_w_hh; a.b_ih = w->node_b_ih;
+    a.b_hh = w->node_b_hh; a.out = vbuf(0); a.M = N; a.H = H;
+    if ((rc = launch_gru<GRU_INIT>(a, st))) return rc;
+    GruArgs b{}; b.x = rel_rep; b.h = nullptr; b.w_ih = w->edge_w_ih; b.w_hh = w->edge_w_hh; b.b_ih = w->edge_b_ih;
+    b.b_hh = w->edge_b_hh; b.out = ebuf(0); b.M = E; b.H = H;
+    if ((rc = launch_gru<GRU_INIT>(b, st))) return rc;
+  }
+  for (int it = 0; it < T; ++it) {
+    const float *V = vbuf(it), *Eh = ebuf(it);
+    if (N > 0) {
+      k_gate_node<<<(N * 32 + 255) / 256, 256, 0, st>>>(V, N, H, w->gate_w[0], w->gate_w[1], w->gate_w[2],
+                                                        w->gate_w[3], s.a);
+      SGG_RETURN_IF_LAUNCH_FAILED("k_gate_node");
+    }
+    if (E > 0) {
+      k_gate_edge<<<(int)(((size_t)E * 32 + 255) / 256), 256, 0, st>>>(
+          Eh, E, H, w->gate_w[0], w->gate_w[1], w->gate_w[2], w->gate_w[3], w->gate_b[0], w->gate_b[1], w->gate_b[2],
+          w->gate_b[3], s.a, g.subj, g.obj, s.g);
+      SGG_RETURN_IF_LAUNCH_FAILED("k_gate_edge");
+      if ((rc = launch_linear(V, w->edge_w_ih, nullptr, s.P, N, 3 * H, H, 0, st))) return rc;
+    }
+    if (N > 0) {
+      k_ctx<<<N, (H / 4 < 128 ? H / 4 : 128), 0, st>>>(Eh, s.g, g.out_ptr, g.out_idx, g.in_ptr, g.in_idx, H, s.ctx);
+      SGG_RETURN_IF_LAUNCH_FAILED("k_ctx");
+    }
+    {
+      GruArgs a{}; a.h = Eh; a.w_ih = w->edge_w_ih; a.w_hh = w->edge_w_hh; a.b_ih = w->edge_b_ih;
+      a.b_hh = w->edge_b_hh; a.P = s.P; a.gates = s.g; a.subj = g.subj; a.obj = g.obj; a.out = ebuf(it + 1);
+      a.M = E; a.H = H;
+      if ((rc = launch_gru<GRU_EDGE>(a, st))) return rc;
+    }
+    {
+      GruArgs a{}; a.x = s.ctx; a.h = V; a.w_ih = w->node_w_ih; a.w_hh = w->node_w_hh; a.b_ih = w->node_b_ih;
+      a.b_hh = w->node_b_hh; a.out = vbuf(it + 1); a.M = N; a.H = H;
+      if ((rc = launch_gru<GRU_NODE>(a, st))) return rc;
+    }
+  }
+  if (saved) {   // outputs are the last saved slot
+    if (N > 0) SGG_CUDA_TRY(cudaMemcpyAsync(V_out, vbuf(T), vN * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (E > 0) SGG_CUDA_TRY(cudaMemcpyAsync(E_out, ebuf(T), eN * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  }
+  return 0;
+}
+
+size_t mp_workspace_bytes(int N, int E, int H) {
+  MpScratch s;
+  return mp_layout(&s, nullptr, N, E, H);
+}
+
+}  // namespace sgg
+
+extern "C" size_t sgg_mp_workspace_bytes(int N, int E, int H, int T) {
+  (void)T;
+  return sgg::mp_workspace_bytes(N < 0 ? 0 : N, E < 0 ? 0 : E, H);
+}
+
+extern "C" int sgg_mp_forward(const float *obj_rep, const float *rel_rep, const void *graph_ws,
+                              const sgg_mp_weights *w, int N, int E, int H, int T, float *V_out, float *E_out,
+                              float *saved, void *ws, size_t ws_bytes, void *stream) {
+  return sgg::mp_forward(obj_rep, rel_rep, graph_ws, w, N, E, H, T, V_out, E_out, saved, ws, ws_bytes,
+                         (cudaStream_t)stream);
+}
+
+// ---- L1: 4096-d features -> dists (rel_model_stanford.py:103-107 without roi_fmap*) ----
+namespace sgg {
+struct L1Scratch { float *obj_rep, *rel_rep, *V, *Eh; void *mp; size_t mp_bytes; };
+static size_t l1_layout(L1Scratch *s, void *ws, int N, int E, int H) {
+  SggArena ar(ws, (size_t)-1);
+  const size_t n1 = N > 0 ? N : 1, e1 = E > 0 ? E : 1;
+  s->obj_rep = ar.take<float>(n1 * H); s->rel_rep = ar.take<float>(e1 * H);
+  s->V = ar.take<float>(n1 * H); s->Eh = ar.take<float>(e1 * H);
+  s->mp_bytes = mp_workspace_bytes(N, E, H);
+  s->mp = ar.take<char>(s->mp_bytes);
+  return ar.off;
+}
+}  // namespace sgg
+
+extern "C" size_t sgg_l1_workspace_bytes(int N, int E, int H, int T) {
+  (void)T;
+  sgg::L1Scratch s;
+  return sgg::l1_layout(&s, nullptr, N < 0 ? 0 : N, E < 0 ? 0 : E, H);
+}
+
+extern "C" int sgg_l1_forward(const float *obj_feat, const float *edge_feat, const void *graph_ws,
+                              const sgg_head_weights *hw, const sgg_mp_weights *w, int N, int E, int D, int H, int T,
+                              int n_cls, int n_rel, float *obj_dists, float *rel_dists, void *ws, size_t ws_bytes,
+                              void *stream) {
+  if (!hw || !w || !ws) return sgg_set_err(SGG_E_BADARG, "l1_forward: null pointer");
+  if (N < 0 || E < 0 || H <= 0 || (H % sgg::BN) != 0) return sgg_set_err(SGG_E_BADARG, "l1_forward: bad shape");
+  sgg::L1Scratch s;
+  const size_t need = sgg::l1_layout(&s, ws, N, E, H);
+  if (need > ws_bytes) return sgg_set_err(SGG_E_WORKSPACE, "l1_forward: workspace %zu < %zu", ws_bytes, need);
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc;
+  if ((rc = sgg::launch_linear(obj_feat, hw->obj_unary_w, hw->obj_unary_b, s.obj_rep, N, H, D, 0, st))) return rc;
+  if ((rc = sgg::launch_linear(edge_feat, hw->edge_unary_w, hw->edge_unary_b, s.rel_rep, E, H, D, 1, st))) return rc;
+  if ((rc = sgg::mp_forward(s.obj_rep, s.rel_rep, graph_ws, w, N, E, H, T, s.V, s.Eh, nullptr, s.mp, s.mp_bytes, st)))
+    return rc;
+  if ((rc = sgg::launch_linear(s.V, hw->obj_fc_w, hw->obj_fc_b, obj_dists, N, n_cls, H, 0, st))) return rc;
+  if ((rc = sgg::launch_linear(s.Eh, hw->rel_fc_w, hw->rel_fc_b, rel_dists, E, n_rel, H, 0, st))) return rc;
+  return 0;
+}

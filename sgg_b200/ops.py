@@ -1,0 +1,234 @@
+"""Tensor-level entry points over the C-ABI (include/sgg_b200.h).
+
+torch is plumbing here: it owns device memory and the current stream; every op
+below validates its tensors, hands raw device pointers to ``libsgg_b200.so`` and
+returns fresh torch tensors.  There is no CPU path — CPU tensors raise.
+"""
+import ctypes as C
+import torch
+
+from . import _lib
+from ._lib import MpWeights, HeadWeights, GeomWeights, check
+
+MP_KEYS = ('edge_gru.weight_ih', 'edge_gru.weight_hh', 'edge_gru.bias_ih', 'edge_gru.bias_hh',
+           'node_gru.weight_ih', 'node_gru.weight_hh', 'node_gru.bias_ih', 'node_gru.bias_hh')
+GATE_KEYS = ('sub_vert_w_fc', 'obj_vert_w_fc', 'out_edge_w_fc', 'in_edge_w_fc')
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _f32(t, name, shape=None):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise _lib.SggError('%s must be a CUDA tensor (sgg_b200 has no CPU path)' % name)
+    if t.dtype != torch.float32:
+        raise _lib.SggError('%s must be float32, got %s' % (name, t.dtype))
+    t = t.detach()
+    if not t.is_contiguous():
+        t = t.contiguous()
+    if shape is not None and tuple(t.shape) != tuple(shape):
+        raise _lib.SggError('%s has shape %s, expected %s' % (name, tuple(t.shape), tuple(shape)))
+    return t
+
+
+def _i64_rows(t, name):
+    """int64 index matrix, possibly a column-slice view of a wider row-major matrix."""
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise _lib.SggError('%s must be a CUDA tensor' % name)
+    if t.dtype != torch.int64 or t.dim() != 2:
+        raise _lib.SggError('%s must be a 2-d int64 tensor' % name)
+    if t.shape[0] > 1 and (t.stride(1) != 1):
+        t = t.contiguous()
+    if t.shape[0] <= 1:
+        t = t.contiguous()
+    return t, (t.stride(0) if t.shape[0] > 1 else t.shape[1])
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+class Graph(object):
+    """Device-side ragged index of the candidate-edge graph (int32 endpoints + two CSRs)."""
+
+    def __init__(self, ws, N, E):
+        self.ws, self.N, self.E = ws, N, E
+
+    def check(self):
+        check(_lib.load().sgg_graph_check(_ptr(self.ws), self.N, self.E, _stream()), 'sgg_graph_check')
+        return self
+
+
+def build_graph(rel_inds, N, col_subj=0, col_obj=1, validate=False):
+    """rel_inds: int64 [E, >=2] with GLOBAL object ids in columns (col_subj, col_obj)
+    (the ``rel_inds[:, 1:3]`` the reference passes to message_pass, rel_model_stanford.py:105)."""
+    lib = _lib.load()
+    rel, stride = _i64_rows(rel_inds, 'rel_inds')
+    E = rel.shape[0]
+    nbytes = lib.sgg_graph_workspace_bytes(N, E)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=rel.device)
+    check(lib.sgg_graph_build(_ptr(rel), stride, col_subj, col_obj, N, E, _ptr(ws), nbytes, _stream()),
+          'sgg_graph_build')
+    g = Graph(ws, N, E)
+    if validate:
+        g.check()
+    return g
+
+
+def mp_weights(params, device=None):
+    """params: mapping state-dict key -> tensor (reference names).
+    Returns (struct, keepalive list)."""
+    w = MpWeights()
+    keep = []
+    for field, key in zip(('edge_w_ih', 'edge_w_hh', 'edge_b_ih', 'edge_b_hh',
+                           'node_w_ih', 'node_w_hh', 'node_b_ih', 'node_b_hh'), MP_KEYS):
+        t = _f32(params[key], key); keep.append(t)
+        setattr(w, field, t.data_ptr())
+    H = keep[0].shape[1]
+    for i, k in enumerate(GATE_KEYS):
+        tw = _f32(params[k + '.0.weight'], k + '.0.weight', (1, 2 * H)); tb = _f32(params[k + '.0.bias'], k + '.0.bias', (1,))
+        keep += [tw, tb]
+        w.gate_w[i] = tw.data_ptr(); w.gate_b[i] = tb.data_ptr()
+    return w, keep, H
+
+
+def head_weights(params):
+    hw = HeadWeights()
+    keep = []
+    for field, key in (('obj_unary_w', 'obj_unary.weight'), ('obj_unary_b', 'obj_unary.bias'),
+                       ('edge_unary_w', 'edge_unary.weight'), ('edge_unary_b', 'edge_unary.bias'),
+                       ('obj_fc_w', 'obj_fc.weight'), ('obj_fc_b', 'obj_fc.bias'),
+                       ('rel_fc_w', 'rel_fc.weight'), ('rel_fc_b', 'rel_fc.bias')):
+        t = _f32(params[key], key); keep.append(t)
+        setattr(hw, field, t.data_ptr())
+    return hw, keep
+
+
+def message_pass(rel_rep, obj_rep, graph, params, mp_iter=3, save_states=False):
+    """RelModelStanford.message_pass (rel_model_stanford.py:48-94).  Argument order follows the
+    reference (rel_rep first).  Returns (V_T [N,H], E_T [E,H]) (+ saved states if requested)."""
+    lib = _lib.load()
+    w, keep, H = mp_weights(params)
+    N, E = graph.N, graph.E
+    obj_rep = _f32(obj_rep, 'obj_rep', (N, H)); rel_rep = _f32(rel_rep, 'rel_rep', (E, H))
+    dev = obj_rep.device
+    V = torch.empty((N, H), dtype=torch.float32, device=dev)
+    Eo = torch.empty((E, H), dtype=torch.float32, device=dev)
+    saved = torch.empty(((mp_iter + 1) * (N + E) * H,), dtype=torch.float32, device=dev) if save_states else None
+    nbytes = lib.sgg_mp_workspace_bytes(N, E, H, mp_iter)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    check(lib.sgg_mp_forward(_ptr(obj_rep), _ptr(rel_rep), _ptr(graph.ws), C.byref(w), N, E, H, mp_iter,
+                             _ptr(V), _ptr(Eo), _ptr(saved), _ptr(ws), nbytes, _stream()), 'sgg_mp_forward')
+    if save_states:
+        return V, Eo, saved
+    return V, Eo
+
+
+def linear(x, weight, bias=None, relu=False):
+    """nn.Linear forward (+ReLU) — y = act(x @ weight.T + bias)."""
+    lib = _lib.load()
+    x = _f32(x, 'x'); weight = _f32(weight, 'weight')
+    if x.dim() != 2 or weight.dim() != 2 or x.shape[1] != weight.shape[1]:
+        raise _lib.SggError('linear: x %s vs weight %s' % (tuple(x.shape), tuple(weight.shape)))
+    if bias is not None:
+        bias = _f32(bias, 'bias', (weight.shape[0],))
+    M, K = x.shape
+    Nout = weight.shape[0]
+    y = torch.empty((M, Nout), dtype=torch.float32, device=x.device)
+    check(lib.sgg_linear_forward(_ptr(x), _ptr(weight), _ptr(bias), _ptr(y), M, Nout, K, 1 if relu else 0, _stream()),
+          'sgg_linear_forward')
+    return y
+
+
+class L1Plan(object):
+    """Preallocated buffers + weight structs for repeated L1 forwards of one (N, E) shape;
+    ``run`` enqueues exactly one C-ABI call and is CUDA-graph capturable."""
+
+    def __init__(self, params, N, E, D=4096, mp_iter=3, device='cuda'):
+        lib = _lib.load()
+        self.hw, self._k1 = head_weights(params)
+        self.w, self._k2, self.H = mp_weights(params)
+        self.N, self.E, self.D, self.T = N, E, D, mp_iter
+        self.n_cls = params['obj_fc.weight'].shape[0]; self.n_rel = params['rel_fc.weight'].shape[0]
+        self.obj_dists = torch.empty((N, self.n_cls), dtype=torch.float32, device=device)
+        self.rel_dists = torch.empty((E, self.n_rel), dtype=torch.float32, device=device)
+        self.nbytes = lib.sgg_l1_workspace_bytes(N, E, self.H, mp_iter)
+        self.ws = torch.empty(self.nbytes, dtype=torch.uint8, device=device)
+        self._fn = lib.sgg_l1_forward
+
+    def run(self, obj_feat, edge_feat, graph):
+        check(self._fn(_ptr(obj_feat), _ptr(edge_feat), _ptr(graph.ws), C.byref(self.hw), C.byref(self.w),
+                       self.N, self.E, self.D, self.H, self.T, self.n_cls, self.n_rel,
+                       _ptr(self.obj_dists), _ptr(self.rel_dists), _ptr(self.ws), self.nbytes, _stream()),
+              'sgg_l1_forward')
+        return self.obj_dists, self.rel_dists
+
+
+def l1_forward(obj_feat, edge_feat, graph, params, mp_iter=3):
+    """4096-d features -> (obj_dists, rel_dists): rel_model_stanford.py:103-107 without roi_fmap*."""
+    obj_feat = _f32(obj_feat, 'obj_feat'); edge_feat = _f32(edge_feat, 'edge_feat')
+    D = params['obj_unary.weight'].shape[1]
+    if obj_feat.shape != (graph.N, D) or edge_feat.shape != (graph.E, D):
+        raise _lib.SggError('l1_forward: feature shapes %s %s do not match graph (%d, %d) x %d'
+                            % (tuple(obj_feat.shape), tuple(edge_feat.shape), graph.N, graph.E, D))
+    plan = L1Plan(params, graph.N, graph.E, D, mp_iter, obj_feat.device)
+    return plan.run(obj_feat, edge_feat, graph)
+
+
+def draw_union_boxes(rois, union_inds, pooling_size=27, sub_half=False):
+    """lib/draw_rectangles/draw_rectangles.pyx:12-67 on the device.  rois [N,5], union_inds int64 [E,2]."""
+    lib = _lib.load()
+    rois = _f32(rois, 'rois'); ui, stride = _i64_rows(union_inds, 'union_inds')
+    E = ui.shape[0]
+    out = torch.empty((E, 2, pooling_size, pooling_size), dtype=torch.float32, device=rois.device)
+    check(lib.sgg_draw_union_boxes(_ptr(rois), _ptr(ui), stride, 0, 1, E, pooling_size, 1 if sub_half else 0,
+                                   _ptr(out), _stream()), 'sgg_draw_union_boxes')
+    return out
+
+
+def geom_weights(params, prefix='union_boxes.conv.'):
+    gw = GeomWeights()
+    keep = []
+    for field, key in (('conv1_w', '0.weight'), ('conv1_b', '0.bias'), ('bn1_w', '2.weight'), ('bn1_b', '2.bias'),
+                       ('bn1_rm', '2.running_mean'), ('bn1_rv', '2.running_var'), ('conv2_w', '4.weight'),
+                       ('conv2_b', '4.bias'), ('bn2_w', '6.weight'), ('bn2_b', '6.bias'),
+                       ('bn2_rm', '6.running_mean'), ('bn2_rv', '6.running_var')):
+        t = _f32(params[prefix + key], prefix + key); keep.append(t)
+        setattr(gw, field, t.data_ptr())
+    C_out = params[prefix + '4.weight'].shape[0]
+    return gw, keep, C_out
+
+
+def union_geom(rois, union_inds, params, union_pools=None, prefix='union_boxes.conv.'):
+    """UnionBoxesAndFeats.forward, edge_model='motifs', eval-mode BN (lib/get_union_boxes.py:63-101).
+    Returns union_pools + geom (broadcast) if union_pools is given, else geom [E, C]."""
+    lib = _lib.load()
+    rois = _f32(rois, 'rois'); ui, stride = _i64_rows(union_inds, 'union_inds')
+    gw, keep, Cc = geom_weights(params, prefix)
+    E = ui.shape[0]
+    if union_pools is not None:
+        union_pools = _f32(union_pools, 'union_pools', (E, Cc, 7, 7))
+        out = torch.empty_like(union_pools)
+    else:
+        out = torch.empty((E, Cc), dtype=torch.float32, device=rois.device)
+    nbytes = lib.sgg_union_geom_workspace_bytes(E, Cc)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=rois.device)
+    check(lib.sgg_union_geom_forward(_ptr(rois), _ptr(ui), stride, 0, 1, E, Cc, C.byref(gw), _ptr(union_pools),
+                                     _ptr(out), _ptr(ws), nbytes, _stream()), 'sgg_union_geom_forward')
+    return out
+
+
+def node_edge_features(fmap, rois, union_inds, spatial_scale=1.0 / 16, pool=7, sampling_ratio=2,
+                       want_node=True, want_edge=True):
+    """RelModelBase.node_edge_features (rel_model_base.py:245-260)."""
+    lib = _lib.load()
+    fmap = _f32(fmap, 'fmap'); rois = _f32(rois, 'rois'); ui, stride = _i64_rows(union_inds, 'union_inds')
+    B, Cc, Hf, Wf = fmap.shape
+    N, E = rois.shape[0], ui.shape[0]
+    node = torch.empty((N, Cc, pool, pool), dtype=torch.float32, device=fmap.device) if want_node else None
+    edge = torch.empty((E, Cc, pool, pool), dtype=torch.float32, device=fmap.device) if want_edge else None
+    check(lib.sgg_node_edge_features(_ptr(fmap), B, Cc, Hf, Wf, _ptr(rois), N, _ptr(ui), stride, 0, 1, E,
+                                     float(spatial_scale), pool, sampling_ratio, _ptr(node), _ptr(edge), _stream()),
+          'sgg_node_edge_features')
+    return node, edge

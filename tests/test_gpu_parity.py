@@ -1,0 +1,155 @@
+"""GPU parity: the CUDA path (through the C-ABI, via sgg_b200.ops) against
+ (a) golden vectors produced by running the reference itself, and
+ (b) the numpy oracle on the same seeded inputs,
+at sizes the oracle finishes in seconds.  Bar: 1e-4 absolute on fp32 outputs
+(BASELINE.json north_star); draw_union_boxes is bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import imp_numpy as O
+from tests import cases
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def pdev(p):
+    return {k: dev(v) for k, v in p.items()}
+
+
+@pytest.fixture(scope='module')
+def ops():
+    from sgg_b200 import ops as _ops
+    return _ops
+
+
+@pytest.mark.parametrize('name', ['l0_cfg1', 'l0_cfg2_s3', 'l0_ragged_t6', 'l0_special'])
+def test_l0_message_pass_vs_golden_and_oracle(ops, name):
+    fx = cases.load(name)
+    obj, rel, rel_inds, p, T = cases.l0_inputs(fx)
+    g = ops.build_graph(dev(rel_inds)[:, 1:3], obj.shape[0], validate=True)
+    v, e = ops.message_pass(dev(rel), dev(obj), g, pdev(p), T)
+    v, e = v.cpu().numpy(), e.cpu().numpy()
+    vo, eo = O.message_pass(rel, obj, rel_inds[:, 1:3], p, T)
+    assert np.abs(v - vo).max() <= TOL and np.abs(e - eo).max() <= TOL
+    if 'v_rows' in fx:
+        cases.check_rows(v, fx['v_rows'], fx['v'], fx['v_colsum'], TOL, 'V')
+        cases.check_rows(e, fx['e_rows'], fx['e'], fx['e_colsum'], TOL, 'E')
+    else:
+        assert np.abs(v - fx['v']).max() <= TOL and np.abs(e - fx['e']).max() <= TOL
+
+
+def test_l0_saved_states_match_oracle_trajectory(ops):
+    fx = cases.load('l0_ragged_t6')
+    obj, rel, rel_inds, p, T = cases.l0_inputs(fx)
+    N, E = obj.shape[0], rel.shape[0]
+    g = ops.build_graph(dev(rel_inds)[:, 1:3], N)
+    v, e, saved = ops.message_pass(dev(rel), dev(obj), g, pdev(p), T, save_states=True)
+    vs, es = O.message_pass(rel, obj, rel_inds[:, 1:3], p, T, return_all=True)
+    saved = saved.cpu().numpy().reshape(T + 1, (N + E) * 512)
+    for t in range(T + 1):
+        assert np.abs(saved[t, :N * 512].reshape(N, 512) - vs[t]).max() <= TOL
+        assert np.abs(saved[t, N * 512:].reshape(E, 512) - es[t]).max() <= TOL
+    assert np.abs(v.cpu().numpy() - vs[-1]).max() <= TOL
+
+
+@pytest.mark.parametrize('name', ['l1_cfg1', 'l1_cfg2', 'l1_cfg2_s3'])
+def test_l1_forward_vs_golden(ops, name):
+    fx = cases.load(name)
+    of, ef, rel_inds, p, T = cases.l1_inputs(fx)
+    g = ops.build_graph(dev(rel_inds)[:, 1:3], of.shape[0], validate=True)
+    od, rd = ops.l1_forward(dev(of), dev(ef), g, pdev(p), T)
+    od, rd = od.cpu().numpy(), rd.cpu().numpy()
+    cases.check_rows(od, fx['obj_rows'], fx['obj_dists'], fx['obj_colsum'], TOL, 'obj_dists')
+    cases.check_rows(rd, fx['rel_rows'], fx['rel_dists'], fx['rel_colsum'], TOL, 'rel_dists')
+
+
+@pytest.mark.parametrize('M,N,K,relu', [(1, 51, 512, 0), (77, 151, 512, 0), (300, 512, 4096, 1), (130, 4096, 512, 1),
+                                         (5, 64, 25088, 0), (257, 200, 64, 1)])
+def test_linear_vs_numpy(ops, M, N, K, relu):
+    rng = np.random.default_rng(M * 7 + N)
+    x = rng.standard_normal((M, K), dtype=np.float32); w = rng.standard_normal((N, K), dtype=np.float32) / np.sqrt(K)
+    b = rng.standard_normal(N, dtype=np.float32)
+    y = ops.linear(dev(x), dev(w), dev(b), relu=bool(relu)).cpu().numpy()
+    ref = (x.astype(np.float64) @ w.astype(np.float64).T + b)
+    if relu:
+        ref = np.maximum(ref, 0)
+    assert np.abs(y - ref).max() <= 2e-5 * max(1.0, np.abs(ref).max())
+
+
+def test_draw_union_boxes_bit_exact(ops):
+    fx = cases.load('draw_union_boxes')
+    pairs = fx['pairs']
+    E = pairs.shape[0]
+    rois = np.zeros((2 * E, 5), np.float32)
+    rois[:E, 1:] = pairs[:, :4]; rois[E:, 1:] = pairs[:, 4:]
+    ui = np.stack((np.arange(E), np.arange(E) + E), 1).astype(np.int64)
+    out = ops.draw_union_boxes(dev(rois), dev(ui), 27).cpu().numpy()
+    assert np.array_equal(out, fx['out'])
+    out2 = ops.draw_union_boxes(dev(rois), dev(ui), 27, sub_half=True).cpu().numpy()
+    assert np.array_equal(out2, fx['out'] - np.float32(0.5))
+
+
+def test_union_geom_eval(ops):
+    fx = cases.load('union_geom')
+    rois, ui, p = cases.geom_inputs(fx)
+    geom = ops.union_geom(dev(rois), dev(ui), pdev(p)).cpu().numpy()
+    assert np.abs(geom - fx['out_eval']).max() <= TOL
+    pools = np.random.default_rng(0).standard_normal((ui.shape[0], 512, 7, 7), dtype=np.float32)
+    full = ops.union_geom(dev(rois), dev(ui), pdev(p), dev(pools)).cpu().numpy()
+    assert np.abs(full - (pools + fx['out_eval'][:, :, None, None])).max() <= TOL
+
+
+def test_roi_align_node_and_union(ops):
+    fx = cases.load('roi_align')
+    fmap, rois, ui = cases.roi_inputs(fx)
+    nf, ef = ops.node_edge_features(dev(fmap), dev(rois), dev(ui))
+    assert np.abs(nf.cpu().numpy() - fx['node_feat']).max() <= 1e-5
+    assert np.abs(ef.cpu().numpy() - fx['edge_feat']).max() <= 1e-5
+
+
+def test_graph_rejects_out_of_range(ops):
+    from sgg_b200._lib import SggError
+    rel = torch.tensor([[0, 1], [1, 5]], dtype=torch.int64).cuda()
+    with pytest.raises(SggError):
+        ops.build_graph(rel, 3, validate=True)
+
+
+def test_empty_edges_and_cpu_tensor_rejected(ops):
+    from sgg_b200._lib import SggError
+    fx = cases.load('l0_cfg1')
+    obj, rel, rel_inds, p, T = cases.l0_inputs(fx)
+    g = ops.build_graph(torch.zeros((0, 2), dtype=torch.int64).cuda(), obj.shape[0])
+    v, e = ops.message_pass(dev(rel[:0]), dev(obj), g, pdev(p), T)
+    vo, eo = O.message_pass(rel[:0], obj, rel_inds[:0, 1:3], p, T)
+    assert e.shape[0] == 0 and np.abs(v.cpu().numpy() - vo).max() <= TOL
+    with pytest.raises(SggError):
+        ops.linear(torch.zeros(4, 16), torch.zeros(4, 16))
+
+
+def test_full_size_properties_cfg4_shard(ops):
+    """BASELINE cfg4 per-GPU shard (32 images, N=960, E=9600): size-independent properties —
+    permutation equivariance of the edge list and image independence (block-diagonal graph)."""
+    from sgg_b200 import synth
+    g = synth.synth_graph(32, 30, 300, 99)
+    N, E = g['boxes'].shape[0], g['rel_inds'].shape[0]
+    obj, rel = synth.synth_l0_states(N, E, 99)
+    p = pdev(synth.synth_params(99, scale=2.0, level='l0'))
+    ri = dev(g['rel_inds'])
+    gr = ops.build_graph(ri[:, 1:3], N)
+    v, e = ops.message_pass(dev(rel), dev(obj), gr, p, 3)
+    perm = torch.randperm(E, generator=torch.Generator().manual_seed(1)).cuda()
+    gr2 = ops.build_graph(ri[perm][:, 1:3].contiguous(), N)
+    v2, e2 = ops.message_pass(dev(rel)[perm].contiguous(), dev(obj), gr2, p, 3)
+    assert (v - v2).abs().max().item() <= 2e-5 and (e[perm] - e2).abs().max().item() <= 2e-5
+    # first image alone
+    n0 = 30; m0 = int((g['rel_inds'][:, 0] == 0).sum())
+    gr3 = ops.build_graph(ri[:m0, 1:3], n0)
+    v3, e3 = ops.message_pass(dev(rel[:m0]), dev(obj[:n0]), gr3, p, 3)
+    assert (v[:n0] - v3).abs().max().item() <= 2e-5 and (e[:m0] - e3).abs().max().item() <= 2e-5
+    assert torch.isfinite(v).all() and torch.isfinite(e).all()

@@ -70,3 +70,29 @@ def test_get_rel_inds_eval_order():
     r = O.get_rel_inds_eval(im)
     assert r.shape == (3 * 2 + 2, 3)
     assert r[0].tolist() == [0, 0, 1] and r[-1].tolist() == [1, 4, 3]
+
+
+@pytest.mark.parametrize('name', ['l1_cfg1', 'l1_cfg2_s3'])
+def test_torch_cpu_port_l1(name):
+    import torch
+    from oracle.imp_torch_cpu import ImpCpu
+    fx = cases.load(name)
+    of, ef, rel_inds, p, T = cases.l1_inputs(fx)
+    m = ImpCpu(mp_iter=T).load_numpy(p).eval()
+    with torch.no_grad():
+        od, rd = m.l1_forward(torch.from_numpy(of), torch.from_numpy(ef), torch.from_numpy(rel_inds[:, 1:3]))
+    cases.check_rows(od.numpy(), fx['obj_rows'], fx['obj_dists'], fx['obj_colsum'], 2e-5, 'obj_dists')
+    cases.check_rows(rd.numpy(), fx['rel_rows'], fx['rel_dists'], fx['rel_colsum'], 2e-5, 'rel_dists')
+
+
+def test_draw_union_boxes_vs_compiled_reference():
+    """oracle/_ref = the reference's own Cython op built from /root/reference (oracle/build_ref.py)."""
+    from oracle import build_ref
+    mod = build_ref.load()
+    if mod is None:
+        pytest.skip('oracle/_ref not built (no /root/reference on this box)')
+    rng = np.random.default_rng(5)
+    xy = rng.random((200, 2, 2), dtype=np.float32) * 500
+    wh = rng.random((200, 2, 2), dtype=np.float32) * 300 + 1
+    pairs = np.concatenate((xy[:, 0], xy[:, 0] + wh[:, 0], xy[:, 1], xy[:, 1] + wh[:, 1]), 1).astype(np.float32)
+    assert np.array_equal(O.draw_union_boxes(pairs, 27), mod.draw_union_boxes(pairs, 27))
