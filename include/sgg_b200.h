@@ -34,7 +34,7 @@ extern "C" {
 #define SGG_API
 #endif
 
-#define SGG_ABI_VERSION 1
+#define SGG_ABI_VERSION 2
 #define SGG_E_BADARG 10001   /* shape / alignment / null pointer          */
 #define SGG_E_WORKSPACE 10002 /* workspace too small                      */
 #define SGG_E_INDEX 10003    /* rel_inds out of [0, N) (reported by sgg_graph_check) */
@@ -56,6 +56,10 @@ typedef struct {
   const float *node_w_ih, *node_w_hh, *node_b_ih, *node_b_hh;
   const float *gate_w[4];
   const float *gate_b[4];
+  /* optional tensor-core operands: [hi | lo] splits of the four GRU matrices made by
+   * sgg_tc_split_weights (2 * 3H*H floats each).  Non-NULL => that GEMM runs on tcgen05 (3xTF32),
+   * NULL => fp32 SIMT tiles. */
+  const float *edge_w_ih_split, *edge_w_hh_split, *node_w_ih_split, *node_w_hh_split;
 } sgg_mp_weights;
 
 /* ---- ragged graph index (replaces the dense [N,E] incidence matrices of
@@ -75,19 +79,50 @@ SGG_API int sgg_graph_check(const void *graph_ws, int N, int E, void *stream);
 
 /* ---- a1-a3: RelModelStanford.message_pass (rel_model_stanford.py:48-94) -----
  * obj_rep [N,H], rel_rep [E,H] -> V_out [N,H], E_out [E,H] after T iterations.
- * saved (nullable): (T+1) * (N+E) * H floats, states V_0,E_0 ... V_T,E_T for backward.
- * H must be a multiple of 64. */
+ * saved (nullable): training tape of sgg_mp_tape_bytes(N,E,H,T) bytes; it starts with the states
+ * V_0,E_0 ... V_T,E_T ((T+1) * (N+E) * H floats) followed by the GRU gate caches, edge gates, vertex
+ * contexts and P matrices sgg_mp_backward needs.  H must be a multiple of 64. */
+SGG_API size_t sgg_mp_tape_bytes(int N, int E, int H, int T);
 SGG_API size_t sgg_mp_workspace_bytes(int N, int E, int H, int T);
 SGG_API int sgg_mp_forward(const float *obj_rep, const float *rel_rep, const void *graph_ws,
                    const sgg_mp_weights *w, int N, int E, int H, int T,
                    float *V_out, float *E_out, float *saved,
                    void *ws, size_t ws_bytes, void *stream);
 
+/* Backward of sgg_mp_forward (BPTT over the tape).  `grads` has the layout of the first 16 pointers of
+ * sgg_mp_weights; every non-NULL buffer is ACCUMULATED into (+=).  d_obj_rep [N,H] / d_rel_rep [E,H]
+ * (grads of the forward inputs) are overwritten, nullable.  Deterministic (no float atomics). */
+typedef struct {
+  float *edge_w_ih, *edge_w_hh, *edge_b_ih, *edge_b_hh;
+  float *node_w_ih, *node_w_hh, *node_b_ih, *node_b_hh;
+  float *gate_w[4];
+  float *gate_b[4];
+} sgg_mp_grads;
+SGG_API size_t sgg_mp_backward_workspace_bytes(int N, int E, int H, int T);
+SGG_API int sgg_mp_backward(const float *obj_rep, const float *rel_rep, const void *graph_ws,
+                    const sgg_mp_weights *w, const float *tape, int N, int E, int H, int T,
+                    const float *dV_T, const float *dE_T, const sgg_mp_grads *grads,
+                    float *d_obj_rep, float *d_rel_rep, void *ws, size_t ws_bytes, void *stream);
+
 /* ---- a5/a6: nn.Linear (+ReLU): y[M,Nout] = act(x[M,K] @ w[Nout,K]^T + b) ----
  * (obj_unary / edge_unary / obj_fc / rel_fc rel_model_stanford.py:29-33,
  *  roi_fmap / roi_fmap_obj rel_model_base.py:110-111).  b nullable. K % 16 == 0. */
 SGG_API int sgg_linear_forward(const float *x, const float *w, const float *b, float *y,
                        int M, int Nout, int K, int relu, void *stream);
+
+/* nn.Linear backward.  dy [M,Nout] must already be masked by the ReLU derivative when the forward had
+ * relu=1.  dx [M,K] is overwritten (nullable); dw [Nout,K] and db [Nout] are ACCUMULATED into (nullable). */
+SGG_API size_t sgg_linear_backward_workspace_bytes(int M, int Nout);
+SGG_API int sgg_linear_backward(const float *x, const float *w, const float *dy, int M, int Nout, int K,
+                        float *dx, float *dw, float *db, void *ws, size_t ws_bytes, void *stream);
+
+/* ---- tensor-core (tcgen05 / TMEM / TMA) variants -----------------------------------------
+ * fp32 in, fp32 out, fp32-grade accuracy through the 3xTF32 split x = hi + lo.
+ * sgg_tc_split_weights: split[0:n] = hi(w), split[n:2n] = lo(w); call once per weight version.
+ * sgg_tc_linear_forward: same contract as sgg_linear_forward but takes the split weight. K % 4 == 0. */
+SGG_API int sgg_tc_split_weights(const float *w, size_t n, float *split, void *stream);
+SGG_API int sgg_tc_linear_forward(const float *x, const float *w_split, const float *b, float *y,
+                          int M, int Nout, int K, int relu, void *stream);
 
 /* ---- L1: 4096-d features -> obj_dists / rel_dists (rel_model_stanford.py:103-107
  * without roi_fmap*): obj_unary, relu(edge_unary), message_pass, obj_fc, rel_fc. */
@@ -96,6 +131,8 @@ typedef struct {
   const float *edge_unary_w, *edge_unary_b; /* [H,D],[H] */
   const float *obj_fc_w, *obj_fc_b;         /* [n_cls,H],[n_cls] */
   const float *rel_fc_w, *rel_fc_b;         /* [n_rel,H],[n_rel] */
+  /* optional [hi | lo] splits (sgg_tc_split_weights) => tcgen05 path for that projection */
+  const float *obj_unary_w_split, *edge_unary_w_split, *obj_fc_w_split, *rel_fc_w_split;
 } sgg_head_weights;
 SGG_API size_t sgg_l1_workspace_bytes(int N, int E, int H, int T);
 SGG_API int sgg_l1_forward(const float *obj_feat, const float *edge_feat, const void *graph_ws,
@@ -129,6 +166,11 @@ SGG_API int sgg_union_geom_forward(const float *rois, const int64_t *union_inds,
                            int col_subj, int col_obj, int E, int C,
                            const sgg_geom_weights *gw, const float *union_pools,
                            float *out, void *ws, size_t ws_bytes, void *stream);
+
+/* Training path of a7: the four live 7x7x2 conv1 windows of (draw_union_boxes - 0.5) as rows
+ * patches[E,4,98] (tap = ch*49 + ky*7 + kx; zero over the padding), so conv1 becomes a linear op. */
+SGG_API int sgg_geom_patches(const float *rois, const int64_t *union_inds, int64_t row_stride,
+                     int col_subj, int col_obj, int E, float *out, void *stream);
 
 /* ---- a9: node_edge_features (rel_model_base.py:245-260): torchvision
  * roi_align(aligned=False, sampling_ratio=2, 7x7, scale 1/16) for objects and

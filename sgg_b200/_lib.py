@@ -18,12 +18,21 @@ c_i64p = C.c_void_p
 class MpWeights(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ('edge_w_ih', 'edge_w_hh', 'edge_b_ih', 'edge_b_hh',
                                           'node_w_ih', 'node_w_hh', 'node_b_ih', 'node_b_hh')] + \
+               [('gate_w', C.c_void_p * 4), ('gate_b', C.c_void_p * 4)] + \
+               [(n, C.c_void_p) for n in ('edge_w_ih_split', 'edge_w_hh_split', 'node_w_ih_split', 'node_w_hh_split')]
+
+
+class MpGrads(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ('edge_w_ih', 'edge_w_hh', 'edge_b_ih', 'edge_b_hh',
+                                          'node_w_ih', 'node_w_hh', 'node_b_ih', 'node_b_hh')] + \
                [('gate_w', C.c_void_p * 4), ('gate_b', C.c_void_p * 4)]
 
 
 class HeadWeights(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ('obj_unary_w', 'obj_unary_b', 'edge_unary_w', 'edge_unary_b',
-                                          'obj_fc_w', 'obj_fc_b', 'rel_fc_w', 'rel_fc_b')]
+                                          'obj_fc_w', 'obj_fc_b', 'rel_fc_w', 'rel_fc_b',
+                                          'obj_unary_w_split', 'edge_unary_w_split', 'obj_fc_w_split',
+                                          'rel_fc_w_split')]
 
 
 class GeomWeights(C.Structure):
@@ -41,16 +50,26 @@ SIGNATURES = {
     'sgg_graph_build': (C.c_int, [c_i64p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t,
                                   C.c_void_p]),
     'sgg_graph_check': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    'sgg_mp_tape_bytes': (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    'sgg_mp_backward_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    'sgg_mp_backward': (C.c_int, [c_f, c_f, C.c_void_p, C.POINTER(MpWeights), c_f, C.c_int, C.c_int, C.c_int, C.c_int,
+                                  c_f, c_f, C.POINTER(MpGrads), c_f, c_f, C.c_void_p, C.c_size_t, C.c_void_p]),
+    'sgg_linear_backward_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int]),
+    'sgg_linear_backward': (C.c_int, [c_f, c_f, c_f, C.c_int, C.c_int, C.c_int, c_f, c_f, c_f, C.c_void_p, C.c_size_t,
+                                      C.c_void_p]),
     'sgg_mp_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     'sgg_mp_forward': (C.c_int, [c_f, c_f, C.c_void_p, C.POINTER(MpWeights), C.c_int, C.c_int, C.c_int, C.c_int,
                                  c_f, c_f, c_f, C.c_void_p, C.c_size_t, C.c_void_p]),
     'sgg_linear_forward': (C.c_int, [c_f, c_f, c_f, c_f, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    'sgg_tc_split_weights': (C.c_int, [c_f, C.c_size_t, c_f, C.c_void_p]),
+    'sgg_tc_linear_forward': (C.c_int, [c_f, c_f, c_f, c_f, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     'sgg_l1_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     'sgg_l1_forward': (C.c_int, [c_f, c_f, C.c_void_p, C.POINTER(HeadWeights), C.POINTER(MpWeights),
                                  C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                  c_f, c_f, C.c_void_p, C.c_size_t, C.c_void_p]),
     'sgg_draw_union_boxes': (C.c_int, [c_f, c_i64p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_f,
                                        C.c_void_p]),
+    'sgg_geom_patches': (C.c_int, [c_f, c_i64p, C.c_int64, C.c_int, C.c_int, C.c_int, c_f, C.c_void_p]),
     'sgg_union_geom_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int]),
     'sgg_union_geom_forward': (C.c_int, [c_f, c_i64p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int,
                                          C.POINTER(GeomWeights), c_f, c_f, C.c_void_p, C.c_size_t, C.c_void_p]),
@@ -76,7 +95,7 @@ def load():
         fn = getattr(lib, name)      # AttributeError here = header / library mismatch
         fn.restype = res
         fn.argtypes = args
-    if lib.sgg_abi_version() != 1:
+    if lib.sgg_abi_version() != 2:
         raise SggError('libsgg_b200.so ABI version mismatch')
     _lib = lib
     return lib

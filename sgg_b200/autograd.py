@@ -1,0 +1,126 @@
+"""torch.autograd wrappers: forward AND backward of every stage run in libsgg_b200.so.
+
+The model (``sgg_b200.model``) composes these exactly where the reference composes
+nn.Linear / nn.GRUCell / index ops, so ``loss.backward()`` in the reference's
+``main.py:116-120`` works unchanged.  Contract (SURVEY.md §8b "Autograd"): gradients for all
+trainable tensors and for the ``node_feat`` / ``edge_feat`` inputs of ``predict``; ``fmap`` and
+the detector never need gradients (main.py:62-63, rel_model_stanford.py:125-131).
+"""
+import torch
+import torch.nn.functional as F
+
+from . import ops
+from .ops import MP_KEYS, GATE_KEYS
+
+_MP_PARAM_KEYS = tuple(MP_KEYS) + tuple(k + s for k in GATE_KEYS for s in ('.0.weight', '.0.bias'))
+
+
+class _LinearFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, relu):
+        y = ops.linear(x, weight, bias, relu=relu)
+        ctx.relu = relu
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(x, weight, y if relu else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, y = ctx.saved_tensors
+        dy = dy.contiguous()
+        if ctx.relu:
+            dy = dy * (y > 0)                       # elementwise ReLU mask
+        dx, dw, db = ops.linear_backward(x, weight, dy, ctx.needs_input_grad[0], ctx.needs_input_grad[1],
+                                         ctx.has_bias and ctx.needs_input_grad[2])
+        return dx, dw, db, None
+
+
+def linear(x, weight, bias=None, relu=False):
+    """nn.Linear (+ReLU) with CUDA forward/backward.  Inference (no grad) skips the autograd graph."""
+    x = x.contiguous()
+    if torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad or (bias is not None and bias.requires_grad)):
+        return _LinearFn.apply(x, weight, bias, relu)
+    return ops.linear(x, weight, bias, relu=relu)
+
+
+class _MessagePassFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, rel_rep, obj_rep, rel_inds, mp_iter, *plist):
+        params = dict(zip(_MP_PARAM_KEYS, plist))
+        graph = ops.build_graph(rel_inds, obj_rep.shape[0])
+        v, e, tape = ops.message_pass_train(rel_rep, obj_rep, graph, params, mp_iter)
+        ctx.graph, ctx.mp_iter, ctx.tape = graph, mp_iter, tape
+        ctx.save_for_backward(rel_rep, obj_rep, *plist)
+        return v, e
+
+    @staticmethod
+    def backward(ctx, dv, de):
+        rel_rep, obj_rep = ctx.saved_tensors[:2]
+        params = dict(zip(_MP_PARAM_KEYS, ctx.saved_tensors[2:]))
+        dv = torch.zeros_like(obj_rep) if dv is None else dv.contiguous()
+        de = torch.zeros_like(rel_rep) if de is None else de.contiguous()
+        d_rel, d_obj, grads = ops.message_pass_backward(rel_rep, obj_rep, ctx.graph, params, ctx.tape, dv, de, ctx.mp_iter)
+        ctx.tape = None
+        return (d_rel, d_obj, None, None) + tuple(grads[k] for k in _MP_PARAM_KEYS)
+
+
+def message_pass(rel_rep, obj_rep, rel_inds, params, mp_iter=3):
+    """RelModelStanford.message_pass (rel_model_stanford.py:48-94): rel_inds int64 [E,2] global ids."""
+    rel_rep, obj_rep = rel_rep.contiguous(), obj_rep.contiguous()
+    plist = [params[k] for k in _MP_PARAM_KEYS]
+    need = torch.is_grad_enabled() and (rel_rep.requires_grad or obj_rep.requires_grad or any(p.requires_grad for p in plist))
+    if need:
+        return _MessagePassFn.apply(rel_rep, obj_rep, rel_inds, mp_iter, *plist)
+    graph = ops.build_graph(rel_inds, obj_rep.shape[0])
+    return ops.message_pass(rel_rep, obj_rep, graph, params, mp_iter)
+
+
+def node_edge_features(fmap, rois, union_inds, spatial_scale, pool=7, sampling_ratio=2):
+    """RoIAlign of objects and union boxes.  ``fmap`` is produced under no_grad and detached by the caller
+    (rel_model_stanford.py:125-131), so no backward is defined; a differentiable fmap (GAN ``-attachG``
+    path, out of scope) is rejected loudly rather than silently dropping its gradient."""
+    if torch.is_grad_enabled() and fmap.requires_grad:
+        raise NotImplementedError('node_edge_features: gradient w.r.t. fmap (GAN -attachG path) is not implemented')
+    return ops.node_edge_features(fmap.detach(), rois.detach(), union_inds, spatial_scale, pool, sampling_ratio)
+
+
+def _conv_params(conv):
+    p = {}
+    for idx in ('0', '4'):
+        p['union_boxes.conv.%s.weight' % idx] = getattr(conv, idx).weight
+        p['union_boxes.conv.%s.bias' % idx] = getattr(conv, idx).bias
+    for idx in ('2', '6'):
+        bn = getattr(conv, idx)
+        p['union_boxes.conv.%s.weight' % idx] = bn.weight; p['union_boxes.conv.%s.bias' % idx] = bn.bias
+        p['union_boxes.conv.%s.running_mean' % idx] = bn.running_mean
+        p['union_boxes.conv.%s.running_var' % idx] = bn.running_var
+    return p
+
+
+def union_geom(rois, union_inds, conv, training):
+    """Geometry embedding [E, dim] of UnionBoxesAndFeats (lib/get_union_boxes.py:51-59,66-67).
+    eval: one fused CUDA pipeline straight from the boxes (running BN statistics).
+    train: the conv windows are materialised by a CUDA kernel ([4E, 98] patches of the 27x27 masks), the two
+    convolutions run through the CUDA linear op (fwd+bwd), and BatchNorm batch statistics / running-stat
+    updates go through ATen batch_norm on the tiny [4E, dim/2] and [E, dim] activations."""
+    rois = rois.detach()
+    if not training:
+        return ops.union_geom(rois, union_inds, _conv_params(conv))
+    c0, bn1, c1, bn2 = conv[0], conv[2], conv[4], conv[6]
+    patches = ops.geom_patches(rois, union_inds)                                  # [E,4,98]
+    E = patches.shape[0]
+    x = linear(patches.view(E * 4, 98), c0.weight.view(c0.weight.shape[0], -1), c0.bias, relu=True)
+    x = F.batch_norm(x, bn1.running_mean, bn1.running_var, bn1.weight, bn1.bias, True, bn1.momentum, bn1.eps)
+    if bn1.num_batches_tracked is not None:
+        bn1.num_batches_tracked += 1
+    x = x.view(E, 4, -1).amax(1)                                                  # MaxPool2d(3,2,1) over the 2x2 map
+    x = linear(x, c1.weight[:, :, 1, 1].contiguous(), c1.bias, relu=True)         # only the centre tap sees data
+    x = F.batch_norm(x, bn2.running_mean, bn2.running_var, bn2.weight, bn2.bias, True, bn2.momentum, bn2.eps)
+    if bn2.num_batches_tracked is not None:
+        bn2.num_batches_tracked += 1
+    return x
+
+
+def broadcast_add(union_pools, geom):
+    """union_pools [E,C,7,7] + geom [E,C] (lib/get_union_boxes.py:101)."""
+    return union_pools + geom[:, :, None, None]

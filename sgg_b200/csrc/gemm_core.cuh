@@ -1,18 +1,22 @@
-// fp32 SIMT tile-GEMM core shared by the linear and GRU kernels.
+// fp32 SIMT tile-GEMM core shared by the linear, GRU and backward kernels.
 //
-//   acc[BM x (blocks of 64 cols)] += A[BM x K] * W[rows, K]^T
+//   acc[BM x (blocks of 64 cols)] += A[BM x K] * B[cols x K]^T
 //
-// Both operands are K-major (activations [M,K] row-major, nn.Linear / GRUCell
-// weights [out,K] row-major), i.e. a "TN" GEMM.  One CTA = 256 threads laid out
-// 16 (rows) x 16 (cols); a thread owns TM = BM/16 rows x 4 consecutive columns in
-// each of the column blocks.  A column block is 64 consecutive weight rows
-// starting at an arbitrary row base, so one tile can cover e.g. hidden units
-// [j0, j0+64) of the r, z and n gates of a GRUCell (rows j0, H+j0, 2H+j0), which
-// lets the GRU non-linearity run in the GEMM epilogue.
+// One CTA = 256 threads laid out 16 (rows) x 16 (cols); a thread owns TM = BM/16
+// rows x 4 consecutive columns in each column block.  A column block is 64
+// consecutive B-rows starting at an arbitrary base, so one tile can cover hidden
+// units [j0, j0+64) of the r, z and n gates of a GRUCell (weight rows j0, H+j0,
+// 2H+j0) and run the GRU non-linearity in the GEMM epilogue.
 //
-// K is consumed in chunks of 16 through double-buffered shared memory (k-major,
-// so the inner product reads are float4 broadcasts / conflict-free); global loads
-// for chunk c+1 are issued before the FMAs of chunk c (register staging).
+// Operand layouts (template flags):
+//   A_COL = false : A(m,k) = base[(m0+m)*ld + k]    (activations, K-major)
+//   A_COL = true  : A(m,k) = base[k*ld + m0+m]      (transposed view, e.g. dY^T for dW = dY^T X)
+//   B_COL = false : B(j,k) = W[(rowbase+j)*ld + k]  (nn.Linear / GRUCell weight [out,K])
+//   B_COL = true  : B(j,k) = W[k*ld + rowbase+j]    (dX = dY W: reduce over W's rows)
+// K is consumed in chunks of 16 through double-buffered shared memory laid out
+// k-major (inner-product reads are float4 broadcasts / conflict-free); global loads
+// of chunk c+1 are issued before the FMAs of chunk c (register staging).  All edges
+// (M, cols, K) are masked with zero fill; unaligned operands fall back to scalar loads.
 #pragma once
 #include "common.cuh"
 
@@ -34,18 +38,18 @@ struct AccMap {
   __device__ static constexpr int at(int i) { return i == 0 ? A : (i == 1 ? B : (i == 2 ? C : D)); }
 };
 
-// Rows of the A operand: direct rows m0.. of a row-major [M, lda] matrix (zero beyond M).
-struct ARows {
+struct ARows {           // A operand of one tile
   const float *base; int lda; int M; int m0;
 };
 
-// NW weight row-blocks; block b = rows [rowbase[b], rowbase[b] + nvalid[b]) of W (row stride ldw).
 template <int NW>
-struct WBlocks {
+struct WBlocks {         // NW column blocks of the B operand
   const float *W; int ldw; int rowbase[NW]; int nvalid[NW];
 };
 
-template <int BM, int NACC, int NW, class Map>
+__device__ __forceinline__ bool sgg_aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+template <int BM, int NACC, int NW, class Map, bool A_COL = false, bool B_COL = false>
 __device__ __forceinline__ void gemm_segment(float (&acc)[BM / 16][NACC][4], const ARows &A,
                                              const WBlocks<NW> &Wb, int K, float *smem) {
   constexpr int TM = BM / 16;
@@ -56,55 +60,115 @@ __device__ __forceinline__ void gemm_segment(float (&acc)[BM / 16][NACC][4], con
   float *Bs = smem + 2 * BK * LDA;     // [2][BK][LDB]
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
-  const int lrow = tid >> 2, lq = tid & 3;   // loader mapping: 4 threads per 16-float row chunk
+
+  // ---- loader mappings -------------------------------------------------------------
+  // row mode: 4 threads per 16-float k-chunk of one row  -> (row = idx>>2, kq = idx&3)
+  // col mode: one float4 of 4 consecutive rows/cols for one k -> (kk = idx / (W/4), q = idx % (W/4))
+  const bool a_vec = ((A.lda & 3) == 0) && sgg_aligned16(A.base) && (A_COL || (K & 3) == 0);
+  const bool b_vec = ((Wb.ldw & 3) == 0) && sgg_aligned16(Wb.W) && (B_COL || (K & 3) == 0);
+  bool b_vec_blk[NW];
+#pragma unroll
+  for (int b = 0; b < NW; ++b) b_vec_blk[b] = b_vec && (!B_COL || (Wb.rowbase[b] & 3) == 0);
 
   float4 ra[A_LD], rb[NW];
-  const float *ap[A_LD];
-  bool aok[A_LD];
-#pragma unroll
-  for (int l = 0; l < A_LD; ++l) {
-    int r = lrow + l * 64;
-    aok[l] = (A.m0 + r) < A.M;
-    ap[l] = A.base + (size_t)(aok[l] ? A.m0 + r : 0) * A.lda + lq * 4;
-  }
-  const float *bp[NW];
-  bool bok[NW];
-#pragma unroll
-  for (int b = 0; b < NW; ++b) {
-    bok[b] = lrow < Wb.nvalid[b];
-    bp[b] = Wb.W + (size_t)(Wb.rowbase[b] + (bok[b] ? lrow : 0)) * Wb.ldw + lq * 4;
-  }
   auto gload = [&](int k0) {
 #pragma unroll
-    for (int l = 0; l < A_LD; ++l)
-      ra[l] = aok[l] ? __ldg(reinterpret_cast<const float4 *>(ap[l] + k0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int l = 0; l < A_LD; ++l) {
+      const int idx = tid + l * NTHREADS;
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      if (!A_COL) {
+        const int r = idx >> 2, k = k0 + (idx & 3) * 4;
+        if (A.m0 + r < A.M) {
+          const float *p = A.base + (size_t)(A.m0 + r) * A.lda + k;
+          if (a_vec && k + 3 < K) {
+            const float4 t = __ldg(reinterpret_cast<const float4 *>(p));
+            v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+          } else {
 #pragma unroll
-    for (int b = 0; b < NW; ++b)
-      rb[b] = bok[b] ? __ldg(reinterpret_cast<const float4 *>(bp[b] + k0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int c = 0; c < 4; ++c) if (k + c < K) v[c] = __ldg(p + c);
+          }
+        }
+      } else {
+        const int kk = idx / (BM / 4), m = (idx % (BM / 4)) * 4, k = k0 + kk;
+        if (k < K) {
+          const float *p = A.base + (size_t)k * A.lda + A.m0 + m;
+          if (a_vec && A.m0 + m + 3 < A.M) {
+            const float4 t = __ldg(reinterpret_cast<const float4 *>(p));
+            v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+          } else {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) if (A.m0 + m + c < A.M) v[c] = __ldg(p + c);
+          }
+        }
+      }
+      ra[l] = make_float4(v[0], v[1], v[2], v[3]);
+    }
+#pragma unroll
+    for (int b = 0; b < NW; ++b) {
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      if (!B_COL) {
+        const int r = tid >> 2, k = k0 + (tid & 3) * 4;
+        if (r < Wb.nvalid[b]) {
+          const float *p = Wb.W + (size_t)(Wb.rowbase[b] + r) * Wb.ldw + k;
+          if (b_vec_blk[b] && k + 3 < K) {
+            const float4 t = __ldg(reinterpret_cast<const float4 *>(p));
+            v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+          } else {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) if (k + c < K) v[c] = __ldg(p + c);
+          }
+        }
+      } else {
+        const int kk = tid >> 4, j = (tid & 15) * 4, k = k0 + kk;
+        if (k < K && j < Wb.nvalid[b]) {
+          const float *p = Wb.W + (size_t)k * Wb.ldw + Wb.rowbase[b] + j;
+          if (b_vec_blk[b] && j + 3 < Wb.nvalid[b]) {
+            const float4 t = __ldg(reinterpret_cast<const float4 *>(p));
+            v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+          } else {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) if (j + c < Wb.nvalid[b]) v[c] = __ldg(p + c);
+          }
+        }
+      }
+      rb[b] = make_float4(v[0], v[1], v[2], v[3]);
+    }
   };
   auto sstore = [&](int buf) {
     float *as = As + buf * BK * LDA;
     float *bs = Bs + buf * BK * LDB;
 #pragma unroll
     for (int l = 0; l < A_LD; ++l) {
-      int r = lrow + l * 64;
-      as[(lq * 4 + 0) * LDA + r] = ra[l].x;
-      as[(lq * 4 + 1) * LDA + r] = ra[l].y;
-      as[(lq * 4 + 2) * LDA + r] = ra[l].z;
-      as[(lq * 4 + 3) * LDA + r] = ra[l].w;
+      const int idx = tid + l * NTHREADS;
+      if (!A_COL) {
+        const int r = idx >> 2, kq = (idx & 3) * 4;
+        as[(kq + 0) * LDA + r] = ra[l].x;
+        as[(kq + 1) * LDA + r] = ra[l].y;
+        as[(kq + 2) * LDA + r] = ra[l].z;
+        as[(kq + 3) * LDA + r] = ra[l].w;
+      } else {
+        const int kk = idx / (BM / 4), m = (idx % (BM / 4)) * 4;
+        *reinterpret_cast<float4 *>(as + kk * LDA + m) = ra[l];
+      }
     }
 #pragma unroll
     for (int b = 0; b < NW; ++b) {
-      int c = b * BN + lrow;
-      bs[(lq * 4 + 0) * LDB + c] = rb[b].x;
-      bs[(lq * 4 + 1) * LDB + c] = rb[b].y;
-      bs[(lq * 4 + 2) * LDB + c] = rb[b].z;
-      bs[(lq * 4 + 3) * LDB + c] = rb[b].w;
+      if (!B_COL) {
+        const int c = b * BN + (tid >> 2), kq = (tid & 3) * 4;
+        bs[(kq + 0) * LDB + c] = rb[b].x;
+        bs[(kq + 1) * LDB + c] = rb[b].y;
+        bs[(kq + 2) * LDB + c] = rb[b].z;
+        bs[(kq + 3) * LDB + c] = rb[b].w;
+      } else {
+        const int kk = tid >> 4, j = (tid & 15) * 4;
+        *reinterpret_cast<float4 *>(bs + kk * LDB + b * BN + j) = rb[b];
+      }
     }
   };
 
-  const int nchunk = K / BK;
+  const int nchunk = (K + BK - 1) / BK;
   __syncthreads();           // previous users of smem (earlier segment) are done
+  if (nchunk == 0) return;
   gload(0);
   sstore(0);
   __syncthreads();
@@ -124,7 +188,6 @@ __device__ __forceinline__ void gemm_segment(float (&acc)[BM / 16][NACC][4], con
 #pragma unroll
       for (int b = 0; b < NW; ++b) {
         float4 w = *reinterpret_cast<const float4 *>(bs + kk * LDB + b * BN);
-        constexpr int dummy = 0; (void)dummy;
         const int s = Map::at(b);
 #pragma unroll
         for (int i = 0; i < TM; ++i) {

@@ -114,6 +114,24 @@ __global__ void __launch_bounds__(256) k_geom_conv1(const float *__restrict__ ro
   }
 }
 
+// im2col of the 4 live conv1 windows: patches[e][pos][ch*49 + ky*7 + kx] (zero where the window hangs over the
+// padding) — training path: conv1 then runs as a linear op with autograd.
+__global__ void k_geom_patches(const float *__restrict__ rois, const int64_t *__restrict__ ui, int64_t stride, int cs,
+                               int co, int E, float *__restrict__ out) {
+  const size_t total = (size_t)E * 4 * 98;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int tap = (int)(i % 98), pos = (int)((i / 98) % 4), e = (int)(i / (4 * 98));
+    const int ch = tap / 49, ky = (tap % 49) / 7, kx = tap % 7;
+    const int y = (pos >> 1) * 16 - 3 + ky, x = (pos & 1) * 16 - 3 + kx;
+    float v = 0.f;
+    if (y >= 0 && y < GP && x >= 0 && x < GP) {
+      PairBoxes p = load_pair(rois, ui, stride, cs, co, e);
+      v = mask_value(p, ch, y, x, GP) - 0.5f;
+    }
+    out[i] = v;
+  }
+}
+
 // hid[e][c] = max_pos BN1(c1out[e][pos][c])      (BatchNorm then MaxPool2d(3,2,1) on a 2x2 map)
 __global__ void k_geom_pool(const float *__restrict__ c1out, int E, int C1, const float *__restrict__ g,
                             const float *__restrict__ b, const float *__restrict__ mean,
@@ -169,6 +187,17 @@ extern "C" int sgg_draw_union_boxes(const float *rois, const int64_t *union_inds
   sgg::k_draw_union_boxes<<<blocks, 256, 0, (cudaStream_t)stream>>>(rois, union_inds, row_stride, col_subj, col_obj, E,
                                                                      P, sub_half ? 0.5f : 0.f, out);
   SGG_RETURN_IF_LAUNCH_FAILED("k_draw_union_boxes");
+  return 0;
+}
+
+extern "C" int sgg_geom_patches(const float *rois, const int64_t *union_inds, int64_t row_stride, int col_subj,
+                                int col_obj, int E, float *out, void *stream) {
+  if (E <= 0) return 0;
+  if (!rois || !union_inds || !out) return sgg_set_err(SGG_E_BADARG, "geom_patches: null pointer");
+  const size_t total = (size_t)E * 4 * 98;
+  int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
+  sgg::k_geom_patches<<<blocks, 256, 0, (cudaStream_t)stream>>>(rois, union_inds, row_stride, col_subj, col_obj, E, out);
+  SGG_RETURN_IF_LAUNCH_FAILED("k_geom_patches");
   return 0;
 }
 

@@ -4,4 +4,26 @@
 namespace sgg {
 int launch_linear(const float *x, const float *w, const float *b, float *y, int M, int Nout, int K, int relu,
                   cudaStream_t st);
+int launch_gemm(const float *A, int lda, bool a_col, const float *B, int ldb, bool b_col, float *C, int ldc, int M,
+                int N, int K, bool accumulate, cudaStream_t st);
+size_t colsum_workspace_floats(int rows, int cols);
+int launch_colsum(const float *X, int ld, int rows, int cols, float *out, bool accumulate, float *ws, cudaStream_t st);
+int tc_linear(const float *x, const float *w_split, const float *b, float *y, int M, int Nout, int K, int relu,
+              cudaStream_t st);
+// mode 0 = INIT (h = 0), 1 = NODE (x = ctx, h = V), 2 = EDGE (h = Eh, gathered gi)
+int tc_gru(int mode, const float *x, const float *h, const float *w_ih_split, const float *w_hh_split,
+           const float *b_ih, const float *b_hh, const float *P, const float *gates, const int *subj, const int *obj,
+           float *out, float *cache, int M, int H, cudaStream_t st);
+
+struct MpTape {
+  int N, E, H, T;
+  float *states;   // (T+1) x [V_t (N*H) | E_t (E*H)]
+  float *cacheV;   // (T+1) x N x 4H   (r, z, n, gh_n) of the GRU call that produced V_t
+  float *cacheE;   // (T+1) x E x 4H
+  float *gates;    // T x E x 4
+  float *ctx;      // T x N x H
+  float *P;        // T x N x 3H
+  size_t floats;
+};
+MpTape mp_tape_view(float *base, int N, int E, int H, int T);
 }

@@ -35,6 +35,7 @@ struct GruArgs {
   const float *gates;  // [M,4]  (g_sub, g_obj, g_out, g_in)
   const int *subj, *obj;
   float *out;          // [M,H]
+  float *cache;        // nullable [M,4,H]: (r, z, n, gh_n) saved for the backward pass
   int M, H;
 };
 
@@ -135,15 +136,23 @@ k_gru(GruArgs p) {
         gi_n[c] = acc[i][2][c] + bi_n[c]; gh_n[c] = bh_n[c];
       }
     }
-    float o4[4];
+    float o4[4], cr[4], cz[4], cn[4];
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       const float r = sgg_sigmoid(gi_r[c] + gh_r[c]);
       const float z = sgg_sigmoid(gi_z[c] + gh_z[c]);
       const float n = tanhf(gi_n[c] + r * gh_n[c]);
       o4[c] = (1.0f - z) * n + z * hv[c];
+      cr[c] = r; cz[c] = z; cn[c] = n;
     }
     *reinterpret_cast<float4 *>(p.out + (size_t)m * H + j) = make_float4(o4[0], o4[1], o4[2], o4[3]);
+    if (p.cache != nullptr) {
+      float *cp = p.cache + (size_t)m * 4 * H + j;
+      *reinterpret_cast<float4 *>(cp) = make_float4(cr[0], cr[1], cr[2], cr[3]);
+      *reinterpret_cast<float4 *>(cp + H) = make_float4(cz[0], cz[1], cz[2], cz[3]);
+      *reinterpret_cast<float4 *>(cp + 2 * H) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+      *reinterpret_cast<float4 *>(cp + 3 * H) = make_float4(gh_n[0], gh_n[1], gh_n[2], gh_n[3]);
+    }
   }
 }
 
@@ -295,6 +304,23 @@ static size_t mp_layout(MpScratch *s, void *ws, int N, int E, int H) {
   return ar.off;
 }
 
+// Tape written by the forward pass in training mode and consumed by mp_backward (mp_bwd.cu).
+MpTape mp_tape_view(float *base, int N, int E, int H, int T) {
+  MpTape t;
+  const size_t n1 = N > 0 ? N : 1, e1 = E > 0 ? E : 1;
+  size_t off = 0;
+  auto take = [&](size_t n) { float *p = base ? base + off : nullptr; off += (n + 63) / 64 * 64; return p; };
+  t.N = N; t.E = E; t.H = H; t.T = T;
+  t.states = take((size_t)(T + 1) * ((size_t)N + E) * H);
+  t.cacheV = take((size_t)(T + 1) * n1 * 4 * H);
+  t.cacheE = take((size_t)(T + 1) * e1 * 4 * H);
+  t.gates = take((size_t)(T > 0 ? T : 1) * e1 * 4);
+  t.ctx = take((size_t)(T > 0 ? T : 1) * n1 * H);
+  t.P = take((size_t)(T > 0 ? T : 1) * n1 * 3 * H);
+  t.floats = off;
+  return t;
+}
+
 int mp_forward(const float *obj_rep, const float *rel_rep, const void *graph_ws, const sgg_mp_weights *w, int N,
                int E, int H, int T, float *V_out, float *E_out, float *saved, void *ws, size_t ws_bytes,
                cudaStream_t st) {
@@ -307,6 +333,9 @@ int mp_forward(const float *obj_rep, const float *rel_rep, const void *graph_ws,
   if (need > ws_bytes || !ws) return sgg_set_err(SGG_E_WORKSPACE, "mp_forward: workspace %zu < %zu", ws_bytes, need);
   SggGraphView g = sgg_graph_view(graph_ws, N, E);
   const size_t vN = (size_t)N * H, eN = (size_t)E * H;
+  MpTape tape = mp_tape_view(saved, N, E, H, T);
+  auto cacheV = [&](int it) -> float * { return saved ? tape.cacheV + (size_t)it * N * 4 * H : nullptr; };
+  auto cacheE = [&](int it) -> float * { return saved ? tape.cacheE + (size_t)it * E * 4 * H : nullptr; };
   // State buffers: with `saved` every iteration writes into its own slot (no ping-pong copy);
   // otherwise ping-pong in the workspace and write the last iteration straight to the outputs.
   auto vbuf = [&](int it) -> float * {
@@ -320,14 +349,25 @@ int mp_forward(const float *obj_rep, const float *rel_rep, const void *graph_ws,
   int rc;
   {  // hx = 0 initial step (:68-72)
     GruArgs a{}; a.x = obj_rep; a.h = nullptr; a.w_ih = w->node_w_ih; a.w_hh = w->node_w_hh; a.b_ih = w->node_b_ih;
-    a.b_hh = w->node_b_hh; a.out = vbuf(0); a.M = N; a.H = H;
-    if ((rc = launch_gru<GRU_INIT>(a, st))) return rc;
+    a.b_hh = w->node_b_hh; a.out = vbuf(0); a.cache = cacheV(0); a.M = N; a.H = H;
+    if (w->node_w_ih_split) {
+      if ((rc = tc_gru(0, obj_rep, nullptr, w->node_w_ih_split, nullptr, w->node_b_ih, w->node_b_hh, nullptr, nullptr,
+                       nullptr, nullptr, vbuf(0), cacheV(0), N, H, st))) return rc;
+    } else if ((rc = launch_gru<GRU_INIT>(a, st))) return rc;
     GruArgs b{}; b.x = rel_rep; b.h = nullptr; b.w_ih = w->edge_w_ih; b.w_hh = w->edge_w_hh; b.b_ih = w->edge_b_ih;
-    b.b_hh = w->edge_b_hh; b.out = ebuf(0); b.M = E; b.H = H;
-    if ((rc = launch_gru<GRU_INIT>(b, st))) return rc;
+    b.b_hh = w->edge_b_hh; b.out = ebuf(0); b.cache = cacheE(0); b.M = E; b.H = H;
+    if (w->edge_w_ih_split) {
+      if ((rc = tc_gru(0, rel_rep, nullptr, w->edge_w_ih_split, nullptr, w->edge_b_ih, w->edge_b_hh, nullptr, nullptr,
+                       nullptr, nullptr, ebuf(0), cacheE(0), E, H, st))) return rc;
+    } else if ((rc = launch_gru<GRU_INIT>(b, st))) return rc;
   }
   for (int it = 0; it < T; ++it) {
     const float *V = vbuf(it), *Eh = ebuf(it);
+    if (saved) {   // training: per-iteration intermediates go to the tape instead of the scratch
+      s.g = tape.gates + (size_t)it * E * 4;
+      s.ctx = tape.ctx + (size_t)it * N * H;
+      s.P = tape.P + (size_t)it * N * 3 * H;
+    }
     if (N > 0) {
       k_gate_node<<<(N * 32 + 255) / 256, 256, 0, st>>>(V, N, H, w->gate_w[0], w->gate_w[1], w->gate_w[2],
                                                         w->gate_w[3], s.a);
@@ -338,7 +378,9 @@ int mp_forward(const float *obj_rep, const float *rel_rep, const void *graph_ws,
           Eh, E, H, w->gate_w[0], w->gate_w[1], w->gate_w[2], w->gate_w[3], w->gate_b[0], w->gate_b[1], w->gate_b[2],
           w->gate_b[3], s.a, g.subj, g.obj, s.g);
       SGG_RETURN_IF_LAUNCH_FAILED("k_gate_edge");
-      if ((rc = launch_linear(V, w->edge_w_ih, nullptr, s.P, N, 3 * H, H, 0, st))) return rc;
+      if (w->edge_w_ih_split) {
+        if ((rc = tc_linear(V, w->edge_w_ih_split, nullptr, s.P, N, 3 * H, H, 0, st))) return rc;
+      } else if ((rc = launch_linear(V, w->edge_w_ih, nullptr, s.P, N, 3 * H, H, 0, st))) return rc;
     }
     if (N > 0) {
       k_ctx<<<N, (H / 4 < 128 ? H / 4 : 128), 0, st>>>(Eh, s.g, g.out_ptr, g.out_idx, g.in_ptr, g.in_idx, H, s.ctx);
@@ -347,13 +389,20 @@ int mp_forward(const float *obj_rep, const float *rel_rep, const void *graph_ws,
     {
       GruArgs a{}; a.h = Eh; a.w_ih = w->edge_w_ih; a.w_hh = w->edge_w_hh; a.b_ih = w->edge_b_ih;
       a.b_hh = w->edge_b_hh; a.P = s.P; a.gates = s.g; a.subj = g.subj; a.obj = g.obj; a.out = ebuf(it + 1);
+      a.cache = cacheE(it + 1);
       a.M = E; a.H = H;
-      if ((rc = launch_gru<GRU_EDGE>(a, st))) return rc;
+      if (w->edge_w_hh_split) {
+        if ((rc = tc_gru(2, nullptr, Eh, nullptr, w->edge_w_hh_split, w->edge_b_ih, w->edge_b_hh, s.P, s.g, g.subj,
+                         g.obj, ebuf(it + 1), cacheE(it + 1), E, H, st))) return rc;
+      } else if ((rc = launch_gru<GRU_EDGE>(a, st))) return rc;
     }
     {
       GruArgs a{}; a.x = s.ctx; a.h = V; a.w_ih = w->node_w_ih; a.w_hh = w->node_w_hh; a.b_ih = w->node_b_ih;
-      a.b_hh = w->node_b_hh; a.out = vbuf(it + 1); a.M = N; a.H = H;
-      if ((rc = launch_gru<GRU_NODE>(a, st))) return rc;
+      a.b_hh = w->node_b_hh; a.out = vbuf(it + 1); a.cache = cacheV(it + 1); a.M = N; a.H = H;
+      if (w->node_w_ih_split && w->node_w_hh_split) {
+        if ((rc = tc_gru(1, s.ctx, V, w->node_w_ih_split, w->node_w_hh_split, w->node_b_ih, w->node_b_hh, nullptr,
+                         nullptr, nullptr, nullptr, vbuf(it + 1), cacheV(it + 1), N, H, st))) return rc;
+      } else if ((rc = launch_gru<GRU_NODE>(a, st))) return rc;
     }
   }
   if (saved) {   // outputs are the last saved slot
@@ -369,6 +418,10 @@ size_t mp_workspace_bytes(int N, int E, int H) {
 }
 
 }  // namespace sgg
+
+extern "C" size_t sgg_mp_tape_bytes(int N, int E, int H, int T) {
+  return sgg::mp_tape_view(nullptr, N < 0 ? 0 : N, E < 0 ? 0 : E, H, T < 0 ? 0 : T).floats * sizeof(float);
+}
 
 extern "C" size_t sgg_mp_workspace_bytes(int N, int E, int H, int T) {
   (void)T;
@@ -413,11 +466,15 @@ extern "C" int sgg_l1_forward(const float *obj_feat, const float *edge_feat, con
   if (need > ws_bytes) return sgg_set_err(SGG_E_WORKSPACE, "l1_forward: workspace %zu < %zu", ws_bytes, need);
   cudaStream_t st = (cudaStream_t)stream;
   int rc;
-  if ((rc = sgg::launch_linear(obj_feat, hw->obj_unary_w, hw->obj_unary_b, s.obj_rep, N, H, D, 0, st))) return rc;
-  if ((rc = sgg::launch_linear(edge_feat, hw->edge_unary_w, hw->edge_unary_b, s.rel_rep, E, H, D, 1, st))) return rc;
+  auto lin = [&](const float *x, const float *wt, const float *wsplit, const float *b, float *y, int M, int No, int K,
+                 int relu) -> int {
+    return wsplit ? sgg::tc_linear(x, wsplit, b, y, M, No, K, relu, st) : sgg::launch_linear(x, wt, b, y, M, No, K, relu, st);
+  };
+  if ((rc = lin(obj_feat, hw->obj_unary_w, hw->obj_unary_w_split, hw->obj_unary_b, s.obj_rep, N, H, D, 0))) return rc;
+  if ((rc = lin(edge_feat, hw->edge_unary_w, hw->edge_unary_w_split, hw->edge_unary_b, s.rel_rep, E, H, D, 1))) return rc;
   if ((rc = sgg::mp_forward(s.obj_rep, s.rel_rep, graph_ws, w, N, E, H, T, s.V, s.Eh, nullptr, s.mp, s.mp_bytes, st)))
     return rc;
-  if ((rc = sgg::launch_linear(s.V, hw->obj_fc_w, hw->obj_fc_b, obj_dists, N, n_cls, H, 0, st))) return rc;
-  if ((rc = sgg::launch_linear(s.Eh, hw->rel_fc_w, hw->rel_fc_b, rel_dists, E, n_rel, H, 0, st))) return rc;
+  if ((rc = lin(s.V, hw->obj_fc_w, hw->obj_fc_w_split, hw->obj_fc_b, obj_dists, N, n_cls, H, 0))) return rc;
+  if ((rc = lin(s.Eh, hw->rel_fc_w, hw->rel_fc_w_split, hw->rel_fc_b, rel_dists, E, n_rel, H, 0))) return rc;
   return 0;
 }

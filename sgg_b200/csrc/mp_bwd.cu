@@ -1,0 +1,277 @@
+// Backward of the iterative message passing (BPTT through T iterations) — the autograd
+// counterpart of sgg_models/rel_model_stanford.py:48-94, which the reference gets from
+// torch.autograd over ~100 small kernels and two dense [N,E] incidence matmuls.
+//
+// Forward (mp.cu) saved on the tape, per iteration t: states V_t, E_t; GRU caches
+// (r, z, n, gh_n) of the calls that produced V_{t+1}, E_{t+1}; edge gates g_t; ctx_t; P_t.
+// Per iteration, in reverse:
+//   k_gru_bwd          dgi, dgh, dh*z from dh' and the cache (GRUCell pointwise backward)
+//   GEMMs (gemm.cu)    dW += dG^T X ; dX (+)= dG W ; db += colsum(dG)
+//   k_edge_bwd         warp per edge: dg_sub/obj = <dgi_e, P[s|o]>, dg_out/in = <dctx[s|o], E[e]>,
+//                      dlogit = dg * g (1-g); dE[e] += g_out dctx[s] + g_in dctx[o] + sum_k dlogit_k w_k[H:]
+//   k_node_bwd         CTA per node (CSR, fixed order): dP[n] = sum_out g_sub dgi_e + sum_in g_obj dgi_e;
+//                      da[n,k] = sum of edge dlogits; dV[n] += sum_k da[n,k] w_k[:H]
+// All reductions are deterministic (no float atomics).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace sgg {
+
+// dgi [rows,3H], dgh [rows,3H], dh_prev [rows,H] (= dh' * z, overwritten)
+__global__ void k_gru_bwd(const float *__restrict__ dh_next, const float *__restrict__ cache,
+                          const float *__restrict__ h_prev, int rows, int H, float *__restrict__ dgi,
+                          float *__restrict__ dgh, float *__restrict__ dh_prev) {
+  const size_t total = (size_t)rows * (H / 4);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t m = i / (H / 4);
+    const int j = (int)(i % (H / 4)) * 4;
+    const float4 d4 = *reinterpret_cast<const float4 *>(dh_next + m * H + j);
+    const float *cp = cache + m * 4 * H + j;
+    const float4 r4 = *reinterpret_cast<const float4 *>(cp), z4 = *reinterpret_cast<const float4 *>(cp + H);
+    const float4 n4 = *reinterpret_cast<const float4 *>(cp + 2 * H), g4 = *reinterpret_cast<const float4 *>(cp + 3 * H);
+    float4 h4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (h_prev != nullptr) h4 = *reinterpret_cast<const float4 *>(h_prev + m * H + j);
+    const float d[4] = {d4.x, d4.y, d4.z, d4.w}, r[4] = {r4.x, r4.y, r4.z, r4.w}, z[4] = {z4.x, z4.y, z4.z, z4.w};
+    const float n[4] = {n4.x, n4.y, n4.z, n4.w}, gn[4] = {g4.x, g4.y, g4.z, g4.w}, h[4] = {h4.x, h4.y, h4.z, h4.w};
+    float pr[4], pz[4], pn[4], pnr[4], dp[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float dn = d[c] * (1.f - z[c]);
+      const float dz = d[c] * (h[c] - n[c]);
+      pn[c] = dn * (1.f - n[c] * n[c]);
+      pnr[c] = pn[c] * r[c];
+      const float dr = pn[c] * gn[c];
+      pr[c] = dr * r[c] * (1.f - r[c]);
+      pz[c] = dz * z[c] * (1.f - z[c]);
+      dp[c] = d[c] * z[c];
+    }
+    float *gi = dgi + m * 3 * H + j, *gh = dgh + m * 3 * H + j;
+    const float4 vr = make_float4(pr[0], pr[1], pr[2], pr[3]), vz = make_float4(pz[0], pz[1], pz[2], pz[3]);
+    *reinterpret_cast<float4 *>(gi) = vr;
+    *reinterpret_cast<float4 *>(gi + H) = vz;
+    *reinterpret_cast<float4 *>(gi + 2 * H) = make_float4(pn[0], pn[1], pn[2], pn[3]);
+    *reinterpret_cast<float4 *>(gh) = vr;
+    *reinterpret_cast<float4 *>(gh + H) = vz;
+    *reinterpret_cast<float4 *>(gh + 2 * H) = make_float4(pnr[0], pnr[1], pnr[2], pnr[3]);
+    if (dh_prev != nullptr) *reinterpret_cast<float4 *>(dh_prev + m * H + j) = make_float4(dp[0], dp[1], dp[2], dp[3]);
+  }
+}
+
+// one warp per edge
+__global__ void k_edge_bwd(const float *__restrict__ dgi_e, const float *__restrict__ P, const float *__restrict__ dctx,
+                           const float *__restrict__ Eh, const float *__restrict__ g, const int *__restrict__ subj,
+                           const int *__restrict__ obj, int E, int H, const float *w0, const float *w1, const float *w2,
+                           const float *w3, float *__restrict__ dl, float *__restrict__ dE) {
+  const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (e >= E) return;
+  const int s = subj[e], o = obj[e];
+  const float *gi = dgi_e + (size_t)e * 3 * H, *ps = P + (size_t)s * 3 * H, *po = P + (size_t)o * 3 * H;
+  float ds = 0.f, dob = 0.f;
+  for (int k = lane * 4; k < 3 * H; k += 128) {
+    const float4 a = *reinterpret_cast<const float4 *>(gi + k);
+    const float4 b = *reinterpret_cast<const float4 *>(ps + k), c = *reinterpret_cast<const float4 *>(po + k);
+    ds += a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
+    dob += a.x * c.x + a.y * c.y + a.z * c.z + a.w * c.w;
+  }
+  const float *cs = dctx + (size_t)s * H, *co = dctx + (size_t)o * H, *er = Eh + (size_t)e * H;
+  float dout = 0.f, din = 0.f;
+  for (int k = lane * 4; k < H; k += 128) {
+    const float4 a = *reinterpret_cast<const float4 *>(er + k);
+    const float4 b = *reinterpret_cast<const float4 *>(cs + k), c = *reinterpret_cast<const float4 *>(co + k);
+    dout += a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
+    din += a.x * c.x + a.y * c.y + a.z * c.z + a.w * c.w;
+  }
+  ds = sgg_warp_sum(ds); dob = sgg_warp_sum(dob); dout = sgg_warp_sum(dout); din = sgg_warp_sum(din);
+  const float4 g4 = *reinterpret_cast<const float4 *>(g + (size_t)e * 4);
+  const float l0 = ds * g4.x * (1.f - g4.x), l1 = dob * g4.y * (1.f - g4.y);
+  const float l2 = dout * g4.z * (1.f - g4.z), l3 = din * g4.w * (1.f - g4.w);
+  if (lane == 0) *reinterpret_cast<float4 *>(dl + (size_t)e * 4) = make_float4(l0, l1, l2, l3);
+  float *de = dE + (size_t)e * H;
+  for (int k = lane * 4; k < H; k += 128) {
+    float4 acc = *reinterpret_cast<float4 *>(de + k);
+    const float4 b = *reinterpret_cast<const float4 *>(cs + k), c = *reinterpret_cast<const float4 *>(co + k);
+    const float4 a0 = __ldg(reinterpret_cast<const float4 *>(w0 + H + k)), a1 = __ldg(reinterpret_cast<const float4 *>(w1 + H + k));
+    const float4 a2 = __ldg(reinterpret_cast<const float4 *>(w2 + H + k)), a3 = __ldg(reinterpret_cast<const float4 *>(w3 + H + k));
+    acc.x += g4.z * b.x + g4.w * c.x + l0 * a0.x + l1 * a1.x + l2 * a2.x + l3 * a3.x;
+    acc.y += g4.z * b.y + g4.w * c.y + l0 * a0.y + l1 * a1.y + l2 * a2.y + l3 * a3.y;
+    acc.z += g4.z * b.z + g4.w * c.z + l0 * a0.z + l1 * a1.z + l2 * a2.z + l3 * a3.z;
+    acc.w += g4.z * b.w + g4.w * c.w + l0 * a0.w + l1 * a1.w + l2 * a2.w + l3 * a3.w;
+    *reinterpret_cast<float4 *>(de + k) = acc;
+  }
+}
+
+// one CTA per node; CSR lists ascending => fixed summation order
+__global__ void k_node_bwd(const float *__restrict__ dgi_e, const float *__restrict__ g, const float *__restrict__ dl,
+                           const int *__restrict__ out_ptr, const int *__restrict__ out_idx,
+                           const int *__restrict__ in_ptr, const int *__restrict__ in_idx, int H, const float *w0,
+                           const float *w1, const float *w2, const float *w3, float *__restrict__ dP,
+                           float *__restrict__ da, float *__restrict__ dV) {
+  const int n = blockIdx.x;
+  const int ob = out_ptr[n], oe = out_ptr[n + 1], ib = in_ptr[n], ie = in_ptr[n + 1];
+  for (int j = threadIdx.x * 4; j < 3 * H; j += blockDim.x * 4) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = ob; k < oe; ++k) {
+      const int e = out_idx[k];
+      const float gs = g[(size_t)e * 4 + 0];
+      const float4 v = *reinterpret_cast<const float4 *>(dgi_e + (size_t)e * 3 * H + j);
+      acc.x += gs * v.x; acc.y += gs * v.y; acc.z += gs * v.z; acc.w += gs * v.w;
+    }
+    for (int k = ib; k < ie; ++k) {
+      const int e = in_idx[k];
+      const float go = g[(size_t)e * 4 + 1];
+      const float4 v = *reinterpret_cast<const float4 *>(dgi_e + (size_t)e * 3 * H + j);
+      acc.x += go * v.x; acc.y += go * v.y; acc.z += go * v.z; acc.w += go * v.w;
+    }
+    *reinterpret_cast<float4 *>(dP + (size_t)n * 3 * H + j) = acc;
+  }
+  // every thread redundantly reduces the 4 scalar gate-logit grads (short lists)
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  for (int k = ob; k < oe; ++k) { const int e = out_idx[k]; a0 += dl[(size_t)e * 4 + 0]; a2 += dl[(size_t)e * 4 + 2]; }
+  for (int k = ib; k < ie; ++k) { const int e = in_idx[k]; a1 += dl[(size_t)e * 4 + 1]; a3 += dl[(size_t)e * 4 + 3]; }
+  if (threadIdx.x == 0) *reinterpret_cast<float4 *>(da + (size_t)n * 4) = make_float4(a0, a1, a2, a3);
+  for (int j = threadIdx.x * 4; j < H; j += blockDim.x * 4) {
+    float4 acc = *reinterpret_cast<float4 *>(dV + (size_t)n * H + j);
+    const float4 v0 = __ldg(reinterpret_cast<const float4 *>(w0 + j)), v1 = __ldg(reinterpret_cast<const float4 *>(w1 + j));
+    const float4 v2 = __ldg(reinterpret_cast<const float4 *>(w2 + j)), v3 = __ldg(reinterpret_cast<const float4 *>(w3 + j));
+    acc.x += a0 * v0.x + a1 * v1.x + a2 * v2.x + a3 * v3.x;
+    acc.y += a0 * v0.y + a1 * v1.y + a2 * v2.y + a3 * v3.y;
+    acc.z += a0 * v0.z + a1 * v1.z + a2 * v2.z + a3 * v3.z;
+    acc.w += a0 * v0.w + a1 * v1.w + a2 * v2.w + a3 * v3.w;
+    *reinterpret_cast<float4 *>(dV + (size_t)n * H + j) = acc;
+  }
+}
+
+// gate_w grads: dw[k][0:H] += tV[k], dw[k][H:2H] += tE[k]; db[k] += gb[k]
+__global__ void k_gate_grad_finish(const float *__restrict__ tV, const float *__restrict__ tE,
+                                   const float *__restrict__ gb, int H, float *d0, float *d1, float *d2, float *d3,
+                                   float *b0, float *b1, float *b2, float *b3) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  float *dw[4] = {d0, d1, d2, d3};
+  float *db[4] = {b0, b1, b2, b3};
+  if (i < 4 * H) {
+    const int k = i / H, j = i % H;
+    if (dw[k]) { dw[k][j] += tV[i]; dw[k][H + j] += tE[i]; }
+  }
+  if (i < 4 && db[i]) db[i][0] += gb[i];
+}
+
+struct BwdScratch {
+  float *dV[2], *dE[2], *dgi_n, *dgh_n, *dgi_e, *dgh_e, *dctx, *dP, *dl, *da, *tV, *tE, *gb, *cs;
+};
+static size_t bwd_layout(BwdScratch *s, void *ws, int N, int E, int H) {
+  SggArena ar(ws, (size_t)-1);
+  const size_t n1 = N > 0 ? N : 1, e1 = E > 0 ? E : 1;
+  for (int i = 0; i < 2; ++i) { s->dV[i] = ar.take<float>(n1 * H); s->dE[i] = ar.take<float>(e1 * H); }
+  s->dgi_n = ar.take<float>(n1 * 3 * H); s->dgh_n = ar.take<float>(n1 * 3 * H);
+  s->dgi_e = ar.take<float>(e1 * 3 * H); s->dgh_e = ar.take<float>(e1 * 3 * H);
+  s->dctx = ar.take<float>(n1 * H); s->dP = ar.take<float>(n1 * 3 * H);
+  s->dl = ar.take<float>(e1 * 4); s->da = ar.take<float>(n1 * 4);
+  s->tV = ar.take<float>((size_t)4 * H); s->tE = ar.take<float>((size_t)4 * H); s->gb = ar.take<float>(4);
+  s->cs = ar.take<float>(colsum_workspace_floats((int)(e1 > n1 ? e1 : n1), 3 * H));
+  return ar.off;
+}
+
+}  // namespace sgg
+
+extern "C" size_t sgg_mp_backward_workspace_bytes(int N, int E, int H, int T) {
+  (void)T;
+  sgg::BwdScratch s;
+  return sgg::bwd_layout(&s, nullptr, N < 0 ? 0 : N, E < 0 ? 0 : E, H);
+}
+
+// obj_rep / rel_rep: the forward inputs.  dV_T / dE_T: grads of the outputs.  `grads` mirrors sgg_mp_weights and is
+// ACCUMULATED into (NULL fields are skipped).  d_obj_rep / d_rel_rep are overwritten (nullable).
+extern "C" int sgg_mp_backward(const float *obj_rep, const float *rel_rep, const void *graph_ws, const sgg_mp_weights *w,
+                               const float *tape_base, int N, int E, int H, int T, const float *dV_T, const float *dE_T,
+                               const sgg_mp_grads *grads, float *d_obj_rep, float *d_rel_rep, void *ws, size_t ws_bytes,
+                               void *stream) {
+  using namespace sgg;
+  if (!w || !graph_ws || !tape_base || !grads || !ws) return sgg_set_err(SGG_E_BADARG, "mp_backward: null pointer");
+  if (N < 0 || E < 0 || T < 0 || H <= 0 || (H % 64) != 0) return sgg_set_err(SGG_E_BADARG, "mp_backward: bad shape");
+  BwdScratch s;
+  const size_t need = bwd_layout(&s, ws, N, E, H);
+  if (need > ws_bytes) return sgg_set_err(SGG_E_WORKSPACE, "mp_backward: workspace %zu < %zu", ws_bytes, need);
+  cudaStream_t st = (cudaStream_t)stream;
+  SggGraphView g = sgg_graph_view(graph_ws, N, E);
+  MpTape tp = mp_tape_view(const_cast<float *>(tape_base), N, E, H, T);
+  const size_t vN = (size_t)N * H, eN = (size_t)E * H;
+  auto Vt = [&](int t) { return tp.states + (size_t)t * (vN + eN); };
+  auto Et = [&](int t) { return tp.states + (size_t)t * (vN + eN) + vN; };
+  int rc;
+  SGG_CUDA_TRY(cudaMemsetAsync(s.tV, 0, sizeof(float) * 4 * (size_t)H, st));
+  SGG_CUDA_TRY(cudaMemsetAsync(s.tE, 0, sizeof(float) * 4 * (size_t)H, st));
+  SGG_CUDA_TRY(cudaMemsetAsync(s.gb, 0, sizeof(float) * 4, st));
+  auto ew_blocks = [&](size_t n) { size_t b = (n + 255) / 256; return (int)(b < 4096 ? (b ? b : 1) : 4096); };
+  auto gemm = [&](const float *A, int lda, bool ac, const float *B, int ldb, bool bc, float *C, int ldc, int M, int Nn,
+                  int K, bool acc) { return launch_gemm(A, lda, ac, B, ldb, bc, C, ldc, M, Nn, K, acc, st); };
+  auto colsum = [&](const float *X, int rows, int cols, float *out) -> int {
+    return out ? launch_colsum(X, cols, rows, cols, out, true, s.cs, st) : 0;
+  };
+
+  const float *dVn = dV_T, *dEn = dE_T;   // grads w.r.t. V_{t+1}, E_{t+1}
+  for (int t = T - 1; t >= 0; --t) {
+    float *dV = s.dV[t & 1], *dE = s.dE[t & 1];
+    const float *V = Vt(t), *Eh = Et(t);
+    const float *gt = tp.gates + (size_t)t * E * 4, *ctx = tp.ctx + (size_t)t * N * H, *P = tp.P + (size_t)t * N * 3 * H;
+    if (N > 0) {
+      k_gru_bwd<<<ew_blocks(vN / 4), 256, 0, st>>>(dVn, tp.cacheV + (size_t)(t + 1) * N * 4 * H, V, N, H, s.dgi_n, s.dgh_n, dV);
+      SGG_RETURN_IF_LAUNCH_FAILED("k_gru_bwd");
+      if (grads->node_w_ih && (rc = gemm(s.dgi_n, 3 * H, true, ctx, H, true, grads->node_w_ih, H, 3 * H, H, N, true))) return rc;
+      if (grads->node_w_hh && (rc = gemm(s.dgh_n, 3 * H, true, V, H, true, grads->node_w_hh, H, 3 * H, H, N, true))) return rc;
+      if ((rc = colsum(s.dgi_n, N, 3 * H, grads->node_b_ih))) return rc;
+      if ((rc = colsum(s.dgh_n, N, 3 * H, grads->node_b_hh))) return rc;
+      if ((rc = gemm(s.dgi_n, 3 * H, false, w->node_w_ih, H, true, s.dctx, H, N, H, 3 * H, false))) return rc;
+      if ((rc = gemm(s.dgh_n, 3 * H, false, w->node_w_hh, H, true, dV, H, N, H, 3 * H, true))) return rc;
+    }
+    if (E > 0) {
+      k_gru_bwd<<<ew_blocks(eN / 4), 256, 0, st>>>(dEn, tp.cacheE + (size_t)(t + 1) * E * 4 * H, Eh, E, H, s.dgi_e, s.dgh_e, dE);
+      SGG_RETURN_IF_LAUNCH_FAILED("k_gru_bwd");
+      if (grads->edge_w_hh && (rc = gemm(s.dgh_e, 3 * H, true, Eh, H, true, grads->edge_w_hh, H, 3 * H, H, E, true))) return rc;
+      if ((rc = colsum(s.dgh_e, E, 3 * H, grads->edge_b_hh))) return rc;
+      if ((rc = colsum(s.dgi_e, E, 3 * H, grads->edge_b_ih))) return rc;
+      if ((rc = gemm(s.dgh_e, 3 * H, false, w->edge_w_hh, H, true, dE, H, E, H, 3 * H, true))) return rc;
+      k_edge_bwd<<<(int)(((size_t)E * 32 + 255) / 256), 256, 0, st>>>(s.dgi_e, P, s.dctx, Eh, gt, g.subj, g.obj, E, H,
+                                                                    w->gate_w[0], w->gate_w[1], w->gate_w[2],
+                                                                    w->gate_w[3], s.dl, dE);
+      SGG_RETURN_IF_LAUNCH_FAILED("k_edge_bwd");
+    }
+    if (N > 0) {
+      if (E == 0) {
+        SGG_CUDA_TRY(cudaMemsetAsync(s.dP, 0, sizeof(float) * vN * 3, st));
+        SGG_CUDA_TRY(cudaMemsetAsync(s.da, 0, sizeof(float) * N * 4, st));
+      } else {
+        k_node_bwd<<<N, 128, 0, st>>>(s.dgi_e, gt, s.dl, g.out_ptr, g.out_idx, g.in_ptr, g.in_idx, H, w->gate_w[0],
+                                      w->gate_w[1], w->gate_w[2], w->gate_w[3], s.dP, s.da, dV);
+        SGG_RETURN_IF_LAUNCH_FAILED("k_node_bwd");
+        if (grads->edge_w_ih && (rc = gemm(s.dP, 3 * H, true, V, H, true, grads->edge_w_ih, H, 3 * H, H, N, true))) return rc;
+        if ((rc = gemm(s.dP, 3 * H, false, w->edge_w_ih, H, true, dV, H, N, H, 3 * H, true))) return rc;
+        if ((rc = gemm(s.da, 4, true, V, H, true, s.tV, H, 4, H, N, true))) return rc;
+        if ((rc = gemm(s.dl, 4, true, Eh, H, true, s.tE, H, 4, H, E, true))) return rc;
+        if ((rc = launch_colsum(s.dl, 4, E, 4, s.gb, true, s.cs, st))) return rc;
+      }
+    }
+    dVn = dV; dEn = dE;
+  }
+  // initial step (h = 0): rel_model_stanford.py:68-72
+  if (N > 0) {
+    k_gru_bwd<<<ew_blocks(vN / 4), 256, 0, st>>>(dVn, tp.cacheV, nullptr, N, H, s.dgi_n, s.dgh_n, nullptr);
+    SGG_RETURN_IF_LAUNCH_FAILED("k_gru_bwd");
+    if (grads->node_w_ih && (rc = gemm(s.dgi_n, 3 * H, true, obj_rep, H, true, grads->node_w_ih, H, 3 * H, H, N, true))) return rc;
+    if ((rc = colsum(s.dgi_n, N, 3 * H, grads->node_b_ih))) return rc;
+    if ((rc = colsum(s.dgh_n, N, 3 * H, grads->node_b_hh))) return rc;
+    if (d_obj_rep && (rc = gemm(s.dgi_n, 3 * H, false, w->node_w_ih, H, true, d_obj_rep, H, N, H, 3 * H, false))) return rc;
+  }
+  if (E > 0) {
+    k_gru_bwd<<<ew_blocks(eN / 4), 256, 0, st>>>(dEn, tp.cacheE, nullptr, E, H, s.dgi_e, s.dgh_e, nullptr);
+    SGG_RETURN_IF_LAUNCH_FAILED("k_gru_bwd");
+    if (grads->edge_w_ih && (rc = gemm(s.dgi_e, 3 * H, true, rel_rep, H, true, grads->edge_w_ih, H, 3 * H, H, E, true))) return rc;
+    if ((rc = colsum(s.dgi_e, E, 3 * H, grads->edge_b_ih))) return rc;
+    if ((rc = colsum(s.dgh_e, E, 3 * H, grads->edge_b_hh))) return rc;
+    if (d_rel_rep && (rc = gemm(s.dgi_e, 3 * H, false, w->edge_w_ih, H, true, d_rel_rep, H, E, H, 3 * H, false))) return rc;
+  }
+  k_gate_grad_finish<<<(4 * H + 255) / 256, 256, 0, st>>>(s.tV, s.tE, s.gb, H, grads->gate_w[0], grads->gate_w[1],
+                                                          grads->gate_w[2], grads->gate_w[3], grads->gate_b[0],
+                                                          grads->gate_b[1], grads->gate_b[2], grads->gate_b[3]);
+  SGG_RETURN_IF_LAUNCH_FAILED("k_gate_grad_finish");
+  return 0;
+}

@@ -5,6 +5,7 @@ below validates its tensors, hands raw device pointers to ``libsgg_b200.so`` and
 returns fresh torch tensors.  There is no CPU path — CPU tensors raise.
 """
 import ctypes as C
+import weakref
 import torch
 
 from . import _lib
@@ -43,6 +44,41 @@ def _i64_rows(t, name):
     if t.shape[0] <= 1:
         t = t.contiguous()
     return t, (t.stride(0) if t.shape[0] > 1 else t.shape[1])
+
+
+# ---- tensor-core mode ---------------------------------------------------------------------
+# 'tc'   : GEMM-shaped stages run on tcgen05 tensor cores with the 3xTF32 split (fp32-grade accuracy)
+# 'simt' : fp32 FMA tile kernels
+_MODE = {'gemm': 'tc'}
+_SPLIT_CACHE = {}
+
+
+def set_gemm_mode(mode):
+    if mode not in ('tc', 'simt'):
+        raise ValueError(mode)
+    _MODE['gemm'] = mode
+
+
+def get_gemm_mode():
+    return _MODE['gemm']
+
+
+def split_weight(w):
+    """[hi | lo] 3xTF32 split of a weight tensor, cached per (storage, version) so it is recomputed only
+    after the parameter changes (optimizer step / load_state_dict)."""
+    key = id(w)
+    ver = (w._version, w.data_ptr(), tuple(w.shape))
+    hit = _SPLIT_CACHE.get(key)
+    if hit is not None and hit[0] == ver and hit[2]() is w:      # same live tensor object, unchanged
+        return hit[1]
+    lib = _lib.load()
+    wc = _f32(w, 'weight')
+    out = torch.empty((2,) + tuple(wc.shape), dtype=torch.float32, device=wc.device)
+    check(lib.sgg_tc_split_weights(_ptr(wc), wc.numel(), _ptr(out), _stream()), 'sgg_tc_split_weights')
+    if len(_SPLIT_CACHE) > 256:
+        _SPLIT_CACHE.clear()
+    _SPLIT_CACHE[key] = (ver, out, weakref.ref(w))
+    return out
 
 
 def _ptr(t):
@@ -90,6 +126,11 @@ def mp_weights(params, device=None):
         tw = _f32(params[k + '.0.weight'], k + '.0.weight', (1, 2 * H)); tb = _f32(params[k + '.0.bias'], k + '.0.bias', (1,))
         keep += [tw, tb]
         w.gate_w[i] = tw.data_ptr(); w.gate_b[i] = tb.data_ptr()
+    if _MODE['gemm'] == 'tc':
+        for field, key in (('edge_w_ih_split', 'edge_gru.weight_ih'), ('edge_w_hh_split', 'edge_gru.weight_hh'),
+                           ('node_w_ih_split', 'node_gru.weight_ih'), ('node_w_hh_split', 'node_gru.weight_hh')):
+            sp = split_weight(params[key]); keep.append(sp)
+            setattr(w, field, sp.data_ptr())
     return w, keep, H
 
 
@@ -102,6 +143,11 @@ def head_weights(params):
                        ('rel_fc_w', 'rel_fc.weight'), ('rel_fc_b', 'rel_fc.bias')):
         t = _f32(params[key], key); keep.append(t)
         setattr(hw, field, t.data_ptr())
+    if _MODE['gemm'] == 'tc':
+        for field, key in (('obj_unary_w_split', 'obj_unary.weight'), ('edge_unary_w_split', 'edge_unary.weight'),
+                           ('obj_fc_w_split', 'obj_fc.weight'), ('rel_fc_w_split', 'rel_fc.weight')):
+            sp = split_weight(params[key]); keep.append(sp)
+            setattr(hw, field, sp.data_ptr())
     return hw, keep
 
 
@@ -136,8 +182,13 @@ def linear(x, weight, bias=None, relu=False):
     M, K = x.shape
     Nout = weight.shape[0]
     y = torch.empty((M, Nout), dtype=torch.float32, device=x.device)
-    check(lib.sgg_linear_forward(_ptr(x), _ptr(weight), _ptr(bias), _ptr(y), M, Nout, K, 1 if relu else 0, _stream()),
-          'sgg_linear_forward')
+    if _MODE['gemm'] == 'tc' and K % 4 == 0:
+        sp = split_weight(weight)
+        check(lib.sgg_tc_linear_forward(_ptr(x), _ptr(sp), _ptr(bias), _ptr(y), M, Nout, K, 1 if relu else 0,
+                                        _stream()), 'sgg_tc_linear_forward')
+    else:
+        check(lib.sgg_linear_forward(_ptr(x), _ptr(weight), _ptr(bias), _ptr(y), M, Nout, K, 1 if relu else 0,
+                                     _stream()), 'sgg_linear_forward')
     return y
 
 
@@ -187,6 +238,16 @@ def draw_union_boxes(rois, union_inds, pooling_size=27, sub_half=False):
     return out
 
 
+def geom_patches(rois, union_inds):
+    """[E,4,98] conv1 windows of draw_union_boxes(...) - 0.5 (training path of the geometry branch)."""
+    lib = _lib.load()
+    rois = _f32(rois, 'rois'); ui, stride = _i64_rows(union_inds, 'union_inds')
+    E = ui.shape[0]
+    out = torch.empty((E, 4, 98), dtype=torch.float32, device=rois.device)
+    check(lib.sgg_geom_patches(_ptr(rois), _ptr(ui), stride, 0, 1, E, _ptr(out), _stream()), 'sgg_geom_patches')
+    return out
+
+
 def geom_weights(params, prefix='union_boxes.conv.'):
     gw = GeomWeights()
     keep = []
@@ -232,3 +293,66 @@ def node_edge_features(fmap, rois, union_inds, spatial_scale=1.0 / 16, pool=7, s
                                      float(spatial_scale), pool, sampling_ratio, _ptr(node), _ptr(edge), _stream()),
           'sgg_node_edge_features')
     return node, edge
+
+
+# ---- backward entry points -----------------------------------------------------------------------
+def linear_backward(x, weight, dy, need_dx=True, need_dw=True, need_db=True):
+    """nn.Linear backward through the C-ABI: returns (dx, dw, db); dy must already carry the ReLU mask."""
+    lib = _lib.load()
+    x = _f32(x, 'x'); weight = _f32(weight, 'weight'); dy = _f32(dy, 'dy')
+    M, K = x.shape
+    Nout = weight.shape[0]
+    dev = x.device
+    dx = torch.empty((M, K), dtype=torch.float32, device=dev) if need_dx else None
+    dw = torch.zeros((Nout, K), dtype=torch.float32, device=dev) if need_dw else None
+    db = torch.zeros((Nout,), dtype=torch.float32, device=dev) if need_db else None
+    nbytes = lib.sgg_linear_backward_workspace_bytes(M, Nout)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    check(lib.sgg_linear_backward(_ptr(x), _ptr(weight), _ptr(dy), M, Nout, K, _ptr(dx), _ptr(dw), _ptr(db),
+                                  _ptr(ws), nbytes, _stream()), 'sgg_linear_backward')
+    return dx, dw, db
+
+
+def message_pass_train(rel_rep, obj_rep, graph, params, mp_iter=3):
+    """Forward that records the training tape.  Returns (V_T, E_T, tape)."""
+    lib = _lib.load()
+    w, keep, H = mp_weights(params)
+    N, E = graph.N, graph.E
+    obj_rep = _f32(obj_rep, 'obj_rep', (N, H)); rel_rep = _f32(rel_rep, 'rel_rep', (E, H))
+    dev = obj_rep.device
+    V = torch.empty((N, H), dtype=torch.float32, device=dev)
+    Eo = torch.empty((E, H), dtype=torch.float32, device=dev)
+    tape = torch.empty((lib.sgg_mp_tape_bytes(N, E, H, mp_iter) // 4,), dtype=torch.float32, device=dev)
+    nbytes = lib.sgg_mp_workspace_bytes(N, E, H, mp_iter)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    check(lib.sgg_mp_forward(_ptr(obj_rep), _ptr(rel_rep), _ptr(graph.ws), C.byref(w), N, E, H, mp_iter,
+                             _ptr(V), _ptr(Eo), _ptr(tape), _ptr(ws), nbytes, _stream()), 'sgg_mp_forward')
+    return V, Eo, tape
+
+
+def message_pass_backward(rel_rep, obj_rep, graph, params, tape, dV, dE, mp_iter=3):
+    """BPTT through message_pass.  Returns (d_rel_rep, d_obj_rep, grads dict keyed like ``params``)."""
+    lib = _lib.load()
+    w, keep, H = mp_weights(params)
+    N, E = graph.N, graph.E
+    obj_rep = _f32(obj_rep, 'obj_rep', (N, H)); rel_rep = _f32(rel_rep, 'rel_rep', (E, H))
+    dV = _f32(dV, 'dV', (N, H)); dE = _f32(dE, 'dE', (E, H))
+    dev = obj_rep.device
+    grads = {}
+    gs = _lib.MpGrads()
+    for field, key in zip(('edge_w_ih', 'edge_w_hh', 'edge_b_ih', 'edge_b_hh',
+                           'node_w_ih', 'node_w_hh', 'node_b_ih', 'node_b_hh'), MP_KEYS):
+        grads[key] = torch.zeros_like(params[key], dtype=torch.float32, device=dev)
+        setattr(gs, field, grads[key].data_ptr())
+    for i, k in enumerate(GATE_KEYS):
+        grads[k + '.0.weight'] = torch.zeros((1, 2 * H), dtype=torch.float32, device=dev)
+        grads[k + '.0.bias'] = torch.zeros((1,), dtype=torch.float32, device=dev)
+        gs.gate_w[i] = grads[k + '.0.weight'].data_ptr(); gs.gate_b[i] = grads[k + '.0.bias'].data_ptr()
+    d_obj = torch.empty((N, H), dtype=torch.float32, device=dev)
+    d_rel = torch.empty((E, H), dtype=torch.float32, device=dev)
+    nbytes = lib.sgg_mp_backward_workspace_bytes(N, E, H, mp_iter)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    check(lib.sgg_mp_backward(_ptr(obj_rep), _ptr(rel_rep), _ptr(graph.ws), C.byref(w), _ptr(tape), N, E, H, mp_iter,
+                              _ptr(dV), _ptr(dE), C.byref(gs), _ptr(d_obj), _ptr(d_rel), _ptr(ws), nbytes, _stream()),
+          'sgg_mp_backward')
+    return d_rel, d_obj, grads

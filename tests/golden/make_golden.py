@@ -150,6 +150,39 @@ def main():
              obj_rows=orow, obj_dists=osub, rel_rows=rrow, rel_dists=rsub,
              obj_colsum=od.astype(np.float64).sum(0), rel_colsum=rd.astype(np.float64).sum(0))
 
+    # ---------------- L1 gradients (torch.autograd through the reference's modules) ------------
+    for name, B, nb, ne, ap_, T, scale, seed in [('grad_l1_cfg1', 1, 10, 90, True, 3, 1.0, 7235),
+                                                  ('grad_l1_small_s2', 3, 9, 30, False, 3, 2.0, 7236)]:
+        if not want(name):
+            continue
+        g = synth.synth_graph(B, nb, ne, seed, all_pairs=ap_)
+        N, E = g['boxes'].shape[0], g['rel_inds'].shape[0]
+        of, ef = synth.synth_l1_feats(N, E, seed)
+        p = synth.synth_params(seed, scale=scale, level='l1')
+        load_params(model, p)
+        model.mp_iter = T
+        rng = np.random.default_rng(seed + 5)
+        r1 = rng.standard_normal((N, 151), dtype=np.float32); r2 = rng.standard_normal((E, 51), dtype=np.float32)
+        oft, eft = tt(of).requires_grad_(), tt(ef).requires_grad_()
+        model.zero_grad()
+        nf = model.obj_unary(oft); efu = torch.relu(model.edge_unary(eft))
+        v, e = model.message_pass(efu, nf, tt(g['rel_inds'][:, 1:3]))
+        loss = (model.obj_fc(v) * tt(r1)).sum() + (model.rel_fc(e) * tt(r2)).sum()
+        loss.backward()
+        out = dict(B=B, n_box=nb, n_edge=ne, all_pairs=ap_, T=T, scale=scale, seed=seed, N=N, E=E,
+                   digest=synth.digest(of, ef, g['rel_inds'], p['obj_unary.weight']), loss=float(loss))
+        sd = dict(model.named_parameters())
+        gr = {k: sd[k].grad.numpy() for k in p.keys()}
+        gr['obj_feat'] = oft.grad.numpy(); gr['edge_feat'] = eft.grad.numpy()
+        for k, gv in gr.items():
+            flat = gv.reshape(-1)
+            idx = np.sort(np.random.default_rng(seed + 11).choice(flat.shape[0], min(512, flat.shape[0]), replace=False))
+            kk = k.replace('.', '__')
+            out['idx__' + kk] = idx; out['val__' + kk] = flat[idx]
+            out['sum__' + kk] = np.float64(flat.astype(np.float64).sum())
+            out['asum__' + kk] = np.float64(np.abs(flat).astype(np.float64).sum())
+        save(name, **out)
+
     # ---------------- a8: draw_union_boxes (Cython) ---------------------------
     if want('draw_union_boxes'):
         from lib.draw_rectangles.draw_rectangles import draw_union_boxes

@@ -29,7 +29,7 @@ def test_ctypes_signatures_cover_header(built_lib):
     from sgg_b200 import _lib
     assert sorted(_lib.SIGNATURES) == declared_symbols()
     lib = _lib.load()
-    assert lib.sgg_abi_version() == 1
+    assert lib.sgg_abi_version() == 2
     # size queries are host-only and must work without a device
     assert lib.sgg_graph_workspace_bytes(240, 2400) > 0
     assert lib.sgg_mp_workspace_bytes(240, 2400, 512, 3) > (2 * 2640 * 512 * 4)

@@ -1,0 +1,66 @@
+"""GPU gradient parity: CUDA forward+backward (sgg_b200.autograd -> C-ABI) against gradients obtained by
+running torch.autograd through the REFERENCE's own modules (tests/golden/grad_*.npz), for all MP /
+unary / head tensors and the 4096-d feature inputs (SURVEY.md §4 item 2, §8b Autograd)."""
+import numpy as np
+import pytest
+import torch
+
+from tests import cases
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(name, mode):
+    from sgg_b200 import ops, autograd as K
+    ops.set_gemm_mode(mode)
+    fx = cases.load(name)
+    of, ef, rel_inds, p, T = cases.l1_inputs(fx)
+    N, E = of.shape[0], ef.shape[0]
+    seed = int(fx['seed'])
+    rng = np.random.default_rng(seed + 5)
+    r1 = torch.from_numpy(rng.standard_normal((N, 151), dtype=np.float32)).cuda()
+    r2 = torch.from_numpy(rng.standard_normal((E, 51), dtype=np.float32)).cuda()
+    P = {k: torch.from_numpy(v).cuda().requires_grad_() for k, v in p.items()}
+    oft = torch.from_numpy(of).cuda().requires_grad_(); eft = torch.from_numpy(ef).cuda().requires_grad_()
+    rel = torch.from_numpy(rel_inds).cuda()
+    nf = K.linear(oft, P['obj_unary.weight'], P['obj_unary.bias'])
+    efu = K.linear(eft, P['edge_unary.weight'], P['edge_unary.bias'], relu=True)
+    v, e = K.message_pass(efu, nf, rel[:, 1:3], P, T)
+    od = K.linear(v, P['obj_fc.weight'], P['obj_fc.bias']); rd = K.linear(e, P['rel_fc.weight'], P['rel_fc.bias'])
+    loss = (od * r1).sum() + (rd * r2).sum()
+    loss.backward()
+    ops.set_gemm_mode('tc')
+    assert abs(float(loss) - float(fx['loss'])) <= 1e-3 * max(1.0, abs(float(fx['loss'])))
+    grads = {k: P[k].grad for k in P}
+    grads['obj_feat'] = oft.grad; grads['edge_feat'] = eft.grad
+    worst = 0.0
+    for k, gval in grads.items():
+        assert gval is not None, 'no gradient for ' + k
+        kk = k.replace('.', '__')
+        flat = gval.detach().cpu().numpy().reshape(-1)
+        ref = fx['val__' + kk]; got = flat[fx['idx__' + kk]]
+        scale = max(1.0, float(np.abs(ref).max()))
+        err = float(np.abs(got - ref).max()) / scale
+        worst = max(worst, err)
+        assert err <= 2e-4, '%s: max|d|/scale = %.3e' % (k, err)
+        asum = float(np.abs(flat).astype(np.float64).sum())
+        assert abs(asum - float(fx['asum__' + kk])) <= 2e-4 * max(1.0, float(fx['asum__' + kk])), k
+    return worst
+
+
+@pytest.mark.parametrize('mode', ['simt', 'tc'])
+@pytest.mark.parametrize('name', ['grad_l1_cfg1', 'grad_l1_small_s2'])
+def test_l1_gradients_vs_reference_autograd(name, mode):
+    _run(name, mode)
+
+
+def test_linear_backward_vs_torch():
+    from sgg_b200 import ops
+    g = torch.Generator(device='cuda').manual_seed(3)
+    for (M, N, K) in [(77, 151, 512), (300, 512, 4096), (5, 51, 512), (130, 256, 98)]:
+        x = torch.randn(M, K, device='cuda', generator=g); w = torch.randn(N, K, device='cuda', generator=g)
+        dy = torch.randn(M, N, device='cuda', generator=g)
+        dx, dw, db = ops.linear_backward(x, w, dy)
+        rx, rw, rb = dy.double() @ w.double(), dy.double().t() @ x.double(), dy.double().sum(0)
+        for a, b in ((dx, rx), (dw, rw), (db, rb)):
+            assert (a.double() - b).abs().max().item() <= 1e-5 * max(1.0, b.abs().max().item())

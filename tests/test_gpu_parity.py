@@ -22,10 +22,13 @@ def pdev(p):
     return {k: dev(v) for k, v in p.items()}
 
 
-@pytest.fixture(scope='module')
-def ops():
+@pytest.fixture(scope='module', params=['tc', 'simt'])
+def ops(request):
+    """Every parity test runs twice: tcgen05 tensor-core path (3xTF32) and fp32 SIMT path."""
     from sgg_b200 import ops as _ops
-    return _ops
+    _ops.set_gemm_mode(request.param)
+    yield _ops
+    _ops.set_gemm_mode('tc')
 
 
 @pytest.mark.parametrize('name', ['l0_cfg1', 'l0_cfg2_s3', 'l0_ragged_t6', 'l0_special'])
@@ -73,7 +76,7 @@ def test_l1_forward_vs_golden(ops, name):
                                          (5, 64, 25088, 0), (257, 200, 64, 1)])
 def test_linear_vs_numpy(ops, M, N, K, relu):
     rng = np.random.default_rng(M * 7 + N)
-    x = rng.standard_normal((M, K), dtype=np.float32); w = rng.standard_normal((N, K), dtype=np.float32) / np.sqrt(K)
+    x = rng.standard_normal((M, K), dtype=np.float32); w = (rng.standard_normal((N, K), dtype=np.float32) / np.float32(np.sqrt(K))).astype(np.float32)
     b = rng.standard_normal(N, dtype=np.float32)
     y = ops.linear(dev(x), dev(w), dev(b), relu=bool(relu)).cpu().numpy()
     ref = (x.astype(np.float64) @ w.astype(np.float64).T + b)
