@@ -121,8 +121,9 @@ SGG_API int sgg_linear_backward(const float *x, const float *w, const float *dy,
  * sgg_tc_split_weights: split[0:n] = hi(w), split[n:2n] = lo(w); call once per weight version.
  * sgg_tc_linear_forward: same contract as sgg_linear_forward but takes the split weight. K % 4 == 0. */
 SGG_API int sgg_tc_split_weights(const float *w, size_t n, float *split, void *stream);
+SGG_API size_t sgg_tc_linear_workspace_bytes(int M, int Nout, int K);   /* split-K partials (0 = none needed) */
 SGG_API int sgg_tc_linear_forward(const float *x, const float *w_split, const float *b, float *y,
-                          int M, int Nout, int K, int relu, void *stream);
+                          int M, int Nout, int K, int relu, void *ws, size_t ws_bytes, void *stream);
 
 /* ---- L1: 4096-d features -> obj_dists / rel_dists (rel_model_stanford.py:103-107
  * without roi_fmap*): obj_unary, relu(edge_unary), message_pass, obj_fc, rel_fc. */

@@ -62,7 +62,9 @@ SIGNATURES = {
                                  c_f, c_f, c_f, C.c_void_p, C.c_size_t, C.c_void_p]),
     'sgg_linear_forward': (C.c_int, [c_f, c_f, c_f, c_f, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     'sgg_tc_split_weights': (C.c_int, [c_f, C.c_size_t, c_f, C.c_void_p]),
-    'sgg_tc_linear_forward': (C.c_int, [c_f, c_f, c_f, c_f, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    'sgg_tc_linear_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    'sgg_tc_linear_forward': (C.c_int, [c_f, c_f, c_f, c_f, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t,
+                                        C.c_void_p]),
     'sgg_l1_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     'sgg_l1_forward': (C.c_int, [c_f, c_f, C.c_void_p, C.POINTER(HeadWeights), C.POINTER(MpWeights),
                                  C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,

@@ -8,8 +8,9 @@ int launch_gemm(const float *A, int lda, bool a_col, const float *B, int ldb, bo
                 int N, int K, bool accumulate, cudaStream_t st);
 size_t colsum_workspace_floats(int rows, int cols);
 int launch_colsum(const float *X, int ld, int rows, int cols, float *out, bool accumulate, float *ws, cudaStream_t st);
+size_t tc_linear_workspace_floats(int M, int Nout, int K);
 int tc_linear(const float *x, const float *w_split, const float *b, float *y, int M, int Nout, int K, int relu,
-              cudaStream_t st);
+              float *ws, cudaStream_t st);
 // mode 0 = INIT (h = 0), 1 = NODE (x = ctx, h = V), 2 = EDGE (h = Eh, gathered gi)
 int tc_gru(int mode, const float *x, const float *h, const float *w_ih_split, const float *w_hh_split,
            const float *b_ih, const float *b_hh, const float *P, const float *gates, const int *subj, const int *obj,

@@ -290,7 +290,7 @@ static int launch_gru(const GruArgs &a, cudaStream_t st) {
 }
 
 struct MpScratch {
-  float *V[2], *Eh[2], *P, *a, *g, *ctx;
+  float *V[2], *Eh[2], *P, *a, *g, *ctx, *lin_ws;
 };
 
 static size_t mp_layout(MpScratch *s, void *ws, int N, int E, int H) {
@@ -301,6 +301,7 @@ static size_t mp_layout(MpScratch *s, void *ws, int N, int E, int H) {
   s->a = ar.take<float>(n1 * 4);
   s->g = ar.take<float>(e1 * 4);
   s->ctx = ar.take<float>(n1 * H);
+  s->lin_ws = ar.take<float>(tc_linear_workspace_floats(N, 3 * H, H) + 4);   // split-K partials of P = V W_ih^T
   return ar.off;
 }
 
@@ -379,7 +380,7 @@ int mp_forward(const float *obj_rep, const float *rel_rep, const void *graph_ws,
           w->gate_b[3], s.a, g.subj, g.obj, s.g);
       SGG_RETURN_IF_LAUNCH_FAILED("k_gate_edge");
       if (w->edge_w_ih_split) {
-        if ((rc = tc_linear(V, w->edge_w_ih_split, nullptr, s.P, N, 3 * H, H, 0, st))) return rc;
+        if ((rc = tc_linear(V, w->edge_w_ih_split, nullptr, s.P, N, 3 * H, H, 0, s.lin_ws, st))) return rc;
       } else if ((rc = launch_linear(V, w->edge_w_ih, nullptr, s.P, N, 3 * H, H, 0, st))) return rc;
     }
     if (N > 0) {
@@ -437,12 +438,17 @@ extern "C" int sgg_mp_forward(const float *obj_rep, const float *rel_rep, const 
 
 // ---- L1: 4096-d features -> dists (rel_model_stanford.py:103-107 without roi_fmap*) ----
 namespace sgg {
-struct L1Scratch { float *obj_rep, *rel_rep, *V, *Eh; void *mp; size_t mp_bytes; };
-static size_t l1_layout(L1Scratch *s, void *ws, int N, int E, int H) {
+struct L1Scratch { float *obj_rep, *rel_rep, *V, *Eh, *lin_ws; void *mp; size_t mp_bytes; };
+static size_t l1_layout(L1Scratch *s, void *ws, int N, int E, int H, int D = 4096, int n_cls = 151, int n_rel = 51) {
   SggArena ar(ws, (size_t)-1);
   const size_t n1 = N > 0 ? N : 1, e1 = E > 0 ? E : 1;
   s->obj_rep = ar.take<float>(n1 * H); s->rel_rep = ar.take<float>(e1 * H);
   s->V = ar.take<float>(n1 * H); s->Eh = ar.take<float>(e1 * H);
+  size_t lw = tc_linear_workspace_floats(N, H, D);
+  const size_t c2 = tc_linear_workspace_floats(E, H, D), c3 = tc_linear_workspace_floats(N, n_cls, H),
+               c4 = tc_linear_workspace_floats(E, n_rel, H);
+  lw = lw > c2 ? lw : c2; lw = lw > c3 ? lw : c3; lw = lw > c4 ? lw : c4;
+  s->lin_ws = ar.take<float>(lw + 4);
   s->mp_bytes = mp_workspace_bytes(N, E, H);
   s->mp = ar.take<char>(s->mp_bytes);
   return ar.off;
@@ -468,7 +474,7 @@ extern "C" int sgg_l1_forward(const float *obj_feat, const float *edge_feat, con
   int rc;
   auto lin = [&](const float *x, const float *wt, const float *wsplit, const float *b, float *y, int M, int No, int K,
                  int relu) -> int {
-    return wsplit ? sgg::tc_linear(x, wsplit, b, y, M, No, K, relu, st) : sgg::launch_linear(x, wt, b, y, M, No, K, relu, st);
+    return wsplit ? sgg::tc_linear(x, wsplit, b, y, M, No, K, relu, s.lin_ws, st) : sgg::launch_linear(x, wt, b, y, M, No, K, relu, st);
   };
   if ((rc = lin(obj_feat, hw->obj_unary_w, hw->obj_unary_w_split, hw->obj_unary_b, s.obj_rep, N, H, D, 0))) return rc;
   if ((rc = lin(edge_feat, hw->edge_unary_w, hw->edge_unary_w_split, hw->edge_unary_b, s.rel_rep, E, H, D, 1))) return rc;

@@ -103,10 +103,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
-// K-major SWIZZLE_128B tile, rows of 128 bytes: SBO = 1024, LBO = 0, version 1, layout 2
-__device__ __forceinline__ uint64_t make_sdesc_sw128(const void *smem_tile) {
+// K-major swizzled tile whose rows are exactly one swizzle span (BKF floats): SBO = 8 rows x span, LBO = 0,
+// version 1; layout 2 = SWIZZLE_128B (BKF = 32), 4 = SWIZZLE_64B (BKF = 16)
+template <int BKF>
+__device__ __forceinline__ uint64_t make_sdesc(const void *smem_tile) {
   const uint64_t addr = (uint64_t)((smem_u32(smem_tile) & 0x3FFFF) >> 4);
-  return addr | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+  constexpr uint64_t sbo = (uint64_t)((8 * BKF * 4) >> 4);
+  constexpr uint64_t layout = BKF == 32 ? 2ull : 4ull;
+  return addr | (sbo << 32) | (1ull << 46) | (layout << 61);
 }
 __device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                             uint32_t accumulate) {

@@ -151,7 +151,8 @@ class RelModelBase(nn.Module):
             imgs.append(x[i].to(dev).squeeze())
             org_sizes.append(tuple(x[i].shape[-2:]))
         images, targets = self.detector.transform(imgs, targets)
-        fmaps = self.detector.backbone(images.tensors)
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):     # fp32 parity with the reference (1e-4)
+            fmaps = self.detector.backbone(images.tensors)
         if isinstance(fmaps, torch.Tensor):
             fmaps = OrderedDict([('0', fmaps)])
         if self.mode != 'sgdet':

@@ -161,7 +161,8 @@ def message_pass(rel_rep, obj_rep, graph, params, mp_iter=3, save_states=False):
     dev = obj_rep.device
     V = torch.empty((N, H), dtype=torch.float32, device=dev)
     Eo = torch.empty((E, H), dtype=torch.float32, device=dev)
-    saved = torch.empty(((mp_iter + 1) * (N + E) * H,), dtype=torch.float32, device=dev) if save_states else None
+    saved = (torch.empty((lib.sgg_mp_tape_bytes(N, E, H, mp_iter) // 4,), dtype=torch.float32, device=dev)
+             if save_states else None)   # tape: states first, then caches (include/sgg_b200.h)
     nbytes = lib.sgg_mp_workspace_bytes(N, E, H, mp_iter)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
     check(lib.sgg_mp_forward(_ptr(obj_rep), _ptr(rel_rep), _ptr(graph.ws), C.byref(w), N, E, H, mp_iter,
@@ -184,8 +185,10 @@ def linear(x, weight, bias=None, relu=False):
     y = torch.empty((M, Nout), dtype=torch.float32, device=x.device)
     if _MODE['gemm'] == 'tc' and K % 4 == 0:
         sp = split_weight(weight)
+        nb = lib.sgg_tc_linear_workspace_bytes(M, Nout, K)
+        ws = torch.empty(nb, dtype=torch.uint8, device=x.device) if nb else None
         check(lib.sgg_tc_linear_forward(_ptr(x), _ptr(sp), _ptr(bias), _ptr(y), M, Nout, K, 1 if relu else 0,
-                                        _stream()), 'sgg_tc_linear_forward')
+                                        _ptr(ws), nb, _stream()), 'sgg_tc_linear_forward')
     else:
         check(lib.sgg_linear_forward(_ptr(x), _ptr(weight), _ptr(bias), _ptr(y), M, Nout, K, 1 if relu else 0,
                                      _stream()), 'sgg_linear_forward')

@@ -145,3 +145,23 @@ def digest(*arrays):
     for a in arrays:
         h.update(np.ascontiguousarray(a).tobytes())
     return h.hexdigest()[:16]
+
+
+def synth_backbone_params(model_state_shapes, seed):
+    """He-scaled weights for the frozen detector backbone (VGG16 conv stack): keeps activations O(1) so the
+    L3 fixtures exercise a realistic feature map.  ``model_state_shapes``: {key: shape} of detector.backbone.*"""
+    rng = np.random.default_rng(seed + 2750159)
+    p = {}
+    for k in sorted(model_state_shapes):
+        shp = tuple(model_state_shapes[k])
+        if k.endswith('.weight'):
+            fan_in = int(np.prod(shp[1:]))
+            p[k] = (rng.standard_normal(shp, dtype=np.float32) * np.float32(np.sqrt(2.0 / fan_in))).astype(np.float32)
+        else:
+            p[k] = _u(rng, shp, 0.05)
+    return p
+
+
+def synth_images(sizes, seed):
+    rng = np.random.default_rng(seed + 86028121)
+    return [rng.random((3, h, w), dtype=np.float32) for (h, w) in sizes]

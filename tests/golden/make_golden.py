@@ -235,6 +235,36 @@ def main():
         save('roi_align', seed=seed, rois=g['rois'], union_inds=g['rel_inds'][:, 1:],
              digest=synth.digest(fmap), node_feat=nf.numpy(), edge_feat=ef.numpy())
 
+    # ---------------- state-dict contract ------------------------------------------------
+    if want('state_dict'):
+        import json
+        sd = model.state_dict()
+        with open(os.path.join(args.out, 'state_dict_keys.json'), 'w') as f:
+            json.dump({k: list(v.shape) for k, v in sd.items()}, f, indent=0, sort_keys=True)
+        print('wrote state_dict_keys.json', len(sd))
+
+    # ---------------- L3: forward(batch) eval, predcls + sgcls ------------------------------
+    if want('l3_forward'):
+        seed = 8235
+        sizes, boxes, gt_classes, gt_rels = l3_case(seed)
+        imgs = synth.synth_images(sizes, seed)
+        p = synth.synth_params(seed, level='l2', scale=1.0)
+        shapes = {k: tuple(v.shape) for k, v in model.state_dict().items() if k.startswith('detector.backbone.')}
+        p.update(synth.synth_backbone_params(shapes, seed))
+        load_params(model, p)
+        model.mp_iter = 3
+        out = dict(seed=seed, digest=synth.digest(imgs[0], imgs[1], boxes, p['detector.backbone.0.weight']))
+        for mode in ('predcls', 'sgcls'):
+            model.mode = mode
+            model.eval()
+            batch = [([tt(i)[None] for i in imgs], None, 0, tt(boxes), tt(gt_classes), tt(gt_rels), None, ['a', 'b'])]
+            with torch.no_grad():
+                b, oc, os_, rels, ps = model(batch)
+            out.update({mode + '_boxes': b, mode + '_obj_classes': oc, mode + '_obj_scores': os_,
+                        mode + '_rels': rels, mode + '_pred_scores': ps})
+        model.mode = 'predcls'
+        save('l3_forward', **out)
+
     # ---------------- L2: predict ---------------------------------------------
     if want('l2_predict'):
         seed = 6235
@@ -248,6 +278,17 @@ def main():
             od, rd = model.predict(tt(nfe), tt(efe), tt(g['rel_inds']), tt(g['rois']), None)
         save('l2_predict', seed=seed, N=N, E=E, digest=synth.digest(nfe, efe, p['roi_fmap.1.0.weight'][:64]),
              obj_dists=od.numpy(), rel_dists=rd.numpy())
+
+
+def l3_case(seed=8235):
+    """Shared by make_golden and the tests: 2 images (one non-square), GT boxes inside the image."""
+    sizes = [(592, 592), (400, 592)]
+    g = synth.synth_graph(2, 7, 10, seed)
+    boxes = g['boxes'].copy()
+    n0 = int((g['gt_classes'][:, 0] == 0).sum())
+    boxes[n0:, [1, 3]] *= np.float32(400.0 / 592.0)            # second image is 400 px high
+    boxes[n0:, 3] = np.maximum(boxes[n0:, 3], boxes[n0:, 1] + 8)
+    return sizes, boxes.astype(np.float32), g['gt_classes'], g['gt_rels']
 
 
 if __name__ == '__main__':

@@ -1,0 +1,114 @@
+"""CPU: drop-in contract of the model class and host-side logic (no CUDA compute)."""
+import json
+import os
+import numpy as np
+import pytest
+import torch
+
+from tests import cases
+from sgg_b200 import host
+
+
+class FakeData:
+    ind_to_classes = ['__background__'] + ['c%d' % i for i in range(150)]
+    ind_to_predicates = ['__background__'] + ['p%d' % i for i in range(50)]
+
+
+@pytest.fixture(scope='module')
+def model():
+    from sgg_b200.model import RelModelStanford
+    return RelModelStanford(train_data=FakeData(), mode='predcls')
+
+
+def test_state_dict_keys_and_shapes_match_reference(model):
+    ref = json.load(open(os.path.join(cases.GOLDEN, 'state_dict_keys.json')))
+    mine = {k: list(v.shape) for k, v in model.state_dict().items()}
+    assert sorted(mine) == sorted(ref)
+    for k in ref:
+        assert mine[k] == ref[k], k
+    # optimizer grouping of lib/pytorch_misc.py:135-142: names starting with roi_fmap go to the lr/10 group
+    fc = [n for n, p in model.named_parameters() if n.startswith('roi_fmap')]
+    assert len(fc) == 8
+    assert sum(p.numel() for n, p in model.named_parameters() if not n.startswith('detector.')) == 247753678
+
+
+def test_plugin_surface(model):
+    for attr in ('detector', 'edge_dim', 'pool_sz', 'fmap_sz', 'mode', 'hidden_dim', 'mp_iter', 'roi_fmap',
+                 'roi_fmap_obj', 'union_boxes', 'roi_pool'):
+        assert hasattr(model, attr)
+    assert (model.edge_dim, model.pool_sz, model.fmap_sz, model.hidden_dim, model.mp_iter) == (512, 7, 38, 512, 3)
+    for fn in ('forward', 'predict', 'message_pass', 'node_edge_features', 'get_rel_inds', 'get_scaled_boxes',
+               'set_box_score_thresh', 'faster_rcnn', 'gt_labels'):
+        assert callable(getattr(model, fn))
+    with pytest.raises(AssertionError):
+        model([1, 2])                                   # len(batch) != 1 (rel_model_stanford.py:121)
+    model.set_box_score_thresh(0.05)
+    assert model.detector.roi_heads.score_thresh == 0.05
+
+
+def test_get_rel_inds_eval_and_train():
+    im = torch.tensor([0, 0, 0, 1, 1])
+    r = host.get_rel_inds(im)
+    from oracle import imp_numpy as O
+    assert np.array_equal(r.numpy(), O.get_rel_inds_eval(im.numpy()))
+    labels = torch.tensor([[0, 0, 1, 5], [0, 1, 2, 0]])
+    assert host.get_rel_inds(im, labels, training=True).tolist() == [[0, 0, 1], [0, 1, 2]]
+    boxes = torch.tensor([[0, 0, 10, 10], [5, 5, 20, 20], [50, 50, 60, 60], [0, 0, 5, 5], [1, 1, 3, 3]], dtype=torch.float32)
+    r2 = host.get_rel_inds(im, box_priors=boxes, require_overlap=True)
+    assert r2.tolist() == [[0, 0, 1], [0, 1, 0], [1, 3, 4], [1, 4, 3]]
+
+
+def test_filter_dets_matches_oracle():
+    from oracle import imp_numpy as O
+    rng = np.random.default_rng(0)
+    N, E = 6, 30
+    boxes = rng.random((N, 4)).astype(np.float32); scores = rng.random(N).astype(np.float32)
+    cls = rng.integers(1, 151, N); rel = np.stack((rng.integers(0, N, E), rng.integers(0, N, E)), 1)
+    ps = O.softmax(rng.standard_normal((E, 51)).astype(np.float32))
+    out = host.filter_dets(torch.from_numpy(boxes), torch.from_numpy(scores), torch.from_numpy(cls),
+                           torch.from_numpy(rel), torch.from_numpy(ps))
+    ref = O.filter_dets(boxes, scores, cls, rel, ps)
+    for a, b in zip(out, ref):
+        assert np.allclose(a, b)
+    with pytest.raises(ValueError):
+        host.filter_dets(torch.zeros(2, 3, 4), torch.zeros(2), torch.zeros(2), torch.zeros(1, 2).long(), torch.zeros(1, 51))
+
+
+def test_proposal_assignments_gtbox_semantics():
+    from sgg_b200 import synth
+    g = synth.synth_graph(3, 6, 10, 5)
+    rois = torch.from_numpy(g['rois']); gt_cls = torch.from_numpy(g['gt_classes']); gt_rels = torch.from_numpy(g['gt_rels'])
+    _, labels, rl = host.proposal_assignments_gtbox(rois, rois[:, 1:], gt_cls, gt_rels, 0, 1024)
+    n = rois.shape[0]
+    assert rl.shape[0] == 3 * 6 * 5                       # every ordered same-image pair exactly once
+    key = rl[:, 0] * n * n + rl[:, 1] * n + rl[:, 2]
+    assert torch.all(key[1:] > key[:-1])                  # sorted by (img, subj, obj), no duplicates
+    assert torch.all(gt_cls[rl[:, 1], 0] == rl[:, 0]) and torch.all(gt_cls[rl[:, 2], 0] == rl[:, 0])
+    assert int((rl[:, 3] > 0).sum()) == gt_rels.shape[0]
+    fg = rl[rl[:, 3] > 0]
+    first = torch.tensor([0, 6, 12])
+    want = sorted((int(r[0]), int(r[1] + first[r[0]]), int(r[2] + first[r[0]]), int(r[3])) for r in gt_rels)
+    assert sorted(map(tuple, fg.tolist())) == want
+    # budget: RELS_PER_IMG * num_im total, FG capped at 25 %
+    np.random.seed(0)
+    _, _, rl2 = host.proposal_assignments_gtbox(rois, rois[:, 1:], gt_cls, gt_rels, 0, 8)
+    assert rl2.shape[0] == 24 and int((rl2[:, 3] > 0).sum()) == 6
+
+
+def test_result_container():
+    r = host.Result(rel_dists=torch.zeros(2), od_obj_dists=None)
+    assert hasattr(r, 'rel_dists') and not hasattr(r, 'od_obj_dists') and not r.is_none()
+    with pytest.raises(TypeError):
+        host.Result(bogus=1)
+
+
+def test_rel_assignments_shapes():
+    np.random.seed(1)
+    boxes = torch.tensor([[0, 0, 50, 50], [10, 10, 60, 60], [40, 40, 90, 90], [0, 0, 30, 30], [20, 20, 80, 80]], dtype=torch.float32)
+    im_inds = torch.tensor([0, 0, 0, 1, 1])
+    labels = torch.tensor([3, 5, 7, 2, 9])
+    gt_classes = torch.stack((im_inds, labels), 1)
+    gt_rels = torch.tensor([[0, 0, 1, 4], [1, 0, 1, 6]])
+    out = host.rel_assignments(im_inds, boxes, labels, boxes, gt_classes, gt_rels, 0, num_sample_per_gt=1)
+    assert out.shape[1] == 4 and out.dtype == torch.int64
+    assert [0, 0, 1, 4] in out.tolist() and [1, 3, 4, 6] in out.tolist()
