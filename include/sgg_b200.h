@@ -106,7 +106,8 @@ SGG_API int sgg_mp_backward(const float *obj_rep, const float *rel_rep, const vo
 
 /* ---- a5/a6: nn.Linear (+ReLU): y[M,Nout] = act(x[M,K] @ w[Nout,K]^T + b) ----
  * (obj_unary / edge_unary / obj_fc / rel_fc rel_model_stanford.py:29-33,
- *  roi_fmap / roi_fmap_obj rel_model_base.py:110-111).  b nullable. K % 16 == 0. */
+ *  roi_fmap / roi_fmap_obj rel_model_base.py:110-111).  b nullable.  Any K (unaligned
+ *  operands fall back to scalar loads). */
 SGG_API int sgg_linear_forward(const float *x, const float *w, const float *b, float *y,
                        int M, int Nout, int K, int relu, void *stream);
 

@@ -38,3 +38,29 @@ extern "C" int sgg_device_info(int out[4]) {
   SGG_CUDA_TRY(cudaDeviceGetAttribute(&out[3], cudaDevAttrL2CacheSize, dev));
   return 0;
 }
+
+// ---- fork/join helper: one side stream + a ring of timing-less events per process (capturable) ----
+namespace sgg {
+cudaStream_t side_stream() {
+  static cudaStream_t s = nullptr;
+  if (!s && cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) s = nullptr;
+  return s;
+}
+cudaEvent_t next_event() {
+  static cudaEvent_t ring[256];
+  static bool init = false;
+  static unsigned idx = 0;
+  if (!init) {
+    for (int i = 0; i < 256; ++i) cudaEventCreateWithFlags(&ring[i], cudaEventDisableTiming);
+    init = true;
+  }
+  return ring[(idx++) & 255];
+}
+// order: everything enqueued on `from` so far happens-before whatever is enqueued on `to` next
+int stream_order(cudaStream_t from, cudaStream_t to) {
+  cudaEvent_t e = next_event();
+  SGG_CUDA_TRY(cudaEventRecord(e, from));
+  SGG_CUDA_TRY(cudaStreamWaitEvent(to, e, 0));
+  return 0;
+}
+}  // namespace sgg

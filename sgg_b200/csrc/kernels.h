@@ -2,6 +2,8 @@
 #pragma once
 #include "common.cuh"
 namespace sgg {
+cudaStream_t side_stream();
+int stream_order(cudaStream_t from, cudaStream_t to);
 int launch_linear(const float *x, const float *w, const float *b, float *y, int M, int Nout, int K, int relu,
                   cudaStream_t st);
 int launch_gemm(const float *A, int lda, bool a_col, const float *B, int ldb, bool b_col, float *C, int ldc, int M,

@@ -85,7 +85,7 @@ static int launch_linear_t(const float *x, const float *w, const float *b, float
 int launch_linear(const float *x, const float *w, const float *b, float *y, int M, int Nout, int K, int relu,
                   cudaStream_t st) {
   if (M <= 0 || Nout <= 0) return 0;
-  if (K <= 0 || (K % BK) != 0) return sgg_set_err(SGG_E_BADARG, "linear: K=%d must be a positive multiple of %d", K, BK);
+  if (K <= 0) return sgg_set_err(SGG_E_BADARG, "linear: K=%d must be positive", K);
   const int sms = sgg_num_sms();
   int best_bm = 64, best_nw = 1;
   double best = 1e30;

@@ -322,9 +322,13 @@ MpTape mp_tape_view(float *base, int N, int E, int H, int T) {
   return t;
 }
 
+// Two-stream schedule: the object branch (P = V W_ih^T, ctx, node GRU) runs on a side stream concurrently with the
+// edge branch (gates, edge GRU) on the caller's stream; they exchange exactly what the data flow needs (V, gates, P)
+// through events, which CUDA-graph capture turns into graph edges.  `obj_on_side`: obj_rep was produced on the side
+// stream (L1 entry) so the node-side initial step may start there immediately.
 int mp_forward(const float *obj_rep, const float *rel_rep, const void *graph_ws, const sgg_mp_weights *w, int N,
                int E, int H, int T, float *V_out, float *E_out, float *saved, void *ws, size_t ws_bytes,
-               cudaStream_t st) {
+               cudaStream_t st, bool obj_on_side) {
   if (N < 0 || E < 0 || T < 0 || H <= 0 || (H % BN) != 0)
     return sgg_set_err(SGG_E_BADARG, "mp_forward: N=%d E=%d H=%d T=%d (H must be a multiple of %d)", N, E, H, T, BN);
   if (!w || !graph_ws || (N > 0 && (!obj_rep || !V_out)) || (E > 0 && (!rel_rep || !E_out)))
@@ -348,13 +352,17 @@ int mp_forward(const float *obj_rep, const float *rel_rep, const void *graph_ws,
     return it == T ? E_out : s.Eh[it & 1];
   };
   int rc;
+  cudaStream_t sb = side_stream();
+  const bool par = sb != nullptr && N > 0 && E > 0;
+  cudaStream_t sn = par ? sb : st;                 // stream of the object branch
+  if (par && !obj_on_side && (rc = stream_order(st, sb))) return rc;
   {  // hx = 0 initial step (:68-72)
     GruArgs a{}; a.x = obj_rep; a.h = nullptr; a.w_ih = w->node_w_ih; a.w_hh = w->node_w_hh; a.b_ih = w->node_b_ih;
     a.b_hh = w->node_b_hh; a.out = vbuf(0); a.cache = cacheV(0); a.M = N; a.H = H;
     if (w->node_w_ih_split) {
       if ((rc = tc_gru(0, obj_rep, nullptr, w->node_w_ih_split, nullptr, w->node_b_ih, w->node_b_hh, nullptr, nullptr,
-                       nullptr, nullptr, vbuf(0), cacheV(0), N, H, st))) return rc;
-    } else if ((rc = launch_gru<GRU_INIT>(a, st))) return rc;
+                       nullptr, nullptr, vbuf(0), cacheV(0), N, H, sn))) return rc;
+    } else if ((rc = launch_gru<GRU_INIT>(a, sn))) return rc;
     GruArgs b{}; b.x = rel_rep; b.h = nullptr; b.w_ih = w->edge_w_ih; b.w_hh = w->edge_w_hh; b.b_ih = w->edge_b_ih;
     b.b_hh = w->edge_b_hh; b.out = ebuf(0); b.cache = cacheE(0); b.M = E; b.H = H;
     if (w->edge_w_ih_split) {
@@ -369,6 +377,10 @@ int mp_forward(const float *obj_rep, const float *rel_rep, const void *graph_ws,
       s.ctx = tape.ctx + (size_t)it * N * H;
       s.P = tape.P + (size_t)it * N * 3 * H;
     }
+    if (par) {     // iteration boundary: both branches see each other's previous-iteration results / reads
+      if ((rc = stream_order(sb, st))) return rc;     // V_it ready for the gates; old gates / ctx no longer read
+      if ((rc = stream_order(st, sb))) return rc;     // Eh_it ready; previous edge GRU no longer reads P
+    }
     if (N > 0) {
       k_gate_node<<<(N * 32 + 255) / 256, 256, 0, st>>>(V, N, H, w->gate_w[0], w->gate_w[1], w->gate_w[2],
                                                         w->gate_w[3], s.a);
@@ -380,11 +392,15 @@ int mp_forward(const float *obj_rep, const float *rel_rep, const void *graph_ws,
           w->gate_b[3], s.a, g.subj, g.obj, s.g);
       SGG_RETURN_IF_LAUNCH_FAILED("k_gate_edge");
       if (w->edge_w_ih_split) {
-        if ((rc = tc_linear(V, w->edge_w_ih_split, nullptr, s.P, N, 3 * H, H, 0, s.lin_ws, st))) return rc;
-      } else if ((rc = launch_linear(V, w->edge_w_ih, nullptr, s.P, N, 3 * H, H, 0, st))) return rc;
+        if ((rc = tc_linear(V, w->edge_w_ih_split, nullptr, s.P, N, 3 * H, H, 0, s.lin_ws, sn))) return rc;
+      } else if ((rc = launch_linear(V, w->edge_w_ih, nullptr, s.P, N, 3 * H, H, 0, sn))) return rc;
+    }
+    if (par) {
+      if ((rc = stream_order(st, sb))) return rc;     // gates -> ctx
+      if ((rc = stream_order(sb, st))) return rc;     // P -> edge GRU
     }
     if (N > 0) {
-      k_ctx<<<N, (H / 4 < 128 ? H / 4 : 128), 0, st>>>(Eh, s.g, g.out_ptr, g.out_idx, g.in_ptr, g.in_idx, H, s.ctx);
+      k_ctx<<<N, (H / 4 < 128 ? H / 4 : 128), 0, sn>>>(Eh, s.g, g.out_ptr, g.out_idx, g.in_ptr, g.in_idx, H, s.ctx);
       SGG_RETURN_IF_LAUNCH_FAILED("k_ctx");
     }
     {
@@ -402,10 +418,11 @@ int mp_forward(const float *obj_rep, const float *rel_rep, const void *graph_ws,
       a.b_hh = w->node_b_hh; a.out = vbuf(it + 1); a.cache = cacheV(it + 1); a.M = N; a.H = H;
       if (w->node_w_ih_split && w->node_w_hh_split) {
         if ((rc = tc_gru(1, s.ctx, V, w->node_w_ih_split, w->node_w_hh_split, w->node_b_ih, w->node_b_hh, nullptr,
-                         nullptr, nullptr, nullptr, vbuf(it + 1), cacheV(it + 1), N, H, st))) return rc;
-      } else if ((rc = launch_gru<GRU_NODE>(a, st))) return rc;
+                         nullptr, nullptr, nullptr, vbuf(it + 1), cacheV(it + 1), N, H, sn))) return rc;
+      } else if ((rc = launch_gru<GRU_NODE>(a, sn))) return rc;
     }
   }
+  if (par && (rc = stream_order(sb, st))) return rc;    // join: V_T (and everything on the side stream) -> caller's stream
   if (saved) {   // outputs are the last saved slot
     if (N > 0) SGG_CUDA_TRY(cudaMemcpyAsync(V_out, vbuf(T), vN * sizeof(float), cudaMemcpyDeviceToDevice, st));
     if (E > 0) SGG_CUDA_TRY(cudaMemcpyAsync(E_out, ebuf(T), eN * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -433,22 +450,21 @@ extern "C" int sgg_mp_forward(const float *obj_rep, const float *rel_rep, const 
                               const sgg_mp_weights *w, int N, int E, int H, int T, float *V_out, float *E_out,
                               float *saved, void *ws, size_t ws_bytes, void *stream) {
   return sgg::mp_forward(obj_rep, rel_rep, graph_ws, w, N, E, H, T, V_out, E_out, saved, ws, ws_bytes,
-                         (cudaStream_t)stream);
+                         (cudaStream_t)stream, false);
 }
 
 // ---- L1: 4096-d features -> dists (rel_model_stanford.py:103-107 without roi_fmap*) ----
 namespace sgg {
-struct L1Scratch { float *obj_rep, *rel_rep, *V, *Eh, *lin_ws; void *mp; size_t mp_bytes; };
+struct L1Scratch { float *obj_rep, *rel_rep, *V, *Eh, *ws_obj, *ws_edge; void *mp; size_t mp_bytes; };
 static size_t l1_layout(L1Scratch *s, void *ws, int N, int E, int H, int D = 4096, int n_cls = 151, int n_rel = 51) {
   SggArena ar(ws, (size_t)-1);
   const size_t n1 = N > 0 ? N : 1, e1 = E > 0 ? E : 1;
   s->obj_rep = ar.take<float>(n1 * H); s->rel_rep = ar.take<float>(e1 * H);
   s->V = ar.take<float>(n1 * H); s->Eh = ar.take<float>(e1 * H);
-  size_t lw = tc_linear_workspace_floats(N, H, D);
-  const size_t c2 = tc_linear_workspace_floats(E, H, D), c3 = tc_linear_workspace_floats(N, n_cls, H),
-               c4 = tc_linear_workspace_floats(E, n_rel, H);
-  lw = lw > c2 ? lw : c2; lw = lw > c3 ? lw : c3; lw = lw > c4 ? lw : c4;
-  s->lin_ws = ar.take<float>(lw + 4);
+  const size_t o1 = tc_linear_workspace_floats(N, H, D), o2 = tc_linear_workspace_floats(N, n_cls, H);
+  const size_t e1w = tc_linear_workspace_floats(E, H, D), e2w = tc_linear_workspace_floats(E, n_rel, H);
+  s->ws_obj = ar.take<float>((o1 > o2 ? o1 : o2) + 4);      // object-branch and edge-branch linears may overlap
+  s->ws_edge = ar.take<float>((e1w > e2w ? e1w : e2w) + 4);
   s->mp_bytes = mp_workspace_bytes(N, E, H);
   s->mp = ar.take<char>(s->mp_bytes);
   return ar.off;
@@ -473,14 +489,21 @@ extern "C" int sgg_l1_forward(const float *obj_feat, const float *edge_feat, con
   cudaStream_t st = (cudaStream_t)stream;
   int rc;
   auto lin = [&](const float *x, const float *wt, const float *wsplit, const float *b, float *y, int M, int No, int K,
-                 int relu) -> int {
-    return wsplit ? sgg::tc_linear(x, wsplit, b, y, M, No, K, relu, s.lin_ws, st) : sgg::launch_linear(x, wt, b, y, M, No, K, relu, st);
+                 int relu, float *lws, cudaStream_t s2) -> int {
+    return wsplit ? sgg::tc_linear(x, wsplit, b, y, M, No, K, relu, lws, s2) : sgg::launch_linear(x, wt, b, y, M, No, K, relu, s2);
   };
-  if ((rc = lin(obj_feat, hw->obj_unary_w, hw->obj_unary_w_split, hw->obj_unary_b, s.obj_rep, N, H, D, 0))) return rc;
-  if ((rc = lin(edge_feat, hw->edge_unary_w, hw->edge_unary_w_split, hw->edge_unary_b, s.rel_rep, E, H, D, 1))) return rc;
-  if ((rc = sgg::mp_forward(s.obj_rep, s.rel_rep, graph_ws, w, N, E, H, T, s.V, s.Eh, nullptr, s.mp, s.mp_bytes, st)))
+  cudaStream_t sb = sgg::side_stream();
+  const bool par = sb != nullptr && N > 0 && E > 0;
+  cudaStream_t sn = par ? sb : st;
+  if (par && (rc = sgg::stream_order(st, sb))) return rc;         // fork: inputs / graph are ready on `st`
+  if ((rc = lin(obj_feat, hw->obj_unary_w, hw->obj_unary_w_split, hw->obj_unary_b, s.obj_rep, N, H, D, 0, s.ws_obj, sn))) return rc;
+  if ((rc = lin(edge_feat, hw->edge_unary_w, hw->edge_unary_w_split, hw->edge_unary_b, s.rel_rep, E, H, D, 1, s.ws_edge, st))) return rc;
+  if ((rc = sgg::mp_forward(s.obj_rep, s.rel_rep, graph_ws, w, N, E, H, T, s.V, s.Eh, nullptr, s.mp, s.mp_bytes, st, par)))
     return rc;
-  if ((rc = lin(s.V, hw->obj_fc_w, hw->obj_fc_w_split, hw->obj_fc_b, obj_dists, N, n_cls, H, 0))) return rc;
-  if ((rc = lin(s.Eh, hw->rel_fc_w, hw->rel_fc_w_split, hw->rel_fc_b, rel_dists, E, n_rel, H, 0))) return rc;
+  // heads: mp_forward joined the side stream into `st`; fork again for the two classifiers
+  if (par && (rc = sgg::stream_order(st, sb))) return rc;
+  if ((rc = lin(s.V, hw->obj_fc_w, hw->obj_fc_w_split, hw->obj_fc_b, obj_dists, N, n_cls, H, 0, s.ws_obj, sn))) return rc;
+  if ((rc = lin(s.Eh, hw->rel_fc_w, hw->rel_fc_w_split, hw->rel_fc_b, rel_dists, E, n_rel, H, 0, s.ws_edge, st))) return rc;
+  if (par && (rc = sgg::stream_order(sb, st))) return rc;
   return 0;
 }

@@ -209,6 +209,31 @@ def rel_assignments(im_inds, rpn_rois, roi_gtlabels, gt_boxes, gt_classes, gt_re
     return torch.from_numpy(np.concatenate(out, 0)).to(dev)
 
 
+def dataset_counts(train_data, must_overlap=True):
+    """Relation statistics for the frequency baseline (lib/get_dataset_counts.py:10-66): fg[o1,o2,pred] counts the
+    annotated triples; bg[o1,o2] counts ordered pairs of (overlapping, if ``must_overlap``; all pairs when an image has
+    no overlapping boxes) GT boxes.  ``train_data`` exposes num_classes, num_predicates and per-image lists
+    gt_classes / relationships / gt_boxes like the reference's VG dataset.  Vectorised with np.add.at."""
+    C, R = train_data.num_classes, train_data.num_predicates
+    fg = np.zeros((C, C, R), dtype=np.int64)
+    bg = np.zeros((C, C), dtype=np.int64)
+    for i in range(len(train_data)):
+        cls = np.asarray(train_data.gt_classes[i])
+        rels = np.asarray(train_data.relationships[i])
+        boxes = torch.as_tensor(np.asarray(train_data.gt_boxes[i]), dtype=torch.float64)
+        if rels.size:
+            np.add.at(fg, (cls[rels[:, 0]], cls[rels[:, 1]], rels[:, 2]), 1)
+        n = cls.shape[0]
+        pairs = ~np.eye(n, dtype=bool)
+        if must_overlap:
+            ov = (box_iou(boxes, boxes) > 0).numpy() & pairs
+            if ov.any():
+                pairs = ov
+        a, b = np.nonzero(pairs)
+        np.add.at(bg, (cls[a], cls[b]), 1)
+    return fg, bg
+
+
 class FrequencyBias(torch.nn.Module):
     """log P(pred | subj, obj) lookup added to rel_dists (lib/sparse_targets.py:7-33).
     Built from (fg_matrix [C,C,R], bg_matrix [C,C]) count arrays — the caller computes them from its

@@ -118,9 +118,7 @@ class RelModelBase(nn.Module):
         self.union_boxes = UnionBoxesAndFeats(pooling_size=self.pool_sz, stride=self.stride, dim=self.edge_dim,
                                               edge_model=edge_model)
         if self.use_bias:
-            fg, bg = train_data.freq_counts() if hasattr(train_data, 'freq_counts') else (None, None)
-            if fg is None:
-                raise ValueError('use_bias=True needs train_data.freq_counts() -> (fg_matrix, bg_matrix)')
+            fg, bg = host.dataset_counts(train_data, must_overlap=True)       # lib/sparse_targets.py:16
             self.freq_bias = host.FrequencyBias(fg, bg)
 
     num_classes = property(lambda self: len(self.classes))

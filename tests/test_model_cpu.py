@@ -112,3 +112,21 @@ def test_rel_assignments_shapes():
     out = host.rel_assignments(im_inds, boxes, labels, boxes, gt_classes, gt_rels, 0, num_sample_per_gt=1)
     assert out.shape[1] == 4 and out.dtype == torch.int64
     assert [0, 0, 1, 4] in out.tolist() and [1, 3, 4, 6] in out.tolist()
+
+
+def test_frequency_bias_counts_and_lookup():
+    class DS:
+        num_classes, num_predicates = 5, 4
+        gt_classes = [np.array([1, 2, 3]), np.array([2, 2])]
+        relationships = [np.array([[0, 1, 2], [1, 2, 3]]), np.array([[0, 1, 1]])]
+        gt_boxes = [np.array([[0, 0, 10, 10], [5, 5, 20, 20], [50, 50, 60, 60]], float), np.array([[0, 0, 5, 5], [9, 9, 12, 12]], float)]
+        def __len__(self): return 2
+    fg, bg = host.dataset_counts(DS())
+    assert fg[1, 2, 2] == 1 and fg[2, 3, 3] == 1 and fg[2, 2, 1] == 1 and fg.sum() == 3
+    assert bg[1, 2] == 1 and bg[2, 1] == 1          # only the overlapping pair of image 0
+    assert bg[2, 2] == 2                            # image 1 has no overlap -> all ordered pairs
+    fb = host.FrequencyBias(fg, bg)
+    assert fb.obj_baseline.weight.shape == (25, 4)
+    out = fb.index_with_labels(torch.tensor([[1, 2], [2, 2]]))
+    ref = np.log((np.array([bg[1, 2] + 1, 0, 1, 0]) / (bg[1, 2] + 1 + 1)) + 1e-3)
+    assert np.allclose(out[0].detach().numpy(), ref, atol=1e-6)
