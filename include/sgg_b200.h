@@ -89,6 +89,13 @@ SGG_API int sgg_mp_forward(const float *obj_rep, const float *rel_rep, const voi
                    float *V_out, float *E_out, float *saved,
                    void *ws, size_t ws_bytes, void *stream);
 
+/* One edge-GRU update in isolation (rel_model_stanford.py:83 with the gathered, gate-scaled input of :76-81
+ * expressed through P = V W_ih^T [N,3H] and gates [E,4] = (g_sub, g_obj, g_out, g_in)):
+ * out[E,H] = GRUCell(g_sub P[s] + g_obj P[o] + b_ih, Eh W_hh^T + b_hh, Eh).  w_hh_split (nullable) selects tcgen05. */
+SGG_API int sgg_edge_gru_forward(const float *Eh, const float *P, const float *gates, const void *graph_ws,
+                         const float *w_ih, const float *w_hh, const float *w_hh_split,
+                         const float *b_ih, const float *b_hh, int N, int E, int H, float *out, void *stream);
+
 /* Backward of sgg_mp_forward (BPTT over the tape).  `grads` has the layout of the first 16 pointers of
  * sgg_mp_weights; every non-NULL buffer is ACCUMULATED into (+=).  d_obj_rep [N,H] / d_rel_rep [E,H]
  * (grads of the forward inputs) are overwritten, nullable.  Deterministic (no float atomics). */
@@ -177,12 +184,15 @@ SGG_API int sgg_geom_patches(const float *rois, const int64_t *union_inds, int64
 /* ---- a9: node_edge_features (rel_model_base.py:245-260): torchvision
  * roi_align(aligned=False, sampling_ratio=2, 7x7, scale 1/16) for objects and
  * for union boxes computed on the fly from (rois, union_inds).
- * fmap [B,C,Hf,Wf]; node_feat [N,C,7,7]; edge_feat [E,C,7,7] (either may be NULL). */
+ * fmap [B,C,Hf,Wf]; node_feat [N,C,7,7]; edge_feat [E,C,7,7] (either may be NULL).
+ * ws (nullable): sgg_node_edge_features_workspace_bytes => channel-last fast path (one CTA per RoI, coalesced
+ * corner fetches, contiguous output block); without it a per-element kernel on the NCHW map is used. */
+SGG_API size_t sgg_node_edge_features_workspace_bytes(int B, int C, int Hf, int Wf);
 SGG_API int sgg_node_edge_features(const float *fmap, int B, int C, int Hf, int Wf,
                            const float *rois, int N,
                            const int64_t *union_inds, int64_t row_stride, int col_subj, int col_obj, int E,
                            float spatial_scale, int pool, int sampling_ratio,
-                           float *node_feat, float *edge_feat, void *stream);
+                           float *node_feat, float *edge_feat, void *ws, size_t ws_bytes, void *stream);
 
 #ifdef __cplusplus
 }

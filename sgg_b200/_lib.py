@@ -50,6 +50,8 @@ SIGNATURES = {
     'sgg_graph_build': (C.c_int, [c_i64p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t,
                                   C.c_void_p]),
     'sgg_graph_check': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    'sgg_edge_gru_forward': (C.c_int, [c_f, c_f, c_f, C.c_void_p, c_f, c_f, c_f, c_f, c_f, C.c_int, C.c_int, C.c_int, c_f,
+                                       C.c_void_p]),
     'sgg_mp_tape_bytes': (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     'sgg_mp_backward_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     'sgg_mp_backward': (C.c_int, [c_f, c_f, C.c_void_p, C.POINTER(MpWeights), c_f, C.c_int, C.c_int, C.c_int, C.c_int,
@@ -75,9 +77,10 @@ SIGNATURES = {
     'sgg_union_geom_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int]),
     'sgg_union_geom_forward': (C.c_int, [c_f, c_i64p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int,
                                          C.POINTER(GeomWeights), c_f, c_f, C.c_void_p, C.c_size_t, C.c_void_p]),
+    'sgg_node_edge_features_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     'sgg_node_edge_features': (C.c_int, [c_f, C.c_int, C.c_int, C.c_int, C.c_int, c_f, C.c_int, c_i64p, C.c_int64,
                                          C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, c_f, c_f,
-                                         C.c_void_p]),
+                                         C.c_void_p, C.c_size_t, C.c_void_p]),
 }
 
 

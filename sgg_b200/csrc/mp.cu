@@ -352,7 +352,7 @@ int mp_forward(const float *obj_rep, const float *rel_rep, const void *graph_ws,
     return it == T ? E_out : s.Eh[it & 1];
   };
   int rc;
-  cudaStream_t sb = side_stream();
+  cudaStream_t sb = side_stream(st);
   const bool par = sb != nullptr && N > 0 && E > 0;
   cudaStream_t sn = par ? sb : st;                 // stream of the object branch
   if (par && !obj_on_side && (rc = stream_order(st, sb))) return rc;
@@ -437,6 +437,23 @@ size_t mp_workspace_bytes(int N, int E, int H) {
 
 }  // namespace sgg
 
+// One edge-GRU update in isolation (the dominant kernel of the path): Eh' = GRU(g_s P[s] + g_o P[o] + b_ih,
+// Eh W_hh^T + b_hh, Eh).  Exposed for unit tests and for bench.py's per-kernel roofline timing.
+extern "C" int sgg_edge_gru_forward(const float *Eh, const float *P, const float *gates, const void *graph_ws,
+                                    const float *w_ih, const float *w_hh, const float *w_hh_split, const float *b_ih,
+                                    const float *b_hh, int N, int E, int H, float *out, void *stream) {
+  using namespace sgg;
+  if (E <= 0) return 0;
+  if (!Eh || !P || !gates || !graph_ws || !w_hh || !b_ih || !b_hh || !out || (H % BN) != 0)
+    return sgg_set_err(SGG_E_BADARG, "edge_gru_forward: bad argument");
+  SggGraphView g = sgg_graph_view(graph_ws, N, E);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (w_hh_split) return tc_gru(2, nullptr, Eh, nullptr, w_hh_split, b_ih, b_hh, P, gates, g.subj, g.obj, out, nullptr, E, H, st);
+  GruArgs a{}; a.h = Eh; a.w_ih = w_ih; a.w_hh = w_hh; a.b_ih = b_ih; a.b_hh = b_hh; a.P = P; a.gates = gates;
+  a.subj = g.subj; a.obj = g.obj; a.out = out; a.M = E; a.H = H;
+  return launch_gru<GRU_EDGE>(a, st);
+}
+
 extern "C" size_t sgg_mp_tape_bytes(int N, int E, int H, int T) {
   return sgg::mp_tape_view(nullptr, N < 0 ? 0 : N, E < 0 ? 0 : E, H, T < 0 ? 0 : T).floats * sizeof(float);
 }
@@ -492,7 +509,7 @@ extern "C" int sgg_l1_forward(const float *obj_feat, const float *edge_feat, con
                  int relu, float *lws, cudaStream_t s2) -> int {
     return wsplit ? sgg::tc_linear(x, wsplit, b, y, M, No, K, relu, lws, s2) : sgg::launch_linear(x, wt, b, y, M, No, K, relu, s2);
   };
-  cudaStream_t sb = sgg::side_stream();
+  cudaStream_t sb = sgg::side_stream(st);
   const bool par = sb != nullptr && N > 0 && E > 0;
   cudaStream_t sn = par ? sb : st;
   if (par && (rc = sgg::stream_order(st, sb))) return rc;         // fork: inputs / graph are ready on `st`

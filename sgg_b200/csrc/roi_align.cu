@@ -63,17 +63,141 @@ k_roi_align(const float *__restrict__ fmap, int C, int Hf, int Wf, const float *
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Fast path: channel-last feature map.  A CTA owns one RoI; threads own channels, so every bilinear corner
+// fetch is a coalesced read of consecutive channels, the separable sample geometry (14 y-samples x 14
+// x-samples for 7x7 bins, sampling_ratio 2) is computed once per RoI in shared memory, and the [C,7,7] result
+// is staged in shared memory and written out as one contiguous, coalesced block.
+__global__ void k_nchw_to_nhwc(const float *__restrict__ in, int C, int HW, float *__restrict__ out) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+  const float *src = in + (size_t)b * C * HW;
+  float *dst = out + (size_t)b * C * HW;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, pp = p0 + threadIdx.x;
+    tile[i][threadIdx.x] = (c < C && pp < HW) ? src[(size_t)c * HW + pp] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int pp = p0 + i, c = c0 + threadIdx.x;
+    if (pp < HW && c < C) dst[(size_t)pp * C + c] = tile[threadIdx.x][i];
+  }
+}
+
+constexpr int RA_MAXS = 32;   // max samples per axis (pool * sampling_ratio)
+
+__global__ void __launch_bounds__(256)
+k_roi_align_nhwc(const float *__restrict__ fmap /*[B,Hf,Wf,C]*/, int C, int Hf, int Wf, const float *__restrict__ rois,
+                 int N, const int64_t *__restrict__ ui, int64_t stride, int cs, int co, int E, float scale, int pool,
+                 int sr, float *__restrict__ node_out, float *__restrict__ edge_out, int r_begin) {
+  extern __shared__ __align__(16) float s_out[];          // [C][pool*pool]
+  __shared__ int s_lo[2][RA_MAXS], s_hi[2][RA_MAXS];
+  __shared__ float s_l[2][RA_MAXS], s_h[2][RA_MAXS];       // lerp weights (l = frac, h = 1 - frac); 0,0 when invalid
+  const int r = r_begin + blockIdx.x;
+  const int pp = pool * pool, ns = pool * sr;
+  float x1, y1, x2, y2; int b;
+  float *dst;
+  if (r < N) {
+    const float *q = rois + (size_t)r * 5;
+    b = (int)q[0]; x1 = q[1]; y1 = q[2]; x2 = q[3]; y2 = q[4];
+    dst = node_out + (size_t)r * C * pp;
+  } else {
+    const size_t e = (size_t)(r - N);
+    const float *qs = rois + (size_t)ui[e * stride + cs] * 5, *qo = rois + (size_t)ui[e * stride + co] * 5;
+    b = (int)qs[0];
+    x1 = fminf(qs[1], qo[1]); y1 = fminf(qs[2], qo[2]); x2 = fmaxf(qs[3], qo[3]); y2 = fmaxf(qs[4], qo[4]);
+    dst = edge_out + e * C * pp;
+  }
+  if (threadIdx.x < 2 * ns) {
+    const int axis = threadIdx.x / ns, i = threadIdx.x % ns;     // axis 0 = y, 1 = x
+    const float start = (axis == 0 ? y1 : x1) * scale;
+    const float len = fmaxf((axis == 0 ? y2 : x2) * scale - start, 1.f);
+    const float bin = len / (float)pool;
+    const int size = axis == 0 ? Hf : Wf;
+    float v = start + (i / sr) * bin + ((i % sr) + 0.5f) * bin / (float)sr;
+    int lo = 0, hi = 0; float l = 0.f, h = 0.f;
+    if (!(v < -1.0f || v > (float)size)) {
+      if (v <= 0.f) v = 0.f;
+      lo = (int)v;
+      if (lo >= size - 1) { hi = lo = size - 1; v = (float)lo; } else hi = lo + 1;
+      l = v - lo; h = 1.f - l;
+    } else {
+      lo = -1;                                                   // marks "sample contributes 0"
+    }
+    s_lo[axis][i] = lo; s_hi[axis][i] = hi; s_l[axis][i] = l; s_h[axis][i] = h;
+  }
+  __syncthreads();
+  const float *f = fmap + (size_t)b * Hf * Wf * C;
+  const float inv = 1.f / (float)(sr * sr);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    for (int ph = 0; ph < pool; ++ph)
+      for (int pw = 0; pw < pool; ++pw) {
+        float acc = 0.f;
+        for (int iy = 0; iy < sr; ++iy) {
+          const int sy = ph * sr + iy;
+          const int yl = s_lo[0][sy], yh = s_hi[0][sy];
+          const float ly = s_l[0][sy], hy = s_h[0][sy];
+          for (int ix = 0; ix < sr; ++ix) {
+            const int sx = pw * sr + ix;
+            const int xl = s_lo[1][sx], xh = s_hi[1][sx];
+            if (yl < 0 || xl < 0) continue;
+            const float lx = s_l[1][sx], hx = s_h[1][sx];
+            const float v1 = f[((size_t)yl * Wf + xl) * C + c], v2 = f[((size_t)yl * Wf + xh) * C + c];
+            const float v3 = f[((size_t)yh * Wf + xl) * C + c], v4 = f[((size_t)yh * Wf + xh) * C + c];
+            acc += hy * hx * v1 + hy * lx * v2 + ly * hx * v3 + ly * lx * v4;
+          }
+        }
+        s_out[c * pp + ph * pool + pw] = acc * inv;
+      }
+  }
+  __syncthreads();
+  const int total = C * pp;
+  if ((total & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+    const float4 *s4 = reinterpret_cast<const float4 *>(s_out);
+    float4 *d4 = reinterpret_cast<float4 *>(dst);
+    for (int i = threadIdx.x; i < total / 4; i += blockDim.x) d4[i] = s4[i];
+  } else {
+    for (int i = threadIdx.x; i < total; i += blockDim.x) dst[i] = s_out[i];
+  }
+}
+
 }  // namespace sgg
+
+extern "C" size_t sgg_node_edge_features_workspace_bytes(int B, int C, int Hf, int Wf) {
+  return (size_t)B * C * Hf * Wf * sizeof(float) + 256;
+}
 
 extern "C" int sgg_node_edge_features(const float *fmap, int B, int C, int Hf, int Wf, const float *rois, int N,
                                       const int64_t *union_inds, int64_t row_stride, int col_subj, int col_obj, int E,
                                       float spatial_scale, int pool, int sampling_ratio, float *node_feat,
-                                      float *edge_feat, void *stream) {
+                                      float *edge_feat, void *ws, size_t ws_bytes, void *stream) {
   if (B <= 0 || C <= 0 || Hf <= 0 || Wf <= 0 || N < 0 || E < 0 || pool <= 0 || sampling_ratio <= 0)
     return sgg_set_err(SGG_E_BADARG, "node_edge_features: bad shape");
   const int do_node = node_feat != nullptr && N > 0, do_edge = edge_feat != nullptr && E > 0;
   if (!do_node && !do_edge) return 0;
   if (!fmap || !rois || (do_edge && !union_inds)) return sgg_set_err(SGG_E_BADARG, "node_edge_features: null pointer");
+  const size_t smem_need = (size_t)C * pool * pool * sizeof(float);
+  if (ws && ws_bytes >= sgg_node_edge_features_workspace_bytes(B, C, Hf, Wf) && smem_need <= 200 * 1024 &&
+      pool * sampling_ratio <= sgg::RA_MAXS) {
+    // channel-last fast path
+    cudaStream_t st = (cudaStream_t)stream;
+    float *nhwc = (float *)ws;
+    const int HW = Hf * Wf;
+    dim3 tg((HW + 31) / 32, (C + 31) / 32, B);
+    sgg::k_nchw_to_nhwc<<<tg, dim3(32, 8), 0, st>>>(fmap, C, HW, nhwc);
+    SGG_RETURN_IF_LAUNCH_FAILED("k_nchw_to_nhwc");
+    static bool attr = false;
+    if (!attr) {
+      SGG_CUDA_TRY(cudaFuncSetAttribute(sgg::k_roi_align_nhwc, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr = true;
+    }
+    const int r0 = do_node ? 0 : N, r1 = do_edge ? N + E : N;
+    sgg::k_roi_align_nhwc<<<r1 - r0, 256, smem_need, st>>>(nhwc, C, Hf, Wf, rois, N, union_inds, row_stride, col_subj,
+                                                          col_obj, E, spatial_scale, pool, sampling_ratio, node_feat,
+                                                          edge_feat, r0);
+    SGG_RETURN_IF_LAUNCH_FAILED("k_roi_align_nhwc");
+    return 0;
+  }
   const size_t total = ((size_t)(do_node ? N : 0) + (do_edge ? E : 0)) * C * pool * pool;
   int blocks = (int)((total + 255) / 256 < (size_t)sgg_num_sms() * 32 ? (total + 255) / 256 : (size_t)sgg_num_sms() * 32);
   sgg::k_roi_align<<<blocks, 256, 0, (cudaStream_t)stream>>>(fmap, C, Hf, Wf, rois, N, union_inds, row_stride,

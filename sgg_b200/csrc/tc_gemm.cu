@@ -106,7 +106,7 @@ k_tc_gemm(Params p, const __grid_constant__ CUtensorMap tmA0, const __grid_const
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA0); prefetch_tmap(&tmBh0); prefetch_tmap(&tmBl0);
     if (NSEG > 1) { prefetch_tmap(&tmA1); prefetch_tmap(&tmBh1); prefetch_tmap(&tmBl1); }
-    for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(ready + s, 128); mbar_init(empty + s, 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(ready + s, 64); mbar_init(empty + s, 1); }
     mbar_init(tmem_full, 1); mbar_init(tmem_full + 1, 1);
     mbar_init(tmem_empty, 128); mbar_init(tmem_empty + 1, 128);
     fence_barrier_init();
@@ -179,23 +179,31 @@ k_tc_gemm(Params p, const __grid_constant__ CUtensorMap tmA0, const __grid_const
     }
   } else if (warp < 6) {
     // ===================== split A (hi / lo) =====================
-    const int t = threadIdx.x - 64;     // 0..127
-    for (int it = 0; it < total; ++it) {
+    // Two groups of two warps alternate k-blocks, so one group's fence.proxy.async (MEMBAR) and barrier
+    // round-trip overlap the other group's loads/stores.
+    const int grp = (warp - 2) >> 1;                 // 0: warps 2,3   1: warps 4,5
+    const int t = (threadIdx.x - 64) & 63;           // 0..63 inside the group
+    for (int it = grp; it < total; it += 2) {
       const int s = it % STAGES, ph = (it / STAGES) & 1;
       mbar_wait(full + s, ph);
-      float4 *a = reinterpret_cast<float4 *>(stage_ptr(s));
-      float4 *lo = reinterpret_cast<float4 *>(stage_ptr(s) + A_BYTES);
+      const uint32_t a_addr = smem_u32(stage_ptr(s)), lo_addr = a_addr + A_BYTES;
+      constexpr int PER = A_BYTES / 16 / 64;         // float4 per thread
 #pragma unroll
-      for (int i = 0; i < A_BYTES / 16 / 128; ++i) {
-        const int idx = t + i * 128;
-        const float4 v = a[idx];
-        float4 hi, l;
-        hi.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); l.x = v.x - hi.x;
-        hi.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); l.y = v.y - hi.y;
-        hi.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); l.z = v.z - hi.z;
-        hi.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); l.w = v.w - hi.w;
-        a[idx] = hi;
-        lo[idx] = l;
+      for (int i0 = 0; i0 < PER; i0 += 8) {
+        float4 v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = lds128(a_addr + (uint32_t)((t + (i0 + i) * 64) * 16));
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float4 hi, l;
+          hi.x = __uint_as_float(__float_as_uint(v[i].x) & 0xffffe000u); l.x = v[i].x - hi.x;
+          hi.y = __uint_as_float(__float_as_uint(v[i].y) & 0xffffe000u); l.y = v[i].y - hi.y;
+          hi.z = __uint_as_float(__float_as_uint(v[i].z) & 0xffffe000u); l.z = v[i].z - hi.z;
+          hi.w = __uint_as_float(__float_as_uint(v[i].w) & 0xffffe000u); l.w = v[i].w - hi.w;
+          const uint32_t off = (uint32_t)((t + (i0 + i) * 64) * 16);
+          sts128(a_addr + off, hi);
+          sts128(lo_addr + off, l);
+        }
       }
       fence_proxy_async_smem();
       mbar_arrive(ready + s);

@@ -284,7 +284,7 @@ def union_geom(rois, union_inds, params, union_pools=None, prefix='union_boxes.c
 
 
 def node_edge_features(fmap, rois, union_inds, spatial_scale=1.0 / 16, pool=7, sampling_ratio=2,
-                       want_node=True, want_edge=True):
+                       want_node=True, want_edge=True, fast=True):
     """RelModelBase.node_edge_features (rel_model_base.py:245-260)."""
     lib = _lib.load()
     fmap = _f32(fmap, 'fmap'); rois = _f32(rois, 'rois'); ui, stride = _i64_rows(union_inds, 'union_inds')
@@ -292,9 +292,11 @@ def node_edge_features(fmap, rois, union_inds, spatial_scale=1.0 / 16, pool=7, s
     N, E = rois.shape[0], ui.shape[0]
     node = torch.empty((N, Cc, pool, pool), dtype=torch.float32, device=fmap.device) if want_node else None
     edge = torch.empty((E, Cc, pool, pool), dtype=torch.float32, device=fmap.device) if want_edge else None
+    nb = lib.sgg_node_edge_features_workspace_bytes(B, Cc, Hf, Wf) if fast else 0
+    ws = torch.empty(nb, dtype=torch.uint8, device=fmap.device) if nb else None
     check(lib.sgg_node_edge_features(_ptr(fmap), B, Cc, Hf, Wf, _ptr(rois), N, _ptr(ui), stride, 0, 1, E,
-                                     float(spatial_scale), pool, sampling_ratio, _ptr(node), _ptr(edge), _stream()),
-          'sgg_node_edge_features')
+                                     float(spatial_scale), pool, sampling_ratio, _ptr(node), _ptr(edge),
+                                     _ptr(ws), nb, _stream()), 'sgg_node_edge_features')
     return node, edge
 
 
@@ -359,3 +361,17 @@ def message_pass_backward(rel_rep, obj_rep, graph, params, tape, dV, dE, mp_iter
                               _ptr(dV), _ptr(dE), C.byref(gs), _ptr(d_obj), _ptr(d_rel), _ptr(ws), nbytes, _stream()),
           'sgg_mp_backward')
     return d_rel, d_obj, grads
+
+
+def edge_gru(Eh, P, gates, graph, params):
+    """One edge-GRU update (dominant kernel) in isolation: see sgg_edge_gru_forward in include/sgg_b200.h."""
+    lib = _lib.load()
+    Eh = _f32(Eh, 'Eh'); P = _f32(P, 'P'); gates = _f32(gates, 'gates')
+    E, H = Eh.shape
+    w_hh = _f32(params['edge_gru.weight_hh'], 'w_hh'); w_ih = _f32(params['edge_gru.weight_ih'], 'w_ih')
+    b_ih = _f32(params['edge_gru.bias_ih'], 'b_ih'); b_hh = _f32(params['edge_gru.bias_hh'], 'b_hh')
+    sp = split_weight(params['edge_gru.weight_hh']) if _MODE['gemm'] == 'tc' else None
+    out = torch.empty_like(Eh)
+    check(lib.sgg_edge_gru_forward(_ptr(Eh), _ptr(P), _ptr(gates), _ptr(graph.ws), _ptr(w_ih), _ptr(w_hh), _ptr(sp),
+                                   _ptr(b_ih), _ptr(b_hh), graph.N, E, H, _ptr(out), _stream()), 'sgg_edge_gru_forward')
+    return out

@@ -111,9 +111,10 @@ def test_union_geom_eval(ops):
 def test_roi_align_node_and_union(ops):
     fx = cases.load('roi_align')
     fmap, rois, ui = cases.roi_inputs(fx)
-    nf, ef = ops.node_edge_features(dev(fmap), dev(rois), dev(ui))
-    assert np.abs(nf.cpu().numpy() - fx['node_feat']).max() <= 1e-5
-    assert np.abs(ef.cpu().numpy() - fx['edge_feat']).max() <= 1e-5
+    for fast in (True, False):            # channel-last CTA-per-RoI kernel and the per-element NCHW kernel
+        nf, ef = ops.node_edge_features(dev(fmap), dev(rois), dev(ui), fast=fast)
+        assert np.abs(nf.cpu().numpy() - fx['node_feat']).max() <= 1e-5
+        assert np.abs(ef.cpu().numpy() - fx['edge_feat']).max() <= 1e-5
 
 
 def test_graph_rejects_out_of_range(ops):
@@ -156,3 +157,23 @@ def test_full_size_properties_cfg4_shard(ops):
     v3, e3 = ops.message_pass(dev(rel[:m0]), dev(obj[:n0]), gr3, p, 3)
     assert (v[:n0] - v3).abs().max().item() <= 2e-5 and (e[:m0] - e3).abs().max().item() <= 2e-5
     assert torch.isfinite(v).all() and torch.isfinite(e).all()
+
+
+def test_edge_gru_kernel_vs_numpy(ops):
+    """The dominant kernel in isolation (fused gather + GRU epilogue) against the numpy GRUCell."""
+    from sgg_b200 import synth
+    g = synth.synth_graph(3, 20, 150, 11)
+    N, E, H = g['boxes'].shape[0], g['rel_inds'].shape[0], 512
+    rng = np.random.default_rng(3)
+    p = synth.synth_params(11, scale=2.0, level='l0')
+    V = rng.standard_normal((N, H), dtype=np.float32) * np.float32(0.5)
+    Eh = rng.standard_normal((E, H), dtype=np.float32) * np.float32(0.5)
+    gates = rng.random((E, 4), dtype=np.float32)
+    P = (V.astype(np.float64) @ p['edge_gru.weight_ih'].astype(np.float64).T).astype(np.float32)
+    s, o = g['rel_inds'][:, 1], g['rel_inds'][:, 2]
+    x = gates[:, :1] * V[s] + gates[:, 1:2] * V[o]
+    ref = O.gru_cell(x.astype(np.float64), Eh.astype(np.float64), *[p['edge_gru.' + k].astype(np.float64)
+                                                                       for k in ('weight_ih', 'weight_hh', 'bias_ih', 'bias_hh')])
+    gr = ops.build_graph(dev(g['rel_inds'])[:, 1:3], N)
+    out = ops.edge_gru(dev(Eh), dev(P), dev(gates), gr, pdev(p)).cpu().numpy()
+    assert np.abs(out - ref).max() <= 5e-5
