@@ -125,9 +125,17 @@ SGG_API int sgg_linear_backward(const float *x, const float *w, const float *dy,
                         float *dx, float *dw, float *db, void *ws, size_t ws_bytes, void *stream);
 
 /* ---- tensor-core (tcgen05 / TMEM / TMA) variants -----------------------------------------
- * fp32 in, fp32 out, fp32-grade accuracy through the 3xTF32 split x = hi + lo.
- * sgg_tc_split_weights: split[0:n] = hi(w), split[n:2n] = lo(w); call once per weight version.
- * sgg_tc_linear_forward: same contract as sgg_linear_forward but takes the split weight. K % 4 == 0. */
+ * fp32 in, fp32 out, fp32-grade accuracy through a 3-pass operand split.  Two engines:
+ *   mode 0 "3xTF32": x = hi + lo (fp32 words, hi = top 19 bits), kind::tf32;     split buffer = 2n floats
+ *   mode 1 "3xFP16": x = hi + 2^-11 lo (fp16 halves), kind::f16, |x| < 65504;    split buffer = 2n halves
+ * sgg_tc_set_mode selects the engine for every later call of this process (default SGG_TC_DEFAULT_MODE, or the
+ * SGG_TC_MODE environment variable); a split made in one mode must not be used in the other.
+ * sgg_tc_split_weights: split = [hi(w) | lo(w)]; always pass a buffer of 2n floats; call once per weight version.
+ * sgg_tc_linear_forward: same contract as sgg_linear_forward but takes the split weight.  K % 4 == 0 (mode 0),
+ * K % 8 == 0 (mode 1). */
+#define SGG_TC_DEFAULT_MODE 0
+SGG_API int sgg_tc_set_mode(int mode);
+SGG_API int sgg_tc_get_mode(void);
 SGG_API int sgg_tc_split_weights(const float *w, size_t n, float *split, void *stream);
 SGG_API size_t sgg_tc_linear_workspace_bytes(int M, int Nout, int K);   /* split-K partials (0 = none needed) */
 SGG_API int sgg_tc_linear_forward(const float *x, const float *w_split, const float *b, float *y,

@@ -1,0 +1,633 @@
+// Tensor-core GEMM engine v2: tcgen05 kind::f16 with a 3-pass fp16 split ("3xFP16"), fp32-grade results.
+//
+//   x = hi + lo * 2^-11,   hi = fp16_rn(x),   lo = fp16_rn((x - hi) * 2^11)         (x - hi is exact in fp32)
+//   D_main[128 x N] = A_hi B_hi^T                      (TMEM, fp32 accumulate, K = 16 per instruction)
+//   D_corr[128 x N] = A_lo B_hi^T + A_hi B_lo^T        (separate accumulator: it carries the 2^11 scale)
+//   result          = D_main + 2^-11 D_corr            (fp32 registers, epilogue)
+//
+// fp16 x fp16 products are exact in fp32; the dropped lo*lo term is 2^-24 relative, i.e. below fp32 rounding.
+// Versus the 3xTF32 engine (tc_gemm.cu) every pass runs at twice the MMA rate and every operand element costs
+// 4 bytes (hi + lo) instead of 8 on the L2 -> shared-memory path, which is what bounds these kernels
+// (profiles/r01_ncu_edge_gru_tc.md).  Range: |x| must stay below 65504 (fp16); smaller magnitudes lose nothing
+// (hi may be subnormal, lo picks up the remainder: absolute error <= 2^-35).
+//
+// One CTA = one 128-row x NCOL-column output tile, 10 warps:
+//   warp 0   : TMA producer.  Per 64-wide k-block: two [128 x 32] fp32 boxes of A (raw) and the pre-split fp16
+//              B_hi / B_lo tiles (sgg_tc_split_weights), all SWIZZLE_128B, K-major, multi-stage mbarrier ring.
+//   warps 2-5: convert the raw A tile IN PLACE into the fp16 [hi | lo] tiles the tensor core reads (the 32 KB of
+//              fp32 become 16 KB hi + 16 KB lo; each 8-row swizzle atom is converted by one warp with a
+//              load-all / __syncwarp / store-all sequence, so no extra staging buffer is needed).
+//   warp 1   : one thread issues the tcgen05.mma triplets and commits stage / accumulator barriers.
+//   warps 6-9: TMEM readers (one accumulator row per thread).
+// Epilogues:
+//   LINEAR  : K is folded into TMEM 256 at a time (the tensor core's accumulator truncates on every add, see
+//             tc_gemm.cu); chunks ping-pong between two TMEM buffer pairs and are drained into fp32 registers.
+//   GRU_*   : accumulators are dumped to shared memory (the pipeline stages are free by then) and ALL 8 worker
+//             warps run the GRUCell pointwise math with a (row, 4 hidden units)-per-thread mapping, so the gathers
+//             of P = V W_ih^T rows, the state read and the state write are fully coalesced.
+// GRU tiles cover hidden units [j0, j0 + NBR) of the r, z, n gates (weight rows j0, H + j0, 2H + j0); NBR is
+// picked per launch from {32, 64, 80} by a wave-quantisation cost model (a ragged last column tile is masked).
+#include <cuda_fp16.h>
+#include "tc_gemm.cuh"
+#include "kernels.h"
+
+namespace sgg {
+namespace tc16 {
+
+constexpr int BM = 128;
+constexpr int BK = 64;                       // fp16 elements per k-block = one 128-byte swizzle span
+constexpr int NTHR = 320;
+constexpr int A_BYTES = BM * BK * 4;         // raw fp32 tile == hi tile + lo tile
+constexpr int A_HALF = A_BYTES / 2;
+constexpr int SMEM_BUDGET = 230000;
+constexpr float LO_SCALE = 2048.0f, LO_INV = 1.0f / 2048.0f;
+
+enum { EPI_LINEAR = 0, EPI_GRU_INIT = 1, EPI_GRU_NODE = 2, EPI_GRU_EDGE = 3 };
+
+struct Params {
+  int M, K, H, Nout, relu;
+  int kb_per_split;           // LINEAR split-K: k-blocks per blockIdx.z
+  const float *bias;          // LINEAR
+  float *out;                 // LINEAR: [M,Nout] (or partials [splits,M,Nout]); GRU: [M,H]
+  const float *b_ih, *b_hh;   // GRU
+  const float *h;             // GRU_NODE / GRU_EDGE: previous state [M,H]
+  const float *P;             // GRU_EDGE: [N,3H]
+  const float *gates;         // GRU_EDGE: [M,4]
+  const int *subj, *obj;      // GRU_EDGE
+  float *cache;               // GRU: nullable [M,4,H] (r, z, n, gh_n) for the backward pass
+};
+
+template <int NCOL>
+struct Cfg {
+  static constexpr int B_BYTES = NCOL * BK * 2;                 // one of hi / lo
+  static constexpr int STAGE_BYTES = A_BYTES + 2 * B_BYTES;
+  static constexpr int STAGES = (SMEM_BUDGET / STAGE_BYTES) > 6 ? 6 : (SMEM_BUDGET / STAGE_BYTES);
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
+  static constexpr int KCB = 256 / BK;                          // k-blocks per accumulation chunk (LINEAR)
+};
+
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+  // c_format = F32 (1) [4,6); a_format = b_format = F16 (0); K-major A and B; N>>3 [17,23); M>>4 [24,29)
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// K-major SWIZZLE_128B tile with 128-byte rows: SBO = 1024 B (8 rows), LBO unused, version 1, layout 2
+__device__ __forceinline__ uint64_t make_sdesc128(const void *smem_tile) {
+  const uint64_t addr = (uint64_t)((tc::smem_u32(smem_tile) & 0x3FFFF) >> 4);
+  return addr | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ uint4 lds128u(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128u(uint32_t addr, const uint4 &v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+// (x0, x1) -> packed fp16 hi pair and packed fp16 scaled-lo pair
+__device__ __forceinline__ void split2(float x0, float x1, uint32_t &hi, uint32_t &lo) {
+  const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
+  const __half l0 = __float2half_rn((x0 - __half2float(h0)) * LO_SCALE);
+  const __half l1 = __float2half_rn((x1 - __half2float(h1)) * LO_SCALE);
+  hi = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+  lo = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+}
+
+__device__ __forceinline__ float4 ld4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
+__device__ __forceinline__ float4 ldg4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
+
+// torch.nn.GRUCell pointwise on 4 hidden units; gi_* / gh_* include the biases
+struct Gru4 { float4 out, r, z, n; };
+__device__ __forceinline__ Gru4 gru4(const float4 &gir, const float4 &ghr, const float4 &giz, const float4 &ghz,
+                                     const float4 &gin, const float4 &ghn, const float4 &h) {
+  Gru4 o;
+  o.r.x = sgg_sigmoid(gir.x + ghr.x); o.r.y = sgg_sigmoid(gir.y + ghr.y);
+  o.r.z = sgg_sigmoid(gir.z + ghr.z); o.r.w = sgg_sigmoid(gir.w + ghr.w);
+  o.z.x = sgg_sigmoid(giz.x + ghz.x); o.z.y = sgg_sigmoid(giz.y + ghz.y);
+  o.z.z = sgg_sigmoid(giz.z + ghz.z); o.z.w = sgg_sigmoid(giz.w + ghz.w);
+  o.n.x = tanhf(gin.x + o.r.x * ghn.x); o.n.y = tanhf(gin.y + o.r.y * ghn.y);
+  o.n.z = tanhf(gin.z + o.r.z * ghn.z); o.n.w = tanhf(gin.w + o.r.w * ghn.w);
+  o.out.x = (1.0f - o.z.x) * o.n.x + o.z.x * h.x; o.out.y = (1.0f - o.z.y) * o.n.y + o.z.y * h.y;
+  o.out.z = (1.0f - o.z.z) * o.n.z + o.z.z * h.z; o.out.w = (1.0f - o.z.w) * o.n.w + o.z.w * h.w;
+  return o;
+}
+__device__ __forceinline__ float4 add4(const float4 &a, const float4 &b) {
+  return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+}
+
+// NBLK gate blocks of NBR weight rows each (LINEAR: NBLK = 1, NBR = tile width); NSEG K-segments (NODE: 2)
+template <int NBLK, int NBR, int NSEG, int EPI>
+__global__ void __launch_bounds__(NTHR, 1)
+k_tc16(Params p, const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+       const __grid_constant__ CUtensorMap tmBh0, const __grid_constant__ CUtensorMap tmBl0,
+       const __grid_constant__ CUtensorMap tmBh1, const __grid_constant__ CUtensorMap tmBl1) {
+  using namespace tc;
+  constexpr int NCOL = NBLK * NBR;                 // MMA N
+  using C = Cfg<NCOL>;
+  constexpr int STAGES = C::STAGES, STAGE_BYTES = C::STAGE_BYTES, B_BYTES = C::B_BYTES, KCB = C::KCB;
+  constexpr bool CHUNKED = (EPI == EPI_LINEAR);
+  static_assert(!CHUNKED || (NSEG == 1 && NBLK == 1 && NCOL <= 128), "chunked LINEAR: NCOL register accumulators");
+  static_assert(NCOL % 16 == 0 && NCOL <= 256 && NBR % 16 == 0, "UMMA N / TMEM load granularity");
+  static_assert(STAGES >= 2, "pipeline needs two stages");
+  // TMEM columns: GRU: [main seg0, main seg1 | corr seg0, corr seg1]; LINEAR: buffer b = [main_b | corr_b]
+  constexpr int CORR = CHUNKED ? NCOL : NSEG * NCOL;
+  constexpr int ACC_COLS = CHUNKED ? 4 * NCOL : 2 * NSEG * NCOL;
+  constexpr uint32_t TMEM_COLS = ACC_COLS <= 32 ? 32 : ACC_COLS <= 64 ? 64 : ACC_COLS <= 128 ? 128 : ACC_COLS <= 256 ? 256 : 512;
+  static_assert(ACC_COLS <= 512, "tile too wide for TMEM");
+  // GRU epilogue staging: NV value blocks of NBR floats per row, row stride RS floats (RS/4 odd: conflict-free)
+  constexpr int NV = (EPI == EPI_GRU_NODE) ? 4 : 3;
+  constexpr int RS = NV * NBR + 4;
+  static_assert(CHUNKED || (BM * RS * 4 <= STAGES * STAGE_BYTES), "epilogue staging must fit in the stage ring");
+  static_assert(CHUNKED || ((RS / 4) & 1) == 1, "staging row stride");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES);
+  uint64_t *full = bars, *ready = bars + STAGES, *empty = bars + 2 * STAGES, *tmem_full = bars + 3 * STAGES;
+  uint64_t *tmem_empty = bars + 3 * STAGES + 2;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 3 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * BM;
+  const int j0 = blockIdx.x * (CHUNKED ? NCOL : NBR);
+  const int kblocks_all = (p.K + BK - 1) / BK;
+  const int kb_lo = CHUNKED ? (int)blockIdx.z * p.kb_per_split : 0;
+  const int kblocks = CHUNKED ? min(p.kb_per_split, kblocks_all - kb_lo) : kblocks_all;
+  const int total = NSEG * kblocks;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA0); prefetch_tmap(&tmBh0); prefetch_tmap(&tmBl0);
+    if (NSEG > 1) { prefetch_tmap(&tmA1); prefetch_tmap(&tmBh1); prefetch_tmap(&tmBl1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(ready + s, 128); mbar_init(empty + s, 1); }
+    mbar_init(tmem_full, 1); mbar_init(tmem_full + 1, 1);
+    mbar_init(tmem_empty, 128); mbar_init(tmem_empty + 1, 128);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto stage_ptr = [&](int s) { return smem + (size_t)s * STAGE_BYTES; };   // [A (raw -> hi|lo) | B_hi | B_lo]
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      for (int it = 0; it < total; ++it) {
+        const int s = it % STAGES, ph = (it / STAGES) & 1;
+        mbar_wait(empty + s, ph ^ 1);
+        const int seg = it / kblocks, k0 = (kb_lo + it - seg * kblocks) * BK;
+        uint8_t *st = stage_ptr(s);
+        mbar_arrive_expect_tx(full + s, A_BYTES + 2 * B_BYTES);
+        const CUtensorMap *ta = (NSEG > 1 && seg == 1) ? &tmA1 : &tmA0;
+        const CUtensorMap *tbh = (NSEG > 1 && seg == 1) ? &tmBh1 : &tmBh0;
+        const CUtensorMap *tbl = (NSEG > 1 && seg == 1) ? &tmBl1 : &tmBl0;
+        tma_load_2d(st, ta, full + s, k0, m0);                       // fp32 k0 .. k0+31
+        tma_load_2d(st + A_HALF, ta, full + s, k0 + 32, m0);         // fp32 k0+32 .. k0+63
+#pragma unroll
+        for (int b = 0; b < NBLK; ++b) {
+          const int row = CHUNKED ? j0 : (b * p.H + j0);
+          tma_load_2d(st + A_BYTES + b * (NBR * BK * 2), tbh, full + s, k0, row);
+          tma_load_2d(st + A_BYTES + B_BYTES + b * (NBR * BK * 2), tbl, full + s, k0, row);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(BM, NCOL);
+      for (int it = 0; it < total; ++it) {
+        const int s = it % STAGES, ph = (it / STAGES) & 1;
+        mbar_wait(full + s, ph);
+        mbar_wait(ready + s, ph);
+        fence_after_sync();
+        const int seg = it / kblocks, kb = it - seg * kblocks;
+        uint8_t *st = stage_ptr(s);
+        const uint64_t ah = make_sdesc128(st), al = make_sdesc128(st + A_HALF);
+        const uint64_t bh = make_sdesc128(st + A_BYTES), bl = make_sdesc128(st + A_BYTES + B_BYTES);
+        uint32_t dm, first;
+        const int chunk = it / KCB, kc = it - chunk * KCB;
+        if (CHUNKED) {
+          if (kc == 0) {                       // buffer pair must have been drained by the TMEM readers
+            mbar_wait(tmem_empty + (chunk & 1), ((chunk >> 1) & 1) ^ 1);
+            fence_after_sync();
+          }
+          dm = tmem_base + (uint32_t)((chunk & 1) * 2 * NCOL);
+          first = (kc == 0) ? 1u : 0u;
+        } else {
+          dm = tmem_base + (uint32_t)(seg * NCOL);
+          first = (kb == 0) ? 1u : 0u;
+        }
+        const uint32_t dc = dm + (uint32_t)CORR;
+#pragma unroll
+        for (int kk = 0; kk < BK / 16; ++kk) {
+          const uint64_t o = (uint64_t)(kk * 2);     // 16 fp16 = 32 bytes >> 4
+          const uint32_t acc = (first && kk == 0) ? 0u : 1u;
+          mma_f16_ss(dc, al + o, bh + o, idesc, acc);      // corrections -> CORR
+          mma_f16_ss(dc, ah + o, bl + o, idesc, 1u);
+          mma_f16_ss(dm, ah + o, bh + o, idesc, acc);      // large term  -> MAIN
+        }
+        mma_commit(empty + s);
+        if (CHUNKED && (kc == KCB - 1 || it == total - 1)) mma_commit(tmem_full + (chunk & 1));
+      }
+      if (!CHUNKED) mma_commit(tmem_full);
+    }
+  } else if (warp < 6) {
+    // ===================== convert A: fp32 -> fp16 [hi | lo], in place =====================
+    // Swizzle atom g = rows 8g..8g+7: its raw floats live at [g*1024, +1024) of both 16 KB boxes, exactly where its
+    // hi (first box) and lo (second box) fp16 rows go.  Lane <-> (row r, 16-byte output chunk c): k = 8c .. 8c+7.
+    const int w4 = warp - 2;                               // atoms 4*w4 .. 4*w4+3
+    const int c = lane & 7, b = c >> 2;                    // output chunk; source box
+    const int ca = 2 * (c & 3);                            // first raw chunk (logical) inside the box
+    for (int it = 0; it < total; ++it) {
+      const int s = it % STAGES, ph = (it / STAGES) & 1;
+      mbar_wait(full + s, ph);
+      const uint32_t a_addr = smem_u32(stage_ptr(s));
+      uint4 v[16];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {                        // i = 2*atom + row half
+        const int g = 4 * w4 + (i >> 1), r = (lane >> 3) + 4 * (i & 1);
+        const uint32_t rowb = a_addr + (uint32_t)(b * A_HALF + g * 1024 + r * 128);
+        // bank spread: lanes reading box 1 fetch the odd chunk first
+        v[2 * i] = lds128u(rowb + (uint32_t)((((ca + b) ^ r) & 7) << 4));
+        v[2 * i + 1] = lds128u(rowb + (uint32_t)((((ca + 1 - b) ^ r) & 7) << 4));
+      }
+      __syncwarp();                                        // every lane's reads of these atoms are done
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int g = 4 * w4 + (i >> 1), r = (lane >> 3) + 4 * (i & 1);
+        const uint4 f0 = b ? v[2 * i + 1] : v[2 * i], f1 = b ? v[2 * i] : v[2 * i + 1];   // floats 0-3, 4-7 of the chunk
+        uint4 hi, lo;
+        split2(__uint_as_float(f0.x), __uint_as_float(f0.y), hi.x, lo.x);
+        split2(__uint_as_float(f0.z), __uint_as_float(f0.w), hi.y, lo.y);
+        split2(__uint_as_float(f1.x), __uint_as_float(f1.y), hi.z, lo.z);
+        split2(__uint_as_float(f1.z), __uint_as_float(f1.w), hi.w, lo.w);
+        const uint32_t dst = a_addr + (uint32_t)(g * 1024 + r * 128 + (((c ^ r) & 7) << 4));
+        sts128u(dst, hi);
+        sts128u(dst + A_HALF, lo);
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(ready + s);
+    }
+  } else if (CHUNKED) {
+    // ===================== LINEAR: drain chunks into fp32 registers, thread <-> output row =====================
+    const int q = warp & 3;                       // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;
+    const int m = m0 + row;
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    float acc[NCOL];
+#pragma unroll
+    for (int cc = 0; cc < NCOL; ++cc) acc[cc] = 0.f;
+    const int nchunks = (total + KCB - 1) / KCB;
+    for (int ch = 0; ch < nchunks; ++ch) {
+      const int bsel = ch & 1;
+      mbar_wait(tmem_full + bsel, (ch >> 1) & 1);
+      fence_after_sync();
+      __syncwarp();
+#pragma unroll
+      for (int c0 = 0; c0 < NCOL; c0 += 16) {
+        float v[16], w[16];
+        tmem_ld16(taddr + (uint32_t)(bsel * 2 * NCOL + c0), v);
+        tmem_ld16(taddr + (uint32_t)(bsel * 2 * NCOL + NCOL + c0), w);
+        tmem_wait_ld();
+#pragma unroll
+        for (int cc = 0; cc < 16; ++cc) acc[c0 + cc] += fmaf(w[cc], LO_INV, v[cc]);
+      }
+      fence_before_sync();
+      mbar_arrive(tmem_empty + bsel);
+    }
+    if (m < p.M) {
+      const bool partial = gridDim.z > 1;        // split-K: raw partial sums, bias/ReLU applied by the reducer
+      const bool vec = (p.Nout & 3) == 0;
+      float *yrow = p.out + ((size_t)blockIdx.z * p.M + m) * p.Nout;
+#pragma unroll
+      for (int c0 = 0; c0 < NCOL; c0 += 4) {
+        const int j = j0 + c0;
+        if (j < p.Nout) {
+          float v[4];
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) {
+            v[cc] = acc[c0 + cc];
+            if (!partial) {
+              if (p.bias != nullptr && j + cc < p.Nout) v[cc] += __ldg(p.bias + j + cc);
+              if (p.relu) v[cc] = fmaxf(v[cc], 0.f);
+            }
+          }
+          if (vec && j + 4 <= p.Nout) {
+            *reinterpret_cast<float4 *>(yrow + j) = make_float4(v[0], v[1], v[2], v[3]);
+          } else {
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) if (j + cc < p.Nout) yrow[j + cc] = v[cc];
+          }
+        }
+      }
+    }
+  } else {
+    // ===================== GRU phase 1: TMEM -> shared staging, thread <-> accumulator row =====================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    float *stg = reinterpret_cast<float *>(smem) + (size_t)row * RS;
+    mbar_wait(tmem_full, 0);                      // all MMAs done => all stages consumed, ring is free
+    fence_after_sync();
+    __syncwarp();
+#pragma unroll
+    for (int blk = 0; blk < NV; ++blk) {
+      // source accumulator columns of this value block
+      const int src = (EPI == EPI_GRU_NODE && blk == 3) ? (NCOL + 2 * NBR) : blk * NBR;   // NODE blk 3 = gh_n (seg 1)
+      const bool add_seg1 = (EPI == EPI_GRU_NODE && blk < 2);                             // r, z: gi + gh
+#pragma unroll
+      for (int c0 = 0; c0 < NBR; c0 += 16) {
+        float v[16], w[16];
+        tmem_ld16(taddr + (uint32_t)(src + c0), v);
+        tmem_ld16(taddr + (uint32_t)(CORR + src + c0), w);
+        tmem_wait_ld();
+#pragma unroll
+        for (int cc = 0; cc < 16; ++cc) v[cc] = fmaf(w[cc], LO_INV, v[cc]);
+        if (add_seg1) {
+          float v1[16], w1[16];
+          tmem_ld16(taddr + (uint32_t)(NCOL + src + c0), v1);
+          tmem_ld16(taddr + (uint32_t)(CORR + NCOL + src + c0), w1);
+          tmem_wait_ld();
+#pragma unroll
+          for (int cc = 0; cc < 16; ++cc) v[cc] += fmaf(w1[cc], LO_INV, v1[cc]);
+        }
+#pragma unroll
+        for (int cc = 0; cc < 16; cc += 4)
+          *reinterpret_cast<float4 *>(stg + blk * NBR + c0 + cc) = make_float4(v[cc], v[cc + 1], v[cc + 2], v[cc + 3]);
+      }
+    }
+  }
+
+  if (!CHUNKED && warp >= 2) {
+    // ===================== GRU phase 2: pointwise, thread <-> (row, 4 hidden units), coalesced =====================
+    named_bar_sync(1, 256);                       // staging complete (warps 6-9), converters idle (warps 2-5)
+    const int H = p.H;
+    constexpr int QPR = NBR / 4;                  // float4 groups per row
+    const float *stg0 = reinterpret_cast<const float *>(smem);
+#pragma unroll 2
+    for (int item = (int)threadIdx.x - 64; item < BM * QPR; item += 256) {
+      const int row = item / QPR, qd = item - row * QPR;
+      const int m = m0 + row, j = j0 + 4 * qd;
+      if (m >= p.M || j >= H) continue;
+      const float *sp = stg0 + (size_t)row * RS + 4 * qd;
+      const float4 a0 = ld4(sp), a1 = ld4(sp + NBR), a2 = ld4(sp + 2 * NBR);
+      const float4 bir = ldg4(p.b_ih + j), biz = ldg4(p.b_ih + H + j), bin = ldg4(p.b_ih + 2 * H + j);
+      const float4 bhr = ldg4(p.b_hh + j), bhz = ldg4(p.b_hh + H + j), bhn = ldg4(p.b_hh + 2 * H + j);
+      Gru4 o;
+      if (EPI == EPI_GRU_INIT) {                  // acc = x W_ih^T ; h = 0 => gh = b_hh
+        o = gru4(add4(a0, bir), bhr, add4(a1, biz), bhz, add4(a2, bin), bhn, make_float4(0.f, 0.f, 0.f, 0.f));
+      } else if (EPI == EPI_GRU_NODE) {           // a0 = gi_r + gh_r, a1 = gi_z + gh_z, a2 = gi_n, a3 = gh_n
+        const float4 a3 = ld4(sp + 3 * NBR);
+        const float4 hv = ld4(p.h + (size_t)m * H + j);
+        o = gru4(add4(a0, bir), bhr, add4(a1, biz), bhz, add4(a2, bin), add4(a3, bhn), hv);
+      } else {                                    // EDGE: acc = Eh W_hh^T ; gi = g_s P[s] + g_o P[o] + b_ih
+        const int s_id = __ldg(p.subj + m), o_id = __ldg(p.obj + m);
+        const float4 g4 = ld4(p.gates + (size_t)m * 4);
+        const float gs = g4.x, go = g4.y;
+        const float *ps = p.P + (size_t)s_id * 3 * H + j, *po = p.P + (size_t)o_id * 3 * H + j;
+        const float4 sr = ld4(ps), sz = ld4(ps + H), sn = ld4(ps + 2 * H);
+        const float4 orr = ld4(po), oz = ld4(po + H), on = ld4(po + 2 * H);
+        const float4 hv = ld4(p.h + (size_t)m * H + j);
+        float4 gir, giz, gin;
+        gir.x = fmaf(gs, sr.x, go * orr.x) + bir.x; gir.y = fmaf(gs, sr.y, go * orr.y) + bir.y;
+        gir.z = fmaf(gs, sr.z, go * orr.z) + bir.z; gir.w = fmaf(gs, sr.w, go * orr.w) + bir.w;
+        giz.x = fmaf(gs, sz.x, go * oz.x) + biz.x; giz.y = fmaf(gs, sz.y, go * oz.y) + biz.y;
+        giz.z = fmaf(gs, sz.z, go * oz.z) + biz.z; giz.w = fmaf(gs, sz.w, go * oz.w) + biz.w;
+        gin.x = fmaf(gs, sn.x, go * on.x) + bin.x; gin.y = fmaf(gs, sn.y, go * on.y) + bin.y;
+        gin.z = fmaf(gs, sn.z, go * on.z) + bin.z; gin.w = fmaf(gs, sn.w, go * on.w) + bin.w;
+        o = gru4(gir, add4(a0, bhr), giz, add4(a1, bhz), gin, add4(a2, bhn), hv);
+      }
+      *reinterpret_cast<float4 *>(p.out + (size_t)m * H + j) = o.out;
+      if (p.cache != nullptr) {
+        float *cp = p.cache + (size_t)m * 4 * H + j;
+        float4 ghn;                                // gh_n incl. bias, as the backward pass expects
+        if (EPI == EPI_GRU_INIT) ghn = bhn;
+        else if (EPI == EPI_GRU_NODE) ghn = add4(ld4(sp + 3 * NBR), bhn);
+        else ghn = add4(a2, bhn);
+        *reinterpret_cast<float4 *>(cp) = o.r;
+        *reinterpret_cast<float4 *>(cp + H) = o.z;
+        *reinterpret_cast<float4 *>(cp + 2 * H) = o.n;
+        *reinterpret_cast<float4 *>(cp + 3 * H) = ghn;
+      }
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// w -> fp16 (hi, scaled lo), once per weight version
+__global__ void k_tc16_split(const float *__restrict__ w, size_t n, __half *__restrict__ hi, __half *__restrict__ lo) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float v = w[i];
+    const __half h = __float2half_rn(v);
+    hi[i] = h;
+    lo[i] = __float2half_rn((v - __half2float(h)) * LO_SCALE);
+  }
+}
+
+// split-K reducer: y = act(sum_z part[z] + bias), fixed summation order
+__global__ void k_tc16_splitk_reduce(const float *__restrict__ part, int splits, size_t mn, int Nout,
+                                     const float *__restrict__ bias, int relu, float *__restrict__ y) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < mn; i += (size_t)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int z = 0; z < splits; ++z) s += part[(size_t)z * mn + i];
+    if (bias != nullptr) s += __ldg(bias + (int)(i % Nout));
+    if (relu) s = fmaxf(s, 0.f);
+    y[i] = s;
+  }
+}
+
+// ------------------------------- host side -------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void *sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)sym;
+  }
+  return fn;
+}
+
+// row-major [rows, K] of fp32 (elem 4) or fp16 (elem 2) -> boxes of box_rows x 128 bytes, SWIZZLE_128B, zero OOB fill
+static int make_tmap(CUtensorMap *m, const void *base, int rows, int K, int box_rows, int elem) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return sgg_set_err(SGG_E_BADARG, "cuTensorMapEncodeTiled unavailable");
+  cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)(rows > 0 ? rows : 1)};
+  cuuint64_t gstr[1] = {(cuuint64_t)K * (cuuint64_t)elem};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / elem), (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, elem == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void *)base,
+                   gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return sgg_set_err(SGG_E_BADARG, "cuTensorMapEncodeTiled failed (%d) rows=%d K=%d elem=%d", (int)r, rows, K, elem);
+  return 0;
+}
+
+struct Seg { const float *A; const __half *Bhi; const __half *Blo; int brows; };
+
+template <int NBLK, int NBR, int NSEG, int EPI>
+static int launch(const Params &p, const Seg *segs, int col_tiles, int splits, cudaStream_t st) {
+  using C = Cfg<NBLK * NBR>;
+  static bool attr = false;
+  if (!attr) {
+    SGG_CUDA_TRY(cudaFuncSetAttribute(k_tc16<NBLK, NBR, NSEG, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    attr = true;
+  }
+  CUtensorMap tm[6];
+  int rc;
+  for (int s = 0; s < 2; ++s) {
+    const Seg &g = segs[s < NSEG ? s : 0];
+    if ((rc = make_tmap(&tm[3 * s + 0], g.A, p.M, p.K, BM, 4))) return rc;
+    if ((rc = make_tmap(&tm[3 * s + 1], g.Bhi, g.brows, p.K, NBR, 2))) return rc;
+    if ((rc = make_tmap(&tm[3 * s + 2], g.Blo, g.brows, p.K, NBR, 2))) return rc;
+  }
+  dim3 grid(col_tiles, (p.M + BM - 1) / BM, splits);
+  k_tc16<NBLK, NBR, NSEG, EPI><<<grid, NTHR, C::SMEM, st>>>(p, tm[0], tm[3], tm[1], tm[2], tm[4], tm[5]);
+  SGG_RETURN_IF_LAUNCH_FAILED("k_tc16");
+  return 0;
+}
+
+static bool ok16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// LINEAR plan: tile width and split-K factor minimising waves x (chunks per CTA + fixed cost), with a penalty per
+// extra split for the partial-sum round trip.  Every split is a whole number of 256-wide accumulation chunks.
+struct LinPlan { int ncol, splits; };
+static LinPlan plan_linear(int M, int Nout, int K, bool allow_split) {
+  const int sms = sgg_num_sms();
+  const int chunks = (K + 255) / 256;
+  const int rows = (M + BM - 1) / BM;
+  LinPlan best{Nout <= 64 ? 64 : 128, 1};
+  double best_cost = 1e30;
+  const int widths[2] = {128, 64};
+  for (int wi = 0; wi < 2; ++wi) {
+    const int ncol = widths[wi];
+    if (ncol == 128 && Nout <= 64) continue;
+    const long tiles = (long)((Nout + ncol - 1) / ncol) * rows;
+    const int max_s = allow_split ? (chunks < 32 ? chunks : 32) : 1;
+    for (int s = 1; s <= max_s; ++s) {
+      const int ch_per = (chunks + s - 1) / s;
+      const int s_eff = (chunks + ch_per - 1) / ch_per;
+      if (s_eff != s) continue;
+      const long waves = (tiles * s + sms - 1) / sms;
+      // per-CTA time ~ chunks x (A rows + B rows) ; fixed prologue/epilogue ~ 0.6 chunk of a 128-wide tile
+      const double per = ch_per * (128.0 + ncol) / 256.0 + 0.6;
+      const double cost = waves * per + (s > 1 ? 0.25 * s + 0.5 : 0.0);
+      if (cost < best_cost - 1e-9) { best_cost = cost; best.ncol = ncol; best.splits = s; }
+    }
+  }
+  return best;
+}
+
+size_t linear_workspace_floats(int M, int Nout, int K) {
+  if (M <= 0 || Nout <= 0) return 0;
+  const LinPlan pl = plan_linear(M, Nout, K, true);
+  return pl.splits > 1 ? (size_t)pl.splits * M * Nout : 0;
+}
+
+int linear(const float *x, const float *w_split, const float *b, float *y, int M, int Nout, int K, int relu, float *ws,
+           cudaStream_t st) {
+  if (M <= 0 || Nout <= 0) return 0;
+  if ((K & 7) || !ok16(x) || !ok16(w_split)) return sgg_set_err(SGG_E_BADARG, "tc16 linear: K %% 8 / alignment");
+  const LinPlan pl = plan_linear(M, Nout, K, ws != nullptr);
+  const int kblocks = (K + BK - 1) / BK, kcb = 256 / BK;
+  int splits = pl.splits, kb_per = kblocks;
+  if (splits > 1) {
+    const int chunks = (kblocks + kcb - 1) / kcb;
+    const int ch_per = (chunks + splits - 1) / splits;
+    kb_per = ch_per * kcb;
+    splits = (kblocks + kb_per - 1) / kb_per;
+  }
+  Params p{}; p.M = M; p.K = K; p.Nout = Nout; p.relu = relu; p.bias = b; p.kb_per_split = kb_per;
+  p.out = splits > 1 ? ws : y;
+  const __half *wh = reinterpret_cast<const __half *>(w_split);
+  Seg sg[2] = {{x, wh, wh + (size_t)Nout * K, Nout}, {}};
+  int rc;
+  if (pl.ncol == 64) rc = launch<1, 64, 1, EPI_LINEAR>(p, sg, (Nout + 63) / 64, splits, st);
+  else rc = launch<1, 128, 1, EPI_LINEAR>(p, sg, (Nout + 127) / 128, splits, st);
+  if (rc) return rc;
+  if (splits > 1) {
+    const size_t mn = (size_t)M * Nout;
+    int blocks = (int)((mn + 255) / 256 < 2048 ? (mn + 255) / 256 : 2048);
+    k_tc16_splitk_reduce<<<blocks, 256, 0, st>>>(ws, splits, mn, Nout, b, relu, y);
+    SGG_RETURN_IF_LAUNCH_FAILED("k_tc16_splitk_reduce");
+  }
+  return 0;
+}
+
+// hidden-block width for INIT / EDGE tiles: minimise waves x (L2->SM bytes per tile + fixed cost)
+static int plan_gru_width(int M, int H, bool edge) {
+  const int sms = sgg_num_sms();
+  const int rows = (M + BM - 1) / BM;
+  const int cand[3] = {80, 64, 32};
+  int best = 64; double best_cost = 1e30;
+  for (int i = 0; i < 3; ++i) {
+    const int nbr = cand[i];
+    const long tiles = (long)((H + nbr - 1) / nbr) * rows;
+    const long waves = (tiles + sms - 1) / sms;
+    const double bytes = (128.0 + 3.0 * nbr) * H * 4.0 + 128.0 * nbr * 4.0 * (edge ? 8.0 : 2.0) + 130e3;
+    const double cost = waves * bytes;
+    if (cost < best_cost) { best_cost = cost; best = nbr; }
+  }
+  return best;
+}
+
+// mode 0 = INIT (h = 0), 1 = NODE (x = ctx, h = V), 2 = EDGE (h = Eh, gathered gi)
+int gru(int mode, const float *x, const float *h, const float *w_ih_split, const float *w_hh_split, const float *b_ih,
+        const float *b_hh, const float *P, const float *gates, const int *subj, const int *obj, float *out, float *cache,
+        int M, int H, cudaStream_t st) {
+  if (M <= 0) return 0;
+  if (H % 16) return sgg_set_err(SGG_E_BADARG, "tc16 gru: H %% 16");
+  Params p{}; p.M = M; p.K = H; p.H = H; p.b_ih = b_ih; p.b_hh = b_hh; p.h = h; p.P = P; p.gates = gates;
+  p.subj = subj; p.obj = obj; p.out = out; p.cache = cache;
+  const size_t wn = (size_t)3 * H * H;
+  const __half *wih = reinterpret_cast<const __half *>(w_ih_split), *whh = reinterpret_cast<const __half *>(w_hh_split);
+  if (mode == 1) {
+    Seg sg[2] = {{x, wih, wih + wn, 3 * H}, {h, whh, whh + wn, 3 * H}};
+    return launch<3, 32, 2, EPI_GRU_NODE>(p, sg, (H + 31) / 32, 1, st);
+  }
+  const int nbr = plan_gru_width(M, H, mode == 2);
+  const int ct = (H + nbr - 1) / nbr;
+  if (mode == 0) {
+    Seg sg[2] = {{x, wih, wih + wn, 3 * H}, {}};
+    if (nbr == 80) return launch<3, 80, 1, EPI_GRU_INIT>(p, sg, ct, 1, st);
+    if (nbr == 64) return launch<3, 64, 1, EPI_GRU_INIT>(p, sg, ct, 1, st);
+    return launch<3, 32, 1, EPI_GRU_INIT>(p, sg, ct, 1, st);
+  }
+  Seg sg[2] = {{h, whh, whh + wn, 3 * H}, {}};
+  if (nbr == 80) return launch<3, 80, 1, EPI_GRU_EDGE>(p, sg, ct, 1, st);
+  if (nbr == 64) return launch<3, 64, 1, EPI_GRU_EDGE>(p, sg, ct, 1, st);
+  return launch<3, 32, 1, EPI_GRU_EDGE>(p, sg, ct, 1, st);
+}
+
+int split_weights(const float *w, size_t n, void *split, cudaStream_t st) {
+  int blocks = (int)((n + 255) / 256 < 2048 ? (n + 255) / 256 : 2048);
+  __half *hp = reinterpret_cast<__half *>(split);
+  k_tc16_split<<<blocks, 256, 0, st>>>(w, n, hp, hp + n);
+  SGG_RETURN_IF_LAUNCH_FAILED("k_tc16_split");
+  return 0;
+}
+
+}  // namespace tc16
+}  // namespace sgg

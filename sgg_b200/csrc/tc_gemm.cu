@@ -450,7 +450,7 @@ static int plan_splits(int M, int Nout, int K, int ncol, int bkf) {
 
 }  // namespace tc
 
-size_t tc_linear_workspace_floats(int M, int Nout, int K) {
+size_t tc32_linear_workspace_floats(int M, int Nout, int K) {
   const int ncol = Nout <= 64 ? 64 : 128;
   const int splits = tc::plan_splits(M, Nout, K, ncol, 32);
   return splits > 1 ? (size_t)splits * M * Nout : 0;
@@ -458,8 +458,8 @@ size_t tc_linear_workspace_floats(int M, int Nout, int K) {
 
 // y = act(x W^T + b) on tensor cores.  w_split = [hi | lo], each [Nout, K].  ws: tc_linear_workspace_floats floats
 // (may be null when that is 0; if it is null although split-K would help, the kernel simply runs unsplit).
-int tc_linear(const float *x, const float *w_split, const float *b, float *y, int M, int Nout, int K, int relu,
-              float *ws, cudaStream_t st) {
+int tc32_linear(const float *x, const float *w_split, const float *b, float *y, int M, int Nout, int K, int relu,
+                float *ws, cudaStream_t st) {
   if (M <= 0 || Nout <= 0) return 0;
   if ((K & 3) || !tc::ok16(x) || !tc::ok16(w_split)) return sgg_set_err(SGG_E_BADARG, "tc_linear: K %% 4 / alignment");
   static const int bk16 = tc::env_flag("SGG_TC_BK16", 0);
@@ -493,8 +493,8 @@ int tc_linear(const float *x, const float *w_split, const float *b, float *y, in
 }
 
 // mode 0 = INIT (h = 0), 1 = NODE (x = ctx, h = V), 2 = EDGE (h = Eh, gathered gi)
-int tc_gru(int mode, const float *x, const float *h, const float *w_ih_split, const float *w_hh_split,
-           const float *b_ih, const float *b_hh, const float *P, const float *gates, const int *subj, const int *obj,
+int tc32_gru(int mode, const float *x, const float *h, const float *w_ih_split, const float *w_hh_split,
+             const float *b_ih, const float *b_hh, const float *P, const float *gates, const int *subj, const int *obj,
            float *out, float *cache, int M, int H, cudaStream_t st) {
   if (M <= 0) return 0;
   if (H % 64) return sgg_set_err(SGG_E_BADARG, "tc_gru: H %% 64");
@@ -525,22 +525,11 @@ int tc_gru(int mode, const float *x, const float *h, const float *w_ih_split, co
 
 }  // namespace sgg
 
-extern "C" int sgg_tc_split_weights(const float *w, size_t n, float *split, void *stream) {
-  if (n == 0) return 0;
-  if (!w || !split) return sgg_set_err(SGG_E_BADARG, "tc_split_weights: null pointer");
+namespace sgg {
+int tc32_split_weights(const float *w, size_t n, float *split, cudaStream_t st) {
   int blocks = (int)((n + 255) / 256 < 2048 ? (n + 255) / 256 : 2048);
-  sgg::tc::k_tc_split<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, n, split, split + n);
+  tc::k_tc_split<<<blocks, 256, 0, st>>>(w, n, split, split + n);
   SGG_RETURN_IF_LAUNCH_FAILED("k_tc_split");
   return 0;
 }
-
-extern "C" size_t sgg_tc_linear_workspace_bytes(int M, int Nout, int K) {
-  return sgg::tc_linear_workspace_floats(M, Nout, K) * sizeof(float);
-}
-
-extern "C" int sgg_tc_linear_forward(const float *x, const float *w_split, const float *b, float *y, int M, int Nout,
-                                     int K, int relu, void *ws, size_t ws_bytes, void *stream) {
-  if ((M > 0 && Nout > 0) && (!x || !w_split || !y)) return sgg_set_err(SGG_E_BADARG, "tc_linear: null pointer");
-  if (ws && ws_bytes < sgg_tc_linear_workspace_bytes(M, Nout, K)) ws = nullptr;
-  return sgg::tc_linear(x, w_split, b, y, M, Nout, K, relu, (float *)ws, (cudaStream_t)stream);
-}
+}  // namespace sgg

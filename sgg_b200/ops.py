@@ -47,15 +47,21 @@ def _i64_rows(t, name):
 
 
 # ---- tensor-core mode ---------------------------------------------------------------------
-# 'tc'   : GEMM-shaped stages run on tcgen05 tensor cores with the 3xTF32 split (fp32-grade accuracy)
+# 'tc16' : GEMM-shaped stages on tcgen05 tensor cores, 3xFP16 split (kind::f16, csrc/tc16_gemm.cu)
+# 'tc32' : same stages, 3xTF32 split (kind::tf32, csrc/tc_gemm.cu)
+# 'tc'   : whichever of the two the library defaults to (SGG_TC_DEFAULT_MODE / env SGG_TC_MODE)
 # 'simt' : fp32 FMA tile kernels
+# All four are CUDA paths with fp32-grade accuracy; there is no CPU path.
 _MODE = {'gemm': 'tc'}
 _SPLIT_CACHE = {}
 
 
 def set_gemm_mode(mode):
-    if mode not in ('tc', 'simt'):
+    if mode not in ('tc', 'tc16', 'tc32', 'simt'):
         raise ValueError(mode)
+    if mode in ('tc16', 'tc32'):
+        check(_lib.load().sgg_tc_set_mode(1 if mode == 'tc16' else 0), 'sgg_tc_set_mode')
+        _SPLIT_CACHE.clear()        # a split is only valid for the engine it was made for
     _MODE['gemm'] = mode
 
 
@@ -63,11 +69,24 @@ def get_gemm_mode():
     return _MODE['gemm']
 
 
+def _use_tc():
+    return _MODE['gemm'] != 'simt'
+
+
+def tc_engine():
+    """'tc16' or 'tc32': the tensor-core engine the library currently dispatches to."""
+    return 'tc16' if _lib.load().sgg_tc_get_mode() == 1 else 'tc32'
+
+
+def _tc_k_ok(K):
+    return K % (8 if _lib.load().sgg_tc_get_mode() == 1 else 4) == 0
+
+
 def split_weight(w):
     """[hi | lo] 3xTF32 split of a weight tensor, cached per (storage, version) so it is recomputed only
     after the parameter changes (optimizer step / load_state_dict)."""
     key = id(w)
-    ver = (w._version, w.data_ptr(), tuple(w.shape))
+    ver = (w._version, w.data_ptr(), tuple(w.shape), _lib.load().sgg_tc_get_mode())
     hit = _SPLIT_CACHE.get(key)
     if hit is not None and hit[0] == ver and hit[2]() is w:      # same live tensor object, unchanged
         return hit[1]
@@ -126,7 +145,7 @@ def mp_weights(params, device=None):
         tw = _f32(params[k + '.0.weight'], k + '.0.weight', (1, 2 * H)); tb = _f32(params[k + '.0.bias'], k + '.0.bias', (1,))
         keep += [tw, tb]
         w.gate_w[i] = tw.data_ptr(); w.gate_b[i] = tb.data_ptr()
-    if _MODE['gemm'] == 'tc':
+    if _use_tc():
         for field, key in (('edge_w_ih_split', 'edge_gru.weight_ih'), ('edge_w_hh_split', 'edge_gru.weight_hh'),
                            ('node_w_ih_split', 'node_gru.weight_ih'), ('node_w_hh_split', 'node_gru.weight_hh')):
             sp = split_weight(params[key]); keep.append(sp)
@@ -143,7 +162,7 @@ def head_weights(params):
                        ('rel_fc_w', 'rel_fc.weight'), ('rel_fc_b', 'rel_fc.bias')):
         t = _f32(params[key], key); keep.append(t)
         setattr(hw, field, t.data_ptr())
-    if _MODE['gemm'] == 'tc':
+    if _use_tc():
         for field, key in (('obj_unary_w_split', 'obj_unary.weight'), ('edge_unary_w_split', 'edge_unary.weight'),
                            ('obj_fc_w_split', 'obj_fc.weight'), ('rel_fc_w_split', 'rel_fc.weight')):
             sp = split_weight(params[key]); keep.append(sp)
@@ -183,7 +202,7 @@ def linear(x, weight, bias=None, relu=False):
     M, K = x.shape
     Nout = weight.shape[0]
     y = torch.empty((M, Nout), dtype=torch.float32, device=x.device)
-    if _MODE['gemm'] == 'tc' and K % 4 == 0:
+    if _use_tc() and _tc_k_ok(K):
         sp = split_weight(weight)
         nb = lib.sgg_tc_linear_workspace_bytes(M, Nout, K)
         ws = torch.empty(nb, dtype=torch.uint8, device=x.device) if nb else None
@@ -370,7 +389,7 @@ def edge_gru(Eh, P, gates, graph, params):
     E, H = Eh.shape
     w_hh = _f32(params['edge_gru.weight_hh'], 'w_hh'); w_ih = _f32(params['edge_gru.weight_ih'], 'w_ih')
     b_ih = _f32(params['edge_gru.bias_ih'], 'b_ih'); b_hh = _f32(params['edge_gru.bias_hh'], 'b_hh')
-    sp = split_weight(params['edge_gru.weight_hh']) if _MODE['gemm'] == 'tc' else None
+    sp = split_weight(params['edge_gru.weight_hh']) if _use_tc() else None
     out = torch.empty_like(Eh)
     check(lib.sgg_edge_gru_forward(_ptr(Eh), _ptr(P), _ptr(gates), _ptr(graph.ws), _ptr(w_ih), _ptr(w_hh), _ptr(sp),
                                    _ptr(b_ih), _ptr(b_hh), graph.N, E, H, _ptr(out), _stream()), 'sgg_edge_gru_forward')
