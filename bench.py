@@ -203,6 +203,8 @@ def main():
     config = {'workload': workload, 'batch_per_gpu': args.batch, 'boxes_per_img': args.boxes,
               'edges_per_img': args.edges, 'mp_iter': args.iters, 'boundary': 'L1 (4096-d features -> dists)',
               'parallelism': 'dp%d (independent image shards, no data-path collective)' % max(world, 1)}
+    if args.impl == 'native' and not args.cpu_baseline_only:
+        torch.set_num_threads(min(8, os.cpu_count() or 1))     # host side of the CUDA arm is plumbing only
     params = synth.synth_params(111, level='l1')
 
     if args.cpu_baseline_only:

@@ -1,4 +1,9 @@
 import os, sys
+
+# The GPU boxes expose far more logical CPUs than the container may use: an unbounded OpenMP / MKL pool makes every
+# CPU-side op (parameter init, the numpy oracle) crawl.  Bound the pools before numpy / torch are imported.
+for _v in ('OMP_NUM_THREADS', 'MKL_NUM_THREADS', 'OPENBLAS_NUM_THREADS'):
+    os.environ.setdefault(_v, '8')
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

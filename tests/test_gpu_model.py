@@ -19,7 +19,9 @@ class FakeData:
 @pytest.fixture(scope='module')
 def model():
     from sgg_b200.model import RelModelStanford
-    m = RelModelStanford(train_data=FakeData(), mode='predcls').cuda()
+    with torch.device('cuda'):        # random init on the device: the weights are overwritten by the fixtures anyway
+        m = RelModelStanford(train_data=FakeData(), mode='predcls')
+    m = m.cuda()
     m.eval()
     return m
 
