@@ -33,6 +33,14 @@ from sgg_b200 import synth  # noqa: E402
 L2_BYTES_FALLBACK = 126 * 1024 * 1024
 
 
+_T0 = time.time()
+
+
+def log(msg):
+    """progress line on stderr (stdout carries exactly one JSON line)"""
+    sys.stderr.write('[bench %7.1fs] %s\n' % (time.time() - _T0, msg)); sys.stderr.flush()
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -133,7 +141,7 @@ def make_case(args, rank, slot):
     return dict(N=N, E=E, obj=of, edge=ef, rel=np.ascontiguousarray(g['rel_inds'][:, 1:3]))
 
 
-def cpu_baseline_subprocess(args, timeout_s=150):
+def cpu_baseline_subprocess(args, timeout_s=100):
     """Run the CPU-baseline leg in a fresh process (no CUDA context, clean OpenMP state) under a hard timeout, so a
     slow or wedged host-thread pool can never stall the benchmark itself."""
     cmd = [sys.executable, os.path.abspath(__file__), '--cpu-baseline-only', '--batch', str(args.batch), '--boxes',
@@ -155,18 +163,20 @@ def cpu_pick_threads(args, cases, params):
     oversubscription on a many-core box makes "all threads" much slower than a moderate count)."""
     from oracle.imp_torch_cpu import ImpCpu
     ncpu = os.cpu_count() or 1
-    cands = sorted(set(t for t in (ncpu, ncpu // 2, 64, 32, 16, 8) if 1 <= t <= ncpu), reverse=True)
+    cands = sorted(set(t for t in (ncpu, ncpu // 2, 64, 32, 16, 8) if 1 <= t <= ncpu))
     m = ImpCpu(mp_iter=args.iters).load_numpy(params).eval()
     o, e, r = (torch.from_numpy(cases[0][k]) for k in ('obj', 'edge', 'rel'))
     best, best_t = None, None
     with torch.no_grad():
-        for t in cands:
+        for t in cands:               # ascending; stop as soon as more threads make it clearly slower
             torch.set_num_threads(t)
             t0 = time.perf_counter(); m.l1_forward(o, e, r); dt = time.perf_counter() - t0
             if dt < 3.0:                  # second (warm) pass only when the first was not hopeless
                 t0 = time.perf_counter(); m.l1_forward(o, e, r); dt = time.perf_counter() - t0
             if best is None or dt < best:
                 best, best_t = dt, t
+            elif dt > 1.5 * best:
+                break
     return best_t, cands
 
 
@@ -251,6 +261,7 @@ def main():
     from sgg_b200 import ops, _lib
     from sgg_b200.runner import ImpL1Runner
     lib = _lib.load()
+    log('library loaded, tensor-core engine %s' % ops.tc_engine())
 
     info = (torch.cuda.get_device_properties(dev))
     l2 = getattr(info, 'L2_cache_size', L2_BYTES_FALLBACK) or L2_BYTES_FALLBACK
@@ -262,6 +273,7 @@ def main():
     config['l2_policy'] = 'input ring of %d x %.1f MB > %.0f MB L2 (features read from HBM every step)' % (
         ring, in_bytes / 1e6, l2 / 1e6)
 
+    log('synthetic cases ready (ring=%d)' % ring)
     dparams = {k: torch.from_numpy(v).to(dev) for k, v in params.items()}
     d_in = [(torch.from_numpy(c['obj']).to(dev), torch.from_numpy(c['edge']).to(dev),
              torch.from_numpy(c['rel']).to(dev)) for c in cases]
@@ -310,6 +322,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    log('launch mode: %s' % config.get('launch'))
     # ---- device-resident throughput ("value")
     for i in range(max(args.warmup, 3)):
         step(i)
@@ -327,6 +340,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
     ms_step = ms_total / args.steps
+    log('device-resident: %.3f ms/step' % ms_step)
 
     # ---- end-to-end through the host-buffer API ("e2e"): pinned host inputs, H2D + D2H inside the timed region
     runner = ImpL1Runner(dparams, N, E, args.iters, slots=3, device=dev)
@@ -350,6 +364,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     clocks = sampler.stop() if sampler is not None else None
+    log('e2e: %.3f ms/step' % (e2e_s * 1e3 / args.steps))
 
     if rank != 0:
         if dist is not None:
@@ -404,14 +419,18 @@ def main():
         traffic = json.load(open(tpath)).get('edge_gru_kernel_dram_bytes_per_launch')
     t_edge = stages['edge_gru_kernel'] * 1e-3
     ach = edge_bytes / t_edge / 1e9
-    roofline = {'bound': 'hbm', 'kernel': 'sgg::tc::k_tc_gemm<EPI_GRU_EDGE> (one edge-GRU update, %d launches/step)' % args.iters,
+    engine = ops.tc_engine()
+    kname = 'sgg::tc16::k_tc16<EPI_GRU_EDGE>' if engine == 'tc16' else 'sgg::tc::k_tc_gemm<EPI_GRU_EDGE>'
+    roofline = {'bound': 'hbm', 'kernel': '%s (one edge-GRU update, %d launches/step)' % (kname, args.iters),
+                'engine': engine,
                 'achieved': ach, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': ach / hbm_peak, 'traffic': traffic,
                 'peak_source': peak_src, 'algorithmic_bytes': edge_bytes, 'ms_per_launch': stages['edge_gru_kernel'],
-                'tensor': {'fp32_equiv_tflops': edge_flops / t_edge / 1e12, 'tf32_pass_tflops': 3 * edge_flops / t_edge / 1e12,
-                           'bf16_peak_tflops': tf_peak,
-                           'note': '3xTF32: every fp32-equivalent flop costs 3 tf32 MMA passes; tf32 dense peak is half the bf16 peak'},
+                'tensor': {'fp32_equiv_tflops': edge_flops / t_edge / 1e12, 'mma_pass_tflops': 3 * edge_flops / t_edge / 1e12,
+                           'bf16_peak_tflops': tf_peak, 'frac_of_bf16_peak_3pass': 3 * edge_flops / t_edge / 1e12 / tf_peak if tf_peak else None,
+                           'note': '3-pass split (3xFP16: kind::f16 at the bf16/fp16 rate; 3xTF32: kind::tf32 at half of it): '
+                                   'every fp32-equivalent flop costs 3 MMA passes'},
                 'note': 'the binding term of this kernel is tensor/operand-ingest, not HBM: its compulsory DRAM traffic is ~13 MB '
-                        '(weights + first touch, everything else L2-resident); see DESIGN.md section 5 and profiles/r01_ncu_edge_gru_tc.md',
+                        '(weights + first touch, everything else L2-resident); see DESIGN.md section 5 and profiles/',
                 'stage_ms': stages,
                 'stage_tflops_fp32_equiv': {'edge_unary_linear': unary_flops / (stages['edge_unary_linear'] * 1e-3) / 1e12,
                                             'message_pass': mp_flops / (stages['message_pass_T%d' % args.iters] * 1e-3) / 1e12},
@@ -424,9 +443,11 @@ def main():
                                'fp32_equiv_tflops': alg_flops_l1(N, E, H, D, args.iters) / (ms_step * 1e-3) / 1e12}}
 
     # ---- CPU baseline: the reference's CPU path (oracle port), bounded sample, rank 0 only at N=1
+    log('stage timings done: %s' % {k: round(v, 4) for k, v in stages.items()})
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline_subprocess(args)
+        log('cpu baseline done')
 
     images = args.batch * world
     line = {'metric': 'images/sec (PredCls, 3 MP iters)', 'value': images / (ms_step * 1e-3), 'unit': 'images/s',

@@ -133,7 +133,7 @@ SGG_API int sgg_linear_backward(const float *x, const float *w, const float *dy,
  * sgg_tc_split_weights: split = [hi(w) | lo(w)]; always pass a buffer of 2n floats; call once per weight version.
  * sgg_tc_linear_forward: same contract as sgg_linear_forward but takes the split weight.  K % 4 == 0 (mode 0),
  * K % 8 == 0 (mode 1). */
-#define SGG_TC_DEFAULT_MODE 0
+#define SGG_TC_DEFAULT_MODE 1
 SGG_API int sgg_tc_set_mode(int mode);
 SGG_API int sgg_tc_get_mode(void);
 SGG_API int sgg_tc_split_weights(const float *w, size_t n, float *split, void *stream);

@@ -55,7 +55,11 @@ struct Cfg {
   static constexpr int A_BYTES = BM * BKF * 4;
   static constexpr int BB_BYTES = NBR * BKF * 4;
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * NBLK * BB_BYTES;
-  static constexpr int STAGES = (SMEM_BUDGET / STAGE_BYTES) > 8 ? 8 : (SMEM_BUDGET / STAGE_BYTES);
+  // EVEN stage count: the two converter groups alternate k-blocks, so with an odd ring a group would revisit a
+  // stage only every second phase and its parity wait could be satisfied by the phase it skipped (mbarrier
+  // phases alias modulo 2) -> stale data / deadlock.  With an even ring group g only ever sees stages of parity g.
+  static constexpr int STAGES_RAW = (SMEM_BUDGET / STAGE_BYTES) > 8 ? 8 : (SMEM_BUDGET / STAGE_BYTES);
+  static constexpr int STAGES = STAGES_RAW >= 2 ? (STAGES_RAW & ~1) : STAGES_RAW;
   static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
   static constexpr int KCB = 256 / BKF;       // k-blocks per accumulation chunk (LINEAR)
 };

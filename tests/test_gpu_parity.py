@@ -22,9 +22,9 @@ def pdev(p):
     return {k: dev(v) for k, v in p.items()}
 
 
-@pytest.fixture(scope='module', params=['tc', 'simt'])
+@pytest.fixture(scope='module', params=['tc16', 'tc32', 'simt'])
 def ops(request):
-    """Every parity test runs twice: tcgen05 tensor-core path (3xTF32) and fp32 SIMT path."""
+    """Every parity test runs three times: tcgen05 tensor-core engines (3xFP16, 3xTF32) and the fp32 SIMT path."""
     from sgg_b200 import ops as _ops
     _ops.set_gemm_mode(request.param)
     yield _ops
