@@ -157,6 +157,16 @@ SGG_API int sgg_l1_forward(const float *obj_feat, const float *edge_feat, const 
                    int N, int E, int D, int H, int T, int n_cls, int n_rel,
                    float *obj_dists, float *rel_dists,
                    void *ws, size_t ws_bytes, void *stream);
+/* Same, starting from the int64 rel_inds the reference passes (rel_model_stanford.py:105): the graph index is
+ * built INSIDE the call, on the object-branch side stream, concurrently with the edge-unary GEMM, into graph_ws
+ * (sgg_graph_workspace_bytes(N, E)); one call = one step of the path. */
+SGG_API int sgg_l1_forward_rel(const float *obj_feat, const float *edge_feat,
+                   const int64_t *rel_inds, int64_t row_stride, int col_subj, int col_obj,
+                   void *graph_ws, size_t graph_ws_bytes,
+                   const sgg_head_weights *hw, const sgg_mp_weights *w,
+                   int N, int E, int D, int H, int T, int n_cls, int n_rel,
+                   float *obj_dists, float *rel_dists,
+                   void *ws, size_t ws_bytes, void *stream);
 
 /* ---- a8: draw_union_boxes (lib/draw_rectangles/draw_rectangles.pyx:12-67) ----
  * rois [N,5] (img,x1,y1,x2,y2) as in rel_model_base.py:147; union_inds int64

@@ -73,6 +73,10 @@ SIGNATURES = {
     'sgg_l1_forward': (C.c_int, [c_f, c_f, C.c_void_p, C.POINTER(HeadWeights), C.POINTER(MpWeights),
                                  C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                  c_f, c_f, C.c_void_p, C.c_size_t, C.c_void_p]),
+    'sgg_l1_forward_rel': (C.c_int, [c_f, c_f, c_i64p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_size_t,
+                                     C.POINTER(HeadWeights), C.POINTER(MpWeights),
+                                     C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                     c_f, c_f, C.c_void_p, C.c_size_t, C.c_void_p]),
     'sgg_draw_union_boxes': (C.c_int, [c_f, c_i64p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_f,
                                        C.c_void_p]),
     'sgg_geom_patches': (C.c_int, [c_f, c_i64p, C.c_int64, C.c_int, C.c_int, C.c_int, c_f, C.c_void_p]),

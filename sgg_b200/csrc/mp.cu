@@ -494,11 +494,12 @@ extern "C" size_t sgg_l1_workspace_bytes(int N, int E, int H, int T) {
   return sgg::l1_layout(&s, nullptr, N < 0 ? 0 : N, E < 0 ? 0 : E, H);
 }
 
-extern "C" int sgg_l1_forward(const float *obj_feat, const float *edge_feat, const void *graph_ws,
-                              const sgg_head_weights *hw, const sgg_mp_weights *w, int N, int E, int D, int H, int T,
-                              int n_cls, int n_rel, float *obj_dists, float *rel_dists, void *ws, size_t ws_bytes,
-                              void *stream) {
-  if (!hw || !w || !ws) return sgg_set_err(SGG_E_BADARG, "l1_forward: null pointer");
+static int l1_forward_impl(const float *obj_feat, const float *edge_feat, const int64_t *rel_inds, int64_t row_stride,
+                           int col_subj, int col_obj, void *graph_ws, size_t graph_ws_bytes,
+                           const sgg_head_weights *hw, const sgg_mp_weights *w, int N, int E, int D, int H, int T,
+                           int n_cls, int n_rel, float *obj_dists, float *rel_dists, void *ws, size_t ws_bytes,
+                           void *stream) {
+  if (!hw || !w || !ws || !graph_ws) return sgg_set_err(SGG_E_BADARG, "l1_forward: null pointer");
   if (N < 0 || E < 0 || H <= 0 || (H % sgg::BN) != 0) return sgg_set_err(SGG_E_BADARG, "l1_forward: bad shape");
   sgg::L1Scratch s;
   const size_t need = sgg::l1_layout(&s, ws, N, E, H);
@@ -512,7 +513,10 @@ extern "C" int sgg_l1_forward(const float *obj_feat, const float *edge_feat, con
   cudaStream_t sb = sgg::side_stream(st);
   const bool par = sb != nullptr && N > 0 && E > 0;
   cudaStream_t sn = par ? sb : st;
-  if (par && (rc = sgg::stream_order(st, sb))) return rc;         // fork: inputs / graph are ready on `st`
+  if (par && (rc = sgg::stream_order(st, sb))) return rc;         // fork: inputs (and a prebuilt graph) are ready on `st`
+  // graph index on the object-branch stream: it overlaps the edge-unary GEMM; every consumer is either on that
+  // stream (k_ctx) or behind the iteration-0 join of mp_forward (gates, edge GRU)
+  if (rel_inds && (rc = sgg_graph_build(rel_inds, row_stride, col_subj, col_obj, N, E, graph_ws, graph_ws_bytes, sn))) return rc;
   if ((rc = lin(obj_feat, hw->obj_unary_w, hw->obj_unary_w_split, hw->obj_unary_b, s.obj_rep, N, H, D, 0, s.ws_obj, sn))) return rc;
   if ((rc = lin(edge_feat, hw->edge_unary_w, hw->edge_unary_w_split, hw->edge_unary_b, s.rel_rep, E, H, D, 1, s.ws_edge, st))) return rc;
   if ((rc = sgg::mp_forward(s.obj_rep, s.rel_rep, graph_ws, w, N, E, H, T, s.V, s.Eh, nullptr, s.mp, s.mp_bytes, st, par)))
@@ -523,4 +527,22 @@ extern "C" int sgg_l1_forward(const float *obj_feat, const float *edge_feat, con
   if ((rc = lin(s.Eh, hw->rel_fc_w, hw->rel_fc_w_split, hw->rel_fc_b, rel_dists, E, n_rel, H, 0, s.ws_edge, st))) return rc;
   if (par && (rc = sgg::stream_order(sb, st))) return rc;
   return 0;
+}
+
+extern "C" int sgg_l1_forward(const float *obj_feat, const float *edge_feat, const void *graph_ws,
+                              const sgg_head_weights *hw, const sgg_mp_weights *w, int N, int E, int D, int H, int T,
+                              int n_cls, int n_rel, float *obj_dists, float *rel_dists, void *ws, size_t ws_bytes,
+                              void *stream) {
+  return l1_forward_impl(obj_feat, edge_feat, nullptr, 0, 0, 0, const_cast<void *>(graph_ws), 0, hw, w, N, E, D, H, T,
+                         n_cls, n_rel, obj_dists, rel_dists, ws, ws_bytes, stream);
+}
+
+extern "C" int sgg_l1_forward_rel(const float *obj_feat, const float *edge_feat, const int64_t *rel_inds,
+                                  int64_t row_stride, int col_subj, int col_obj, void *graph_ws, size_t graph_ws_bytes,
+                                  const sgg_head_weights *hw, const sgg_mp_weights *w, int N, int E, int D, int H, int T,
+                                  int n_cls, int n_rel, float *obj_dists, float *rel_dists, void *ws, size_t ws_bytes,
+                                  void *stream) {
+  if (E > 0 && !rel_inds) return sgg_set_err(SGG_E_BADARG, "l1_forward_rel: null rel_inds");
+  return l1_forward_impl(obj_feat, edge_feat, rel_inds, row_stride, col_subj, col_obj, graph_ws, graph_ws_bytes, hw, w, N,
+                         E, D, H, T, n_cls, n_rel, obj_dists, rel_dists, ws, ws_bytes, stream);
 }

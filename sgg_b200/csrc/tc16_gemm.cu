@@ -149,6 +149,8 @@ k_tc16(Params p, const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   constexpr int RS = NV * NBR + 4;
   static_assert(CHUNKED || (BM * RS * 4 <= STAGES * STAGE_BYTES), "epilogue staging must fit in the stage ring");
   static_assert(CHUNKED || ((RS / 4) & 1) == 1, "staging row stride");
+  constexpr int META_OFF = BM * RS * 4;            // [BM] int4 (subj, obj, g_sub, g_obj) after the staging tile
+  static_assert(CHUNKED || (META_OFF + BM * 16 <= STAGES * STAGE_BYTES), "row metadata must fit in the stage ring");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -339,9 +341,16 @@ k_tc16(Params p, const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     const int row = q * 32 + lane;
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
     float *stg = reinterpret_cast<float *>(smem) + (size_t)row * RS;
+    // EDGE: this row's endpoints and scalar gates, fetched while the main loop runs, parked next to the staging tile
+    int4 meta = make_int4(0, 0, 0, 0);
+    if (EPI == EPI_GRU_EDGE && m0 + row < p.M) {
+      const float4 g4 = ld4(p.gates + (size_t)(m0 + row) * 4);
+      meta = make_int4(__ldg(p.subj + m0 + row), __ldg(p.obj + m0 + row), __float_as_int(g4.x), __float_as_int(g4.y));
+    }
     mbar_wait(tmem_full, 0);                      // all MMAs done => all stages consumed, ring is free
     fence_after_sync();
     __syncwarp();
+    if (EPI == EPI_GRU_EDGE) reinterpret_cast<int4 *>(smem + META_OFF)[row] = meta;
 #pragma unroll
     for (int blk = 0; blk < NV; ++blk) {
       // source accumulator columns of this value block
@@ -371,55 +380,78 @@ k_tc16(Params p, const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   }
 
   if (!CHUNKED && warp >= 2) {
-    // ===================== GRU phase 2: pointwise, thread <-> (row, 4 hidden units), coalesced =====================
+    // ===================== GRU phase 2: pointwise, thread <-> (4 hidden units, every RPI-th row), coalesced =====================
+    // A thread keeps its hidden-unit quad for all its rows (biases live in registers); rows are processed U at a
+    // time with every load of the batch issued before the first use (branch-free: out-of-range rows are clamped
+    // for the loads and only their stores are predicated), so the P-row gathers overlap instead of chaining.
     named_bar_sync(1, 256);                       // staging complete (warps 6-9), converters idle (warps 2-5)
     const int H = p.H;
     constexpr int QPR = NBR / 4;                  // float4 groups per row
+    constexpr int RPI = 256 / QPR;                // rows per sweep of the 256 worker threads
+    constexpr int U = 2;
+    const int t2 = (int)threadIdx.x - 64;
+    const int qd = t2 % QPR, r0 = t2 / QPR;
+    const int j = j0 + 4 * qd;
     const float *stg0 = reinterpret_cast<const float *>(smem);
-#pragma unroll 2
-    for (int item = (int)threadIdx.x - 64; item < BM * QPR; item += 256) {
-      const int row = item / QPR, qd = item - row * QPR;
-      const int m = m0 + row, j = j0 + 4 * qd;
-      if (m >= p.M || j >= H) continue;
-      const float *sp = stg0 + (size_t)row * RS + 4 * qd;
-      const float4 a0 = ld4(sp), a1 = ld4(sp + NBR), a2 = ld4(sp + 2 * NBR);
+    const int4 *meta = reinterpret_cast<const int4 *>(smem + META_OFF);
+    if (r0 < RPI && j < H) {
       const float4 bir = ldg4(p.b_ih + j), biz = ldg4(p.b_ih + H + j), bin = ldg4(p.b_ih + 2 * H + j);
       const float4 bhr = ldg4(p.b_hh + j), bhz = ldg4(p.b_hh + H + j), bhn = ldg4(p.b_hh + 2 * H + j);
-      Gru4 o;
-      if (EPI == EPI_GRU_INIT) {                  // acc = x W_ih^T ; h = 0 => gh = b_hh
-        o = gru4(add4(a0, bir), bhr, add4(a1, biz), bhz, add4(a2, bin), bhn, make_float4(0.f, 0.f, 0.f, 0.f));
-      } else if (EPI == EPI_GRU_NODE) {           // a0 = gi_r + gh_r, a1 = gi_z + gh_z, a2 = gi_n, a3 = gh_n
-        const float4 a3 = ld4(sp + 3 * NBR);
-        const float4 hv = ld4(p.h + (size_t)m * H + j);
-        o = gru4(add4(a0, bir), bhr, add4(a1, biz), bhz, add4(a2, bin), add4(a3, bhn), hv);
-      } else {                                    // EDGE: acc = Eh W_hh^T ; gi = g_s P[s] + g_o P[o] + b_ih
-        const int s_id = __ldg(p.subj + m), o_id = __ldg(p.obj + m);
-        const float4 g4 = ld4(p.gates + (size_t)m * 4);
-        const float gs = g4.x, go = g4.y;
-        const float *ps = p.P + (size_t)s_id * 3 * H + j, *po = p.P + (size_t)o_id * 3 * H + j;
-        const float4 sr = ld4(ps), sz = ld4(ps + H), sn = ld4(ps + 2 * H);
-        const float4 orr = ld4(po), oz = ld4(po + H), on = ld4(po + 2 * H);
-        const float4 hv = ld4(p.h + (size_t)m * H + j);
-        float4 gir, giz, gin;
-        gir.x = fmaf(gs, sr.x, go * orr.x) + bir.x; gir.y = fmaf(gs, sr.y, go * orr.y) + bir.y;
-        gir.z = fmaf(gs, sr.z, go * orr.z) + bir.z; gir.w = fmaf(gs, sr.w, go * orr.w) + bir.w;
-        giz.x = fmaf(gs, sz.x, go * oz.x) + biz.x; giz.y = fmaf(gs, sz.y, go * oz.y) + biz.y;
-        giz.z = fmaf(gs, sz.z, go * oz.z) + biz.z; giz.w = fmaf(gs, sz.w, go * oz.w) + biz.w;
-        gin.x = fmaf(gs, sn.x, go * on.x) + bin.x; gin.y = fmaf(gs, sn.y, go * on.y) + bin.y;
-        gin.z = fmaf(gs, sn.z, go * on.z) + bin.z; gin.w = fmaf(gs, sn.w, go * on.w) + bin.w;
-        o = gru4(gir, add4(a0, bhr), giz, add4(a1, bhz), gin, add4(a2, bhn), hv);
-      }
-      *reinterpret_cast<float4 *>(p.out + (size_t)m * H + j) = o.out;
-      if (p.cache != nullptr) {
-        float *cp = p.cache + (size_t)m * 4 * H + j;
-        float4 ghn;                                // gh_n incl. bias, as the backward pass expects
-        if (EPI == EPI_GRU_INIT) ghn = bhn;
-        else if (EPI == EPI_GRU_NODE) ghn = add4(ld4(sp + 3 * NBR), bhn);
-        else ghn = add4(a2, bhn);
-        *reinterpret_cast<float4 *>(cp) = o.r;
-        *reinterpret_cast<float4 *>(cp + H) = o.z;
-        *reinterpret_cast<float4 *>(cp + 2 * H) = o.n;
-        *reinterpret_cast<float4 *>(cp + 3 * H) = ghn;
+      const int mlast = p.M - 1;
+      for (int rb = r0; rb < BM; rb += U * RPI) {
+        float4 a0[U], a1[U], a2[U], a3[U], hv[U], sr[U], sz[U], sn[U], orr[U], oz[U], on[U];
+        float gs[U], go[U];
+        int mm[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {             // ---- issue every load of the batch
+          const int row = min(rb + u * RPI, BM - 1);
+          mm[u] = m0 + row;
+          const int mc = min(mm[u], mlast);       // clamped row for the loads
+          const float *sp = stg0 + (size_t)row * RS + 4 * qd;
+          a0[u] = ld4(sp); a1[u] = ld4(sp + NBR); a2[u] = ld4(sp + 2 * NBR);
+          if (EPI == EPI_GRU_NODE) a3[u] = ld4(sp + 3 * NBR);
+          if (EPI != EPI_GRU_INIT) hv[u] = ld4(p.h + (size_t)mc * H + j);
+          else hv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (EPI == EPI_GRU_EDGE) {
+            const int4 mt = meta[row];
+            gs[u] = __int_as_float(mt.z); go[u] = __int_as_float(mt.w);
+            const float *ps = p.P + (size_t)mt.x * 3 * H + j, *po = p.P + (size_t)mt.y * 3 * H + j;
+            sr[u] = ld4(ps); sz[u] = ld4(ps + H); sn[u] = ld4(ps + 2 * H);
+            orr[u] = ld4(po); oz[u] = ld4(po + H); on[u] = ld4(po + 2 * H);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {             // ---- GRUCell pointwise + stores
+          Gru4 o;
+          float4 ghn;                             // gh_n incl. bias (saved for the backward pass)
+          if (EPI == EPI_GRU_INIT) {              // acc = x W_ih^T ; h = 0 => gh = b_hh
+            ghn = bhn;
+            o = gru4(add4(a0[u], bir), bhr, add4(a1[u], biz), bhz, add4(a2[u], bin), ghn, hv[u]);
+          } else if (EPI == EPI_GRU_NODE) {       // a0 = gi_r + gh_r, a1 = gi_z + gh_z, a2 = gi_n, a3 = gh_n
+            ghn = add4(a3[u], bhn);
+            o = gru4(add4(a0[u], bir), bhr, add4(a1[u], biz), bhz, add4(a2[u], bin), ghn, hv[u]);
+          } else {                                // EDGE: acc = Eh W_hh^T ; gi = g_s P[s] + g_o P[o] + b_ih
+            float4 gir, giz, gin;
+            gir.x = fmaf(gs[u], sr[u].x, go[u] * orr[u].x) + bir.x; gir.y = fmaf(gs[u], sr[u].y, go[u] * orr[u].y) + bir.y;
+            gir.z = fmaf(gs[u], sr[u].z, go[u] * orr[u].z) + bir.z; gir.w = fmaf(gs[u], sr[u].w, go[u] * orr[u].w) + bir.w;
+            giz.x = fmaf(gs[u], sz[u].x, go[u] * oz[u].x) + biz.x; giz.y = fmaf(gs[u], sz[u].y, go[u] * oz[u].y) + biz.y;
+            giz.z = fmaf(gs[u], sz[u].z, go[u] * oz[u].z) + biz.z; giz.w = fmaf(gs[u], sz[u].w, go[u] * oz[u].w) + biz.w;
+            gin.x = fmaf(gs[u], sn[u].x, go[u] * on[u].x) + bin.x; gin.y = fmaf(gs[u], sn[u].y, go[u] * on[u].y) + bin.y;
+            gin.z = fmaf(gs[u], sn[u].z, go[u] * on[u].z) + bin.z; gin.w = fmaf(gs[u], sn[u].w, go[u] * on[u].w) + bin.w;
+            ghn = add4(a2[u], bhn);
+            o = gru4(gir, add4(a0[u], bhr), giz, add4(a1[u], bhz), gin, ghn, hv[u]);
+          }
+          if (rb + u * RPI < BM && mm[u] < p.M) {
+            *reinterpret_cast<float4 *>(p.out + (size_t)mm[u] * H + j) = o.out;
+            if (p.cache != nullptr) {
+              float *cp = p.cache + (size_t)mm[u] * 4 * H + j;
+              *reinterpret_cast<float4 *>(cp) = o.r;
+              *reinterpret_cast<float4 *>(cp + H) = o.z;
+              *reinterpret_cast<float4 *>(cp + 2 * H) = o.n;
+              *reinterpret_cast<float4 *>(cp + 3 * H) = ghn;
+            }
+          }
+        }
       }
     }
   }

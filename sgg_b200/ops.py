@@ -229,12 +229,29 @@ class L1Plan(object):
         self.nbytes = lib.sgg_l1_workspace_bytes(N, E, self.H, mp_iter)
         self.ws = torch.empty(self.nbytes, dtype=torch.uint8, device=device)
         self._fn = lib.sgg_l1_forward
+        self.graph_ws, self.graph_bytes = None, 0
 
     def run(self, obj_feat, edge_feat, graph):
-        check(self._fn(_ptr(obj_feat), _ptr(edge_feat), _ptr(graph.ws), C.byref(self.hw), C.byref(self.w),
-                       self.N, self.E, self.D, self.H, self.T, self.n_cls, self.n_rel,
-                       _ptr(self.obj_dists), _ptr(self.rel_dists), _ptr(self.ws), self.nbytes, _stream()),
-              'sgg_l1_forward')
+        """graph: a prebuilt ``Graph``, or the int64 rel_inds [E, 2] themselves (global subject / object ids) — then the
+        graph index is built inside the same C-ABI call, overlapped with the edge-unary GEMM."""
+        if isinstance(graph, Graph):
+            check(self._fn(_ptr(obj_feat), _ptr(edge_feat), _ptr(graph.ws), C.byref(self.hw), C.byref(self.w),
+                           self.N, self.E, self.D, self.H, self.T, self.n_cls, self.n_rel,
+                           _ptr(self.obj_dists), _ptr(self.rel_dists), _ptr(self.ws), self.nbytes, _stream()),
+                  'sgg_l1_forward')
+            return self.obj_dists, self.rel_dists
+        rel, stride = _i64_rows(graph, 'rel_inds')
+        if rel.shape[0] != self.E:
+            raise _lib.SggError('rel_inds has %d rows, plan was made for E=%d' % (rel.shape[0], self.E))
+        if self.graph_ws is None:
+            self.graph_bytes = _lib.load().sgg_graph_workspace_bytes(self.N, self.E)
+            self.graph_ws = torch.empty(self.graph_bytes, dtype=torch.uint8, device=self.obj_dists.device)
+        check(_lib.load().sgg_l1_forward_rel(_ptr(obj_feat), _ptr(edge_feat), _ptr(rel), stride, 0, 1, _ptr(self.graph_ws),
+                                             self.graph_bytes, C.byref(self.hw), C.byref(self.w), self.N, self.E, self.D,
+                                             self.H, self.T, self.n_cls, self.n_rel, _ptr(self.obj_dists),
+                                             _ptr(self.rel_dists), _ptr(self.ws), self.nbytes, _stream()),
+              'sgg_l1_forward_rel')
+        self._rel_keep = rel
         return self.obj_dists, self.rel_dists
 
 

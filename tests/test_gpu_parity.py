@@ -72,6 +72,21 @@ def test_l1_forward_vs_golden(ops, name):
     cases.check_rows(rd, fx['rel_rows'], fx['rel_dists'], fx['rel_colsum'], TOL, 'rel_dists')
 
 
+def test_l1_fused_graph_entry_matches_prebuilt_graph(ops):
+    """sgg_l1_forward_rel (graph index built inside the call, on the side stream) == graph build + sgg_l1_forward."""
+    fx = cases.load('l1_cfg2')
+    of, ef, rel_inds, p, T = cases.l1_inputs(fx)
+    N, E = of.shape[0], ef.shape[0]
+    rel = dev(rel_inds)[:, 1:3]
+    plan = ops.L1Plan(pdev(p), N, E, of.shape[1], T, 'cuda')
+    o, e = dev(of), dev(ef)
+    od1, rd1 = (t.clone() for t in plan.run(o, e, ops.build_graph(rel, N)))
+    od2, rd2 = (t.clone() for t in plan.run(o, e, rel))          # column-slice view: stride 3
+    od3, rd3 = (t.clone() for t in plan.run(o, e, rel.contiguous()))
+    assert torch.equal(od1, od2) and torch.equal(rd1, rd2) and torch.equal(od1, od3) and torch.equal(rd1, rd3)
+    cases.check_rows(rd2.cpu().numpy(), fx['rel_rows'], fx['rel_dists'], fx['rel_colsum'], TOL, 'rel_dists')
+
+
 @pytest.mark.parametrize('M,N,K,relu', [(1, 51, 512, 0), (77, 151, 512, 0), (300, 512, 4096, 1), (130, 4096, 512, 1),
                                          (5, 64, 25088, 0), (257, 200, 64, 1)])
 def test_linear_vs_numpy(ops, M, N, K, relu):
