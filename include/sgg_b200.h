@@ -136,6 +136,9 @@ SGG_API int sgg_linear_backward(const float *x, const float *w, const float *dy,
 #define SGG_TC_DEFAULT_MODE 1
 SGG_API int sgg_tc_set_mode(int mode);
 SGG_API int sgg_tc_get_mode(void);
+/* debug aid: 8 clock64 phase timestamps per CTA of the last 3xFP16 kernel (needs SGG_TC_TIMING=1); host_out holds
+ * 8 * n_ctas values; synchronises the device. */
+SGG_API int sgg_tc_debug_timing(long long *host_out, int n_ctas);
 SGG_API int sgg_tc_split_weights(const float *w, size_t n, float *split, void *stream);
 SGG_API size_t sgg_tc_linear_workspace_bytes(int M, int Nout, int K);   /* split-K partials (0 = none needed) */
 SGG_API int sgg_tc_linear_forward(const float *x, const float *w_split, const float *b, float *y,

@@ -65,6 +65,7 @@ SIGNATURES = {
     'sgg_linear_forward': (C.c_int, [c_f, c_f, c_f, c_f, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     'sgg_tc_set_mode': (C.c_int, [C.c_int]),
     'sgg_tc_get_mode': (C.c_int, []),
+    'sgg_tc_debug_timing': (C.c_int, [C.POINTER(C.c_longlong), C.c_int]),
     'sgg_tc_split_weights': (C.c_int, [c_f, C.c_size_t, c_f, C.c_void_p]),
     'sgg_tc_linear_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     'sgg_tc_linear_forward': (C.c_int, [c_f, c_f, c_f, c_f, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t,

@@ -28,6 +28,7 @@
 // GRU tiles cover hidden units [j0, j0 + NBR) of the r, z, n gates (weight rows j0, H + j0, 2H + j0); NBR is
 // picked per launch from {32, 64, 80} by a wave-quantisation cost model (a ragged last column tile is masked).
 #include <cuda_fp16.h>
+#include <stdlib.h>
 #include "tc_gemm.cuh"
 #include "kernels.h"
 
@@ -55,7 +56,18 @@ struct Params {
   const float *gates;         // GRU_EDGE: [M,4]
   const int *subj, *obj;      // GRU_EDGE
   float *cache;               // GRU: nullable [M,4,H] (r, z, n, gh_n) for the backward pass
+  long long *dbg;             // nullable: per-CTA phase timestamps (SGG_TC_TIMING=1, tools/tc16_phases.py)
 };
+
+constexpr int DBG_SLOTS = 8, DBG_MAX_CTAS = 1024;
+__device__ long long g_dbg[DBG_SLOTS * DBG_MAX_CTAS];
+#define SGG_DBG(slot)                                                                                   \
+  do {                                                                                                  \
+    if (p.dbg != nullptr) {                                                                             \
+      const int cta_ = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);                  \
+      if (cta_ < DBG_MAX_CTAS) p.dbg[cta_ * DBG_SLOTS + (slot)] = clock64();                            \
+    }                                                                                                   \
+  } while (0)
 
 template <int NCOL>
 struct Cfg {
@@ -106,17 +118,25 @@ __device__ __forceinline__ void split2(float x0, float x1, uint32_t &hi, uint32_
 __device__ __forceinline__ float4 ld4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
 __device__ __forceinline__ float4 ldg4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
 
+// Fast, fp32-grade activations for the epilogue (it is instruction-bound: 3 transcendentals per hidden unit).
+// ex2.approx / rcp.approx carry ~2^-22 relative error => |error| < 3e-7 on sigmoid / tanh values, far inside the
+// 1e-4 parity bar; the accurate expf / tanhf versions cost ~25 instructions each and doubled the epilogue time.
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float fast_tanh(float x) {
+  const float e = __expf(-2.0f * fminf(fmaxf(x, -15.0f), 15.0f));      // clamp: tanh(+-15) == +-1 in fp32, no inf/inf
+  return __fdividef(1.0f - e, 1.0f + e);
+}
 // torch.nn.GRUCell pointwise on 4 hidden units; gi_* / gh_* include the biases
 struct Gru4 { float4 out, r, z, n; };
 __device__ __forceinline__ Gru4 gru4(const float4 &gir, const float4 &ghr, const float4 &giz, const float4 &ghz,
                                      const float4 &gin, const float4 &ghn, const float4 &h) {
   Gru4 o;
-  o.r.x = sgg_sigmoid(gir.x + ghr.x); o.r.y = sgg_sigmoid(gir.y + ghr.y);
-  o.r.z = sgg_sigmoid(gir.z + ghr.z); o.r.w = sgg_sigmoid(gir.w + ghr.w);
-  o.z.x = sgg_sigmoid(giz.x + ghz.x); o.z.y = sgg_sigmoid(giz.y + ghz.y);
-  o.z.z = sgg_sigmoid(giz.z + ghz.z); o.z.w = sgg_sigmoid(giz.w + ghz.w);
-  o.n.x = tanhf(gin.x + o.r.x * ghn.x); o.n.y = tanhf(gin.y + o.r.y * ghn.y);
-  o.n.z = tanhf(gin.z + o.r.z * ghn.z); o.n.w = tanhf(gin.w + o.r.w * ghn.w);
+  o.r.x = fast_sigmoid(gir.x + ghr.x); o.r.y = fast_sigmoid(gir.y + ghr.y);
+  o.r.z = fast_sigmoid(gir.z + ghr.z); o.r.w = fast_sigmoid(gir.w + ghr.w);
+  o.z.x = fast_sigmoid(giz.x + ghz.x); o.z.y = fast_sigmoid(giz.y + ghz.y);
+  o.z.z = fast_sigmoid(giz.z + ghz.z); o.z.w = fast_sigmoid(giz.w + ghz.w);
+  o.n.x = fast_tanh(gin.x + o.r.x * ghn.x); o.n.y = fast_tanh(gin.y + o.r.y * ghn.y);
+  o.n.z = fast_tanh(gin.z + o.r.z * ghn.z); o.n.w = fast_tanh(gin.w + o.r.w * ghn.w);
   o.out.x = (1.0f - o.z.x) * o.n.x + o.z.x * h.x; o.out.y = (1.0f - o.z.y) * o.n.y + o.z.y * h.y;
   o.out.z = (1.0f - o.z.z) * o.n.z + o.z.z * h.z; o.out.w = (1.0f - o.z.w) * o.n.w + o.z.w * h.w;
   return o;
@@ -168,6 +188,7 @@ k_tc16(Params p, const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   const int total = NSEG * kblocks;
 
   if (warp == 0 && lane == 0) {
+    SGG_DBG(0);
     prefetch_tmap(&tmA0); prefetch_tmap(&tmBh0); prefetch_tmap(&tmBl0);
     if (NSEG > 1) { prefetch_tmap(&tmA1); prefetch_tmap(&tmBh1); prefetch_tmap(&tmBl1); }
     for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(ready + s, 128); mbar_init(empty + s, 1); }
@@ -180,6 +201,7 @@ k_tc16(Params p, const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) SGG_DBG(1);
 
   auto stage_ptr = [&](int s) { return smem + (size_t)s * STAGE_BYTES; };   // [A (raw -> hi|lo) | B_hi | B_lo]
 
@@ -214,6 +236,7 @@ k_tc16(Params p, const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         mbar_wait(full + s, ph);
         mbar_wait(ready + s, ph);
         fence_after_sync();
+        if (it == 0) SGG_DBG(2);
         const int seg = it / kblocks, kb = it - seg * kblocks;
         uint8_t *st = stage_ptr(s);
         const uint64_t ah = make_sdesc128(st), al = make_sdesc128(st + A_HALF);
@@ -351,6 +374,7 @@ k_tc16(Params p, const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     fence_after_sync();
     __syncwarp();
     if (EPI == EPI_GRU_EDGE) reinterpret_cast<int4 *>(smem + META_OFF)[row] = meta;
+    if (threadIdx.x == 192) SGG_DBG(3);
 #pragma unroll
     for (int blk = 0; blk < NV; ++blk) {
       // source accumulator columns of this value block
@@ -377,19 +401,22 @@ k_tc16(Params p, const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           *reinterpret_cast<float4 *>(stg + blk * NBR + c0 + cc) = make_float4(v[cc], v[cc + 1], v[cc + 2], v[cc + 3]);
       }
     }
+    if (threadIdx.x == 192) SGG_DBG(4);
   }
 
-  if (!CHUNKED && warp >= 2) {
+  if (!CHUNKED) {
     // ===================== GRU phase 2: pointwise, thread <-> (4 hidden units, every RPI-th row), coalesced =====================
+    // All 10 warps take part (the TMA / MMA warps are done by now).
     // A thread keeps its hidden-unit quad for all its rows (biases live in registers); rows are processed U at a
     // time with every load of the batch issued before the first use (branch-free: out-of-range rows are clamped
     // for the loads and only their stores are predicated), so the P-row gathers overlap instead of chaining.
-    named_bar_sync(1, 256);                       // staging complete (warps 6-9), converters idle (warps 2-5)
+    __syncthreads();                              // staging complete (warps 6-9); every other warp is idle by now
+    if (threadIdx.x == 64) SGG_DBG(5);
     const int H = p.H;
     constexpr int QPR = NBR / 4;                  // float4 groups per row
-    constexpr int RPI = 256 / QPR;                // rows per sweep of the 256 worker threads
+    constexpr int RPI = NTHR / QPR;               // rows per sweep of the CTA
     constexpr int U = 2;
-    const int t2 = (int)threadIdx.x - 64;
+    const int t2 = (int)threadIdx.x;
     const int qd = t2 % QPR, r0 = t2 / QPR;
     const int j = j0 + 4 * qd;
     const float *stg0 = reinterpret_cast<const float *>(smem);
@@ -455,8 +482,10 @@ k_tc16(Params p, const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       }
     }
   }
+  if (!CHUNKED && threadIdx.x == 64) SGG_DBG(6);
   tc::fence_before_sync();
   __syncthreads();
+  if (threadIdx.x == 0) SGG_DBG(7);
   if (warp == 1) tc::tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
@@ -543,6 +572,25 @@ static int launch(const Params &p, const Seg *segs, int col_tiles, int splits, c
 
 static bool ok16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+static long long *dbg_ptr() {
+  static long long *ptr = nullptr;
+  static bool init = false;
+  if (!init) {
+    init = true;
+    const char *v = getenv("SGG_TC_TIMING");
+    if (v && atoi(v) != 0) {
+      void *sym = nullptr;
+      if (cudaGetSymbolAddress(&sym, g_dbg) == cudaSuccess) ptr = (long long *)sym;
+    }
+  }
+  return ptr;
+}
+int debug_timing(long long *host_out, int n_ctas) {
+  if (n_ctas > DBG_MAX_CTAS) n_ctas = DBG_MAX_CTAS;
+  SGG_CUDA_TRY(cudaMemcpyFromSymbol(host_out, g_dbg, sizeof(long long) * DBG_SLOTS * n_ctas));
+  return 0;
+}
+
 // LINEAR plan: tile width and split-K factor minimising waves x (chunks per CTA + fixed cost), with a penalty per
 // extra split for the partial-sum round trip.  Every split is a whole number of 256-wide accumulation chunks.
 struct LinPlan { int ncol, splits; };
@@ -591,7 +639,7 @@ int linear(const float *x, const float *w_split, const float *b, float *y, int M
     kb_per = ch_per * kcb;
     splits = (kblocks + kb_per - 1) / kb_per;
   }
-  Params p{}; p.M = M; p.K = K; p.Nout = Nout; p.relu = relu; p.bias = b; p.kb_per_split = kb_per;
+  Params p{}; p.M = M; p.K = K; p.Nout = Nout; p.relu = relu; p.bias = b; p.kb_per_split = kb_per; p.dbg = dbg_ptr();
   p.out = splits > 1 ? ws : y;
   const __half *wh = reinterpret_cast<const __half *>(w_split);
   Seg sg[2] = {{x, wh, wh + (size_t)Nout * K, Nout}, {}};
@@ -632,7 +680,7 @@ int gru(int mode, const float *x, const float *h, const float *w_ih_split, const
   if (M <= 0) return 0;
   if (H % 16) return sgg_set_err(SGG_E_BADARG, "tc16 gru: H %% 16");
   Params p{}; p.M = M; p.K = H; p.H = H; p.b_ih = b_ih; p.b_hh = b_hh; p.h = h; p.P = P; p.gates = gates;
-  p.subj = subj; p.obj = obj; p.out = out; p.cache = cache;
+  p.subj = subj; p.obj = obj; p.out = out; p.cache = cache; p.dbg = dbg_ptr();
   const size_t wn = (size_t)3 * H * H;
   const __half *wih = reinterpret_cast<const __half *>(w_ih_split), *whh = reinterpret_cast<const __half *>(w_hh_split);
   if (mode == 1) {

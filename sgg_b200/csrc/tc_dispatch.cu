@@ -22,6 +22,7 @@ int gru(int mode, const float *x, const float *h, const float *w_ih_split, const
         const float *b_hh, const float *P, const float *gates, const int *subj, const int *obj, float *out, float *cache,
         int M, int H, cudaStream_t st);
 int split_weights(const float *w, size_t n, void *split, cudaStream_t st);
+int debug_timing(long long *host_out, int n_ctas);
 }  // namespace tc16
 
 static std::atomic<int> g_tc_mode{-1};
@@ -79,4 +80,13 @@ extern "C" int sgg_tc_linear_forward(const float *x, const float *w_split, const
   if ((M > 0 && Nout > 0) && (!x || !w_split || !y)) return sgg_set_err(SGG_E_BADARG, "tc_linear: null pointer");
   if (ws && ws_bytes < sgg_tc_linear_workspace_bytes(M, Nout, K)) ws = nullptr;
   return sgg::tc_linear(x, w_split, b, y, M, Nout, K, relu, (float *)ws, (cudaStream_t)stream);
+}
+
+/* debug: per-CTA phase timestamps (8 clock64 values per CTA) of the most recent 3xFP16 kernel; only recorded when the
+ * process runs with SGG_TC_TIMING=1.  Synchronises the device. */
+extern "C" int sgg_tc_debug_timing(long long *host_out, int n_ctas) {
+  if (!host_out || n_ctas <= 0) return sgg_set_err(SGG_E_BADARG, "tc_debug_timing: bad argument");
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) return sgg_set_err((int)e, "tc_debug_timing: %s", cudaGetErrorString(e));
+  return sgg::tc16::debug_timing(host_out, n_ctas);
 }
