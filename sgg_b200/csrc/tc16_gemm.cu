@@ -106,13 +106,14 @@ __device__ __forceinline__ uint4 lds128u(uint32_t addr) {
 __device__ __forceinline__ void sts128u(uint32_t addr, const uint4 &v) {
   asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
-// (x0, x1) -> packed fp16 hi pair and packed fp16 scaled-lo pair
+// (x0, x1) -> packed fp16 hi pair and packed fp16 scaled-lo pair (x0 in the low half); cvt.rn.f16x2.f32 packs two
+// conversions into one instruction
 __device__ __forceinline__ void split2(float x0, float x1, uint32_t &hi, uint32_t &lo) {
-  const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
-  const __half l0 = __float2half_rn((x0 - __half2float(h0)) * LO_SCALE);
-  const __half l1 = __float2half_rn((x1 - __half2float(h1)) * LO_SCALE);
-  hi = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-  lo = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+  const __half2 h = __floats2half2_rn(x0, x1);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn((x0 - hf.x) * LO_SCALE, (x1 - hf.y) * LO_SCALE);
+  hi = *reinterpret_cast<const uint32_t *>(&h);
+  lo = *reinterpret_cast<const uint32_t *>(&l);
 }
 
 __device__ __forceinline__ float4 ld4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
@@ -156,6 +157,7 @@ k_tc16(Params p, const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   using C = Cfg<NCOL>;
   constexpr int STAGES = C::STAGES, STAGE_BYTES = C::STAGE_BYTES, B_BYTES = C::B_BYTES, KCB = C::KCB;
   constexpr bool CHUNKED = (EPI == EPI_LINEAR);
+  constexpr int NCONV = CHUNKED ? 4 : 8;           // converter warps (GRU: the TMEM-reader warps convert too)
   static_assert(!CHUNKED || (NSEG == 1 && NBLK == 1 && NCOL <= 128), "chunked LINEAR: NCOL register accumulators");
   static_assert(NCOL % 16 == 0 && NCOL <= 256 && NBR % 16 == 0, "UMMA N / TMEM load granularity");
   static_assert(STAGES >= 2, "pipeline needs two stages");
@@ -191,7 +193,7 @@ k_tc16(Params p, const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     SGG_DBG(0);
     prefetch_tmap(&tmA0); prefetch_tmap(&tmBh0); prefetch_tmap(&tmBl0);
     if (NSEG > 1) { prefetch_tmap(&tmA1); prefetch_tmap(&tmBh1); prefetch_tmap(&tmBl1); }
-    for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(ready + s, 128); mbar_init(empty + s, 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(ready + s, NCONV * 32); mbar_init(empty + s, 1); }
     mbar_init(tmem_full, 1); mbar_init(tmem_full + 1, 1);
     mbar_init(tmem_empty, 128); mbar_init(tmem_empty + 1, 128);
     fence_barrier_init();
@@ -268,21 +270,26 @@ k_tc16(Params p, const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       }
       if (!CHUNKED) mma_commit(tmem_full);
     }
-  } else if (warp < 6) {
+  } else {
+   // warps 2..9
+   if (warp - 2 < NCONV) {
     // ===================== convert A: fp32 -> fp16 [hi | lo], in place =====================
     // Swizzle atom g = rows 8g..8g+7: its raw floats live at [g*1024, +1024) of both 16 KB boxes, exactly where its
     // hi (first box) and lo (second box) fp16 rows go.  Lane <-> (row r, 16-byte output chunk c): k = 8c .. 8c+7.
-    const int w4 = warp - 2;                               // atoms 4*w4 .. 4*w4+3
+    // The loop is instruction-bound (it set the k-block time with 4 warps), hence the packed f16x2 conversions and,
+    // in the GRU kernels whose TMEM readers are idle until the end, 8 converter warps.
+    constexpr int APW = 16 / NCONV;                        // swizzle atoms per warp and k-block
+    const int wc = warp - 2;
     const int c = lane & 7, b = c >> 2;                    // output chunk; source box
     const int ca = 2 * (c & 3);                            // first raw chunk (logical) inside the box
     for (int it = 0; it < total; ++it) {
       const int s = it % STAGES, ph = (it / STAGES) & 1;
       mbar_wait(full + s, ph);
       const uint32_t a_addr = smem_u32(stage_ptr(s));
-      uint4 v[16];
+      uint4 v[4 * APW];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {                        // i = 2*atom + row half
-        const int g = 4 * w4 + (i >> 1), r = (lane >> 3) + 4 * (i & 1);
+      for (int i = 0; i < 2 * APW; ++i) {                  // i = 2*atom + row half
+        const int g = APW * wc + (i >> 1), r = (lane >> 3) + 4 * (i & 1);
         const uint32_t rowb = a_addr + (uint32_t)(b * A_HALF + g * 1024 + r * 128);
         // bank spread: lanes reading box 1 fetch the odd chunk first
         v[2 * i] = lds128u(rowb + (uint32_t)((((ca + b) ^ r) & 7) << 4));
@@ -290,8 +297,8 @@ k_tc16(Params p, const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       }
       __syncwarp();                                        // every lane's reads of these atoms are done
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int g = 4 * w4 + (i >> 1), r = (lane >> 3) + 4 * (i & 1);
+      for (int i = 0; i < 2 * APW; ++i) {
+        const int g = APW * wc + (i >> 1), r = (lane >> 3) + 4 * (i & 1);
         const uint4 f0 = b ? v[2 * i + 1] : v[2 * i], f1 = b ? v[2 * i] : v[2 * i + 1];   // floats 0-3, 4-7 of the chunk
         uint4 hi, lo;
         split2(__uint_as_float(f0.x), __uint_as_float(f0.y), hi.x, lo.x);
@@ -305,7 +312,10 @@ k_tc16(Params p, const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       fence_proxy_async_smem();
       mbar_arrive(ready + s);
     }
-  } else if (CHUNKED) {
+   }
+   if (warp < 6) {
+    // converter-only warps: nothing else until the pointwise phase
+   } else if (CHUNKED) {
     // ===================== LINEAR: drain chunks into fp32 registers, thread <-> output row =====================
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;
@@ -358,7 +368,7 @@ k_tc16(Params p, const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         }
       }
     }
-  } else {
+   } else {
     // ===================== GRU phase 1: TMEM -> shared staging, thread <-> accumulator row =====================
     const int q = warp & 3;
     const int row = q * 32 + lane;
@@ -402,6 +412,7 @@ k_tc16(Params p, const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       }
     }
     if (threadIdx.x == 192) SGG_DBG(4);
+   }
   }
 
   if (!CHUNKED) {
