@@ -41,17 +41,19 @@ extern "C" int sgg_device_info(int out[4]) {
 
 // ---- fork/join helper: one side stream + a ring of timing-less events per process (capturable) ----
 namespace sgg {
-// one side stream per caller stream (so pipelined callers on different streams do not serialise on it)
-cudaStream_t side_stream(cudaStream_t main) {
-  static cudaStream_t keys[16];
-  static cudaStream_t vals[16];
+// side streams per caller stream (so pipelined callers on different streams do not serialise on them);
+// idx 0 = object branch, idx 1 = the P = V W_ih^T GEMM of the message-passing loop
+cudaStream_t side_stream(cudaStream_t main, int idx) {
+  static cudaStream_t keys[32];
+  static int kidx[32];
+  static cudaStream_t vals[32];
   static int n = 0;
   for (int i = 0; i < n; ++i)
-    if (keys[i] == main) return vals[i];
+    if (keys[i] == main && kidx[i] == idx) return vals[i];
   cudaStream_t s = nullptr;
   if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
-  if (n < 16) { keys[n] = main; vals[n] = s; ++n; return s; }
-  keys[0] = main; vals[0] = s;      // table full: recycle slot 0 (the old stream is leaked, bounded)
+  if (n < 32) { keys[n] = main; kidx[n] = idx; vals[n] = s; ++n; return s; }
+  keys[0] = main; kidx[0] = idx; vals[0] = s;      // table full: recycle slot 0 (the old stream is leaked, bounded)
   return s;
 }
 cudaEvent_t next_event() {

@@ -2,7 +2,7 @@
 #pragma once
 #include "common.cuh"
 namespace sgg {
-cudaStream_t side_stream(cudaStream_t main);
+cudaStream_t side_stream(cudaStream_t main, int idx = 0);
 int stream_order(cudaStream_t from, cudaStream_t to);
 int launch_linear(const float *x, const float *w, const float *b, float *y, int M, int Nout, int K, int relu,
                   cudaStream_t st);

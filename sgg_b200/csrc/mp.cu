@@ -352,10 +352,12 @@ int mp_forward(const float *obj_rep, const float *rel_rep, const void *graph_ws,
     return it == T ? E_out : s.Eh[it & 1];
   };
   int rc;
-  cudaStream_t sb = side_stream(st);
-  const bool par = sb != nullptr && N > 0 && E > 0;
-  cudaStream_t sn = par ? sb : st;                 // stream of the object branch
+  cudaStream_t sb = side_stream(st, 0), sc = side_stream(st, 1);
+  const bool par = sb != nullptr && sc != nullptr && N > 0 && E > 0;
+  cudaStream_t sn = par ? sb : st;                 // stream of the object branch (ctx, node GRU)
+  cudaStream_t sp = par ? sc : st;                 // stream of P = V W_ih^T (needs only V: starts at the iteration boundary)
   if (par && !obj_on_side && (rc = stream_order(st, sb))) return rc;
+  if (!par && obj_on_side && sb != nullptr && (rc = stream_order(sb, st))) return rc;   // caller forked, we run serial
   {  // hx = 0 initial step (:68-72)
     GruArgs a{}; a.x = obj_rep; a.h = nullptr; a.w_ih = w->node_w_ih; a.w_hh = w->node_w_hh; a.b_ih = w->node_b_ih;
     a.b_hh = w->node_b_hh; a.out = vbuf(0); a.cache = cacheV(0); a.M = N; a.H = H;
@@ -377,9 +379,11 @@ int mp_forward(const float *obj_rep, const float *rel_rep, const void *graph_ws,
       s.ctx = tape.ctx + (size_t)it * N * H;
       s.P = tape.P + (size_t)it * N * 3 * H;
     }
-    if (par) {     // iteration boundary: both branches see each other's previous-iteration results / reads
+    if (par) {     // iteration boundary: every branch sees the others' previous-iteration results / reads
       if ((rc = stream_order(sb, st))) return rc;     // V_it ready for the gates; old gates / ctx no longer read
-      if ((rc = stream_order(st, sb))) return rc;     // Eh_it ready; previous edge GRU no longer reads P
+      if ((rc = stream_order(st, sb))) return rc;     // Eh_it ready for ctx
+      if ((rc = stream_order(sb, sp))) return rc;     // V_it ready for P
+      if ((rc = stream_order(st, sp))) return rc;     // previous edge GRU no longer reads P
     }
     if (N > 0) {
       k_gate_node<<<(N * 32 + 255) / 256, 256, 0, st>>>(V, N, H, w->gate_w[0], w->gate_w[1], w->gate_w[2],
@@ -392,12 +396,12 @@ int mp_forward(const float *obj_rep, const float *rel_rep, const void *graph_ws,
           w->gate_b[3], s.a, g.subj, g.obj, s.g);
       SGG_RETURN_IF_LAUNCH_FAILED("k_gate_edge");
       if (w->edge_w_ih_split) {
-        if ((rc = tc_linear(V, w->edge_w_ih_split, nullptr, s.P, N, 3 * H, H, 0, s.lin_ws, sn))) return rc;
-      } else if ((rc = launch_linear(V, w->edge_w_ih, nullptr, s.P, N, 3 * H, H, 0, sn))) return rc;
+        if ((rc = tc_linear(V, w->edge_w_ih_split, nullptr, s.P, N, 3 * H, H, 0, s.lin_ws, sp))) return rc;
+      } else if ((rc = launch_linear(V, w->edge_w_ih, nullptr, s.P, N, 3 * H, H, 0, sp))) return rc;
     }
     if (par) {
       if ((rc = stream_order(st, sb))) return rc;     // gates -> ctx
-      if ((rc = stream_order(sb, st))) return rc;     // P -> edge GRU
+      if ((rc = stream_order(sp, st))) return rc;     // P -> edge GRU
     }
     if (N > 0) {
       k_ctx<<<N, (H / 4 < 128 ? H / 4 : 128), 0, sn>>>(Eh, s.g, g.out_ptr, g.out_idx, g.in_ptr, g.in_idx, H, s.ctx);

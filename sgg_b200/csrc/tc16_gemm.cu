@@ -157,8 +157,8 @@ k_tc16(Params p, const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   using C = Cfg<NCOL>;
   constexpr int STAGES = C::STAGES, STAGE_BYTES = C::STAGE_BYTES, B_BYTES = C::B_BYTES, KCB = C::KCB;
   constexpr bool CHUNKED = (EPI == EPI_LINEAR);
-  constexpr int NCONV = CHUNKED ? 4 : 8;           // converter warps (GRU: the TMEM-reader warps convert too)
-  static_assert(!CHUNKED || (NSEG == 1 && NBLK == 1 && NCOL <= 128), "chunked LINEAR: NCOL register accumulators");
+  constexpr int NCONV = 8;                         // converter warps = all worker warps (2..9)
+  static_assert(!CHUNKED || (NSEG == 1 && NBLK == 1 && NCOL <= 128 && NCOL % 32 == 0), "chunked LINEAR: NCOL/2 register accumulators per thread");
   static_assert(NCOL % 16 == 0 && NCOL <= 256 && NBR % 16 == 0, "UMMA N / TMEM load granularity");
   static_assert(STAGES >= 2, "pipeline needs two stages");
   // TMEM columns: GRU: [main seg0, main seg1 | corr seg0, corr seg1]; LINEAR: buffer b = [main_b | corr_b]
@@ -195,7 +195,7 @@ k_tc16(Params p, const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     if (NSEG > 1) { prefetch_tmap(&tmA1); prefetch_tmap(&tmBh1); prefetch_tmap(&tmBl1); }
     for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(ready + s, NCONV * 32); mbar_init(empty + s, 1); }
     mbar_init(tmem_full, 1); mbar_init(tmem_full + 1, 1);
-    mbar_init(tmem_empty, 128); mbar_init(tmem_empty + 1, 128);
+    mbar_init(tmem_empty, 256); mbar_init(tmem_empty + 1, 256);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -271,18 +271,16 @@ k_tc16(Params p, const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       if (!CHUNKED) mma_commit(tmem_full);
     }
   } else {
-   // warps 2..9
-   if (warp - 2 < NCONV) {
-    // ===================== convert A: fp32 -> fp16 [hi | lo], in place =====================
+    // ===================== warps 2..9: convert A (fp32 -> fp16 [hi | lo], in place); LINEAR: + chunk drains =====================
     // Swizzle atom g = rows 8g..8g+7: its raw floats live at [g*1024, +1024) of both 16 KB boxes, exactly where its
     // hi (first box) and lo (second box) fp16 rows go.  Lane <-> (row r, 16-byte output chunk c): k = 8c .. 8c+7.
-    // The loop is instruction-bound (it set the k-block time with 4 warps), hence the packed f16x2 conversions and,
-    // in the GRU kernels whose TMEM readers are idle until the end, 8 converter warps.
+    // The conversion is instruction-bound and every k-block passes through it, so all eight worker warps take part
+    // (two atoms each) and use packed f16x2 conversions.
     constexpr int APW = 16 / NCONV;                        // swizzle atoms per warp and k-block
     const int wc = warp - 2;
     const int c = lane & 7, b = c >> 2;                    // output chunk; source box
     const int ca = 2 * (c & 3);                            // first raw chunk (logical) inside the box
-    for (int it = 0; it < total; ++it) {
+    auto convert = [&](int it) {
       const int s = it % STAGES, ph = (it / STAGES) & 1;
       mbar_wait(full + s, ph);
       const uint32_t a_addr = smem_u32(stage_ptr(s));
@@ -311,27 +309,28 @@ k_tc16(Params p, const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       }
       fence_proxy_async_smem();
       mbar_arrive(ready + s);
-    }
-   }
-   if (warp < 6) {
-    // converter-only warps: nothing else until the pointwise phase
-   } else if (CHUNKED) {
-    // ===================== LINEAR: drain chunks into fp32 registers, thread <-> output row =====================
+    };
+   if (CHUNKED) {
+    // ===================== LINEAR: thread <-> (output row, half of the tile's columns) =====================
+    // Chunk ch (256 of K) is drained from TMEM into fp32 registers one k-block AFTER its last k-block was converted,
+    // when its MMAs have (nearly) finished, so the drains do not stall the conversion stream; the MMA issuer needs
+    // the buffer back only a whole chunk later.
+    constexpr int HC = NCOL / 2;
+    const int half = warp >= 6 ? 1 : 0;
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;
     const int m = m0 + row;
-    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-    float acc[NCOL];
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * HC);
+    float acc[HC];
 #pragma unroll
-    for (int cc = 0; cc < NCOL; ++cc) acc[cc] = 0.f;
-    const int nchunks = (total + KCB - 1) / KCB;
-    for (int ch = 0; ch < nchunks; ++ch) {
+    for (int cc = 0; cc < HC; ++cc) acc[cc] = 0.f;
+    auto drain = [&](int ch) {
       const int bsel = ch & 1;
       mbar_wait(tmem_full + bsel, (ch >> 1) & 1);
       fence_after_sync();
       __syncwarp();
 #pragma unroll
-      for (int c0 = 0; c0 < NCOL; c0 += 16) {
+      for (int c0 = 0; c0 < HC; c0 += 16) {
         float v[16], w[16];
         tmem_ld16(taddr + (uint32_t)(bsel * 2 * NCOL + c0), v);
         tmem_ld16(taddr + (uint32_t)(bsel * 2 * NCOL + NCOL + c0), w);
@@ -341,14 +340,20 @@ k_tc16(Params p, const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       }
       fence_before_sync();
       mbar_arrive(tmem_empty + bsel);
+    };
+    const int nchunks = (total + KCB - 1) / KCB;
+    for (int it = 0; it < total; ++it) {
+      convert(it);
+      if (it > 0 && (it % KCB) == 0) drain(it / KCB - 1);
     }
+    drain(nchunks - 1);
     if (m < p.M) {
       const bool partial = gridDim.z > 1;        // split-K: raw partial sums, bias/ReLU applied by the reducer
       const bool vec = (p.Nout & 3) == 0;
       float *yrow = p.out + ((size_t)blockIdx.z * p.M + m) * p.Nout;
 #pragma unroll
-      for (int c0 = 0; c0 < NCOL; c0 += 4) {
-        const int j = j0 + c0;
+      for (int c0 = 0; c0 < HC; c0 += 4) {
+        const int j = j0 + half * HC + c0;
         if (j < p.Nout) {
           float v[4];
 #pragma unroll
@@ -369,6 +374,9 @@ k_tc16(Params p, const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       }
     }
    } else {
+    for (int it = 0; it < total; ++it) convert(it);
+   }
+   if (!CHUNKED && warp >= 6) {
     // ===================== GRU phase 1: TMEM -> shared staging, thread <-> accumulator row =====================
     const int q = warp & 3;
     const int row = q * 32 + lane;
@@ -622,9 +630,10 @@ static LinPlan plan_linear(int M, int Nout, int K, bool allow_split) {
       const int s_eff = (chunks + ch_per - 1) / ch_per;
       if (s_eff != s) continue;
       const long waves = (tiles * s + sms - 1) / sms;
-      // per-CTA time ~ chunks x (A rows + B rows) ; fixed prologue/epilogue ~ 0.6 chunk of a 128-wide tile
-      const double per = ch_per * (128.0 + ncol) / 256.0 + 0.6;
-      const double cost = waves * per + (s > 1 ? 0.25 * s + 0.5 : 0.0);
+      // per-CTA time ~ chunks x (A rows + B rows) ; fixed prologue/epilogue ~ 1.5 chunks of a 128-wide tile (measured: ~7k of ~1k-cycle k-blocks)
+      const double per = ch_per * (128.0 + ncol) / 256.0 + 1.5;
+      // split-K adds the partial-sum round trip, the reducer kernel and one more dependent launch (~13 us measured)
+      const double cost = waves * per + (s > 1 ? 0.3 * s + 3.0 : 0.0);
       if (cost < best_cost - 1e-9) { best_cost = cost; best.ncol = ncol; best.splits = s; }
     }
   }
