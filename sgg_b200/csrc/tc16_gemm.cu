@@ -615,6 +615,7 @@ int debug_timing(long long *host_out, int n_ctas) {
 struct LinPlan { int ncol, splits; };
 static LinPlan plan_linear(int M, int Nout, int K, bool allow_split) {
   const int sms = sgg_num_sms();
+  static const double split_fixed = getenv("SGG_TC16_SPLIT_COST") ? atof(getenv("SGG_TC16_SPLIT_COST")) : 3.0;   // tuning knob
   const int chunks = (K + 255) / 256;
   const int rows = (M + BM - 1) / BM;
   LinPlan best{Nout <= 64 ? 64 : 128, 1};
@@ -633,7 +634,7 @@ static LinPlan plan_linear(int M, int Nout, int K, bool allow_split) {
       // per-CTA time ~ chunks x (A rows + B rows) ; fixed prologue/epilogue ~ 1.5 chunks of a 128-wide tile (measured: ~7k of ~1k-cycle k-blocks)
       const double per = ch_per * (128.0 + ncol) / 256.0 + 1.5;
       // split-K adds the partial-sum round trip, the reducer kernel and one more dependent launch (~13 us measured)
-      const double cost = waves * per + (s > 1 ? 0.3 * s + 3.0 : 0.0);
+      const double cost = waves * per + (s > 1 ? 0.3 * s + split_fixed : 0.0);
       if (cost < best_cost - 1e-9) { best_cost = cost; best.ncol = ncol; best.splits = s; }
     }
   }

@@ -100,6 +100,20 @@ def test_linear_vs_numpy(ops, M, N, K, relu):
     assert np.abs(y - ref).max() <= 2e-5 * max(1.0, np.abs(ref).max())
 
 
+@pytest.mark.parametrize('scale', [1e3, 1.0, 1e-5])
+def test_linear_dynamic_range(ops, scale):
+    """The 3xFP16 engine keeps fp32-grade RELATIVE accuracy across magnitudes: large inputs (below the fp16 limit of
+    65504) and inputs whose fp16 'hi' part is subnormal or zero (the scaled 'lo' part carries them)."""
+    rng = np.random.default_rng(17)
+    M, N, K = 200, 96, 1024
+    x = (rng.standard_normal((M, K), dtype=np.float32) * np.float32(scale)).astype(np.float32)
+    w = (rng.standard_normal((N, K), dtype=np.float32) / np.float32(np.sqrt(K))).astype(np.float32)
+    y = ops.linear(dev(x), dev(w), None).cpu().numpy()
+    ref = x.astype(np.float64) @ w.astype(np.float64).T
+    assert np.isfinite(y).all()
+    assert np.abs(y - ref).max() <= 2e-5 * np.abs(ref).max()
+
+
 def test_draw_union_boxes_bit_exact(ops):
     fx = cases.load('draw_union_boxes')
     pairs = fx['pairs']
