@@ -48,6 +48,11 @@ enum { EPI_LINEAR = 0, EPI_GRU_INIT = 1, EPI_GRU_NODE = 2, EPI_GRU_EDGE = 3 };
 struct Params {
   int M, K, H, Nout, relu;
   int kb_per_split;           // LINEAR split-K: k-blocks per blockIdx.z
+  // LINEAR stream-K (sk_W > 0): the (tile, 256-wide K chunk) space of sk_W chunks is cut into gridDim.x equal
+  // contiguous ranges; a CTA writes one [BM x NCOL] partial per tile it touches into sk_part (slot = cta * sk_maxseg
+  // + segment) and k_tc16_streamk_reduce sums them in CTA order.  sk_C = chunks per tile, sk_ct = column tiles.
+  int sk_W, sk_C, sk_ct, sk_maxseg;
+  float *sk_part;
   const float *bias;          // LINEAR
   float *out;                 // LINEAR: [M,Nout] (or partials [splits,M,Nout]); GRU: [M,H]
   const float *b_ih, *b_hh;   // GRU
@@ -182,12 +187,16 @@ k_tc16(Params p, const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 3 * STAGES + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool SK = CHUNKED && p.sk_W > 0;          // stream-K LINEAR
   const int m0 = blockIdx.y * BM;
   const int j0 = blockIdx.x * (CHUNKED ? NCOL : NBR);
   const int kblocks_all = (p.K + BK - 1) / BK;
   const int kb_lo = CHUNKED ? (int)blockIdx.z * p.kb_per_split : 0;
   const int kblocks = CHUNKED ? min(p.kb_per_split, kblocks_all - kb_lo) : kblocks_all;
-  const int total = NSEG * kblocks;
+  // stream-K: this CTA's range of global chunks [gc_lo, gc_hi); k-block `it` of the CTA is global k-block gc_lo*KCB + it
+  const int gc_lo = SK ? (int)((long long)blockIdx.x * p.sk_W / gridDim.x) : 0;
+  const int gc_hi = SK ? (int)((long long)(blockIdx.x + 1) * p.sk_W / gridDim.x) : 0;
+  const int total = SK ? (gc_hi - gc_lo) * KCB : NSEG * kblocks;
 
   if (warp == 0 && lane == 0) {
     SGG_DBG(0);
@@ -213,17 +222,23 @@ k_tc16(Params p, const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       for (int it = 0; it < total; ++it) {
         const int s = it % STAGES, ph = (it / STAGES) & 1;
         mbar_wait(empty + s, ph ^ 1);
-        const int seg = it / kblocks, k0 = (kb_lo + it - seg * kblocks) * BK;
+        const int seg = SK ? 0 : it / kblocks;
+        int k0 = (kb_lo + it - seg * kblocks) * BK, am0 = m0, bj0 = j0;
+        if (SK) {                                  // global k-block -> (tile, k-block inside the tile)
+          const int gk = gc_lo * KCB + it, kbt = p.sk_C * KCB;
+          const int t = gk / kbt;
+          k0 = (gk - t * kbt) * BK; am0 = (t / p.sk_ct) * BM; bj0 = (t % p.sk_ct) * NCOL;
+        }
         uint8_t *st = stage_ptr(s);
         mbar_arrive_expect_tx(full + s, A_BYTES + 2 * B_BYTES);
         const CUtensorMap *ta = (NSEG > 1 && seg == 1) ? &tmA1 : &tmA0;
         const CUtensorMap *tbh = (NSEG > 1 && seg == 1) ? &tmBh1 : &tmBh0;
         const CUtensorMap *tbl = (NSEG > 1 && seg == 1) ? &tmBl1 : &tmBl0;
-        tma_load_2d(st, ta, full + s, k0, m0);                       // fp32 k0 .. k0+31
-        tma_load_2d(st + A_HALF, ta, full + s, k0 + 32, m0);         // fp32 k0+32 .. k0+63
+        tma_load_2d(st, ta, full + s, k0, am0);                      // fp32 k0 .. k0+31
+        tma_load_2d(st + A_HALF, ta, full + s, k0 + 32, am0);        // fp32 k0+32 .. k0+63
 #pragma unroll
         for (int b = 0; b < NBLK; ++b) {
-          const int row = CHUNKED ? j0 : (b * p.H + j0);
+          const int row = CHUNKED ? bj0 : (b * p.H + j0);
           tma_load_2d(st + A_BYTES + b * (NBR * BK * 2), tbh, full + s, k0, row);
           tma_load_2d(st + A_BYTES + B_BYTES + b * (NBR * BK * 2), tbl, full + s, k0, row);
         }
@@ -239,7 +254,7 @@ k_tc16(Params p, const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         mbar_wait(ready + s, ph);
         fence_after_sync();
         if (it == 0) SGG_DBG(2);
-        const int seg = it / kblocks, kb = it - seg * kblocks;
+        const int seg = CHUNKED ? 0 : it / kblocks, kb = it - seg * kblocks;
         uint8_t *st = stage_ptr(s);
         const uint64_t ah = make_sdesc128(st), al = make_sdesc128(st + A_HALF);
         const uint64_t bh = make_sdesc128(st + A_BYTES), bl = make_sdesc128(st + A_BYTES + B_BYTES);
@@ -342,12 +357,25 @@ k_tc16(Params p, const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       mbar_arrive(tmem_empty + bsel);
     };
     const int nchunks = (total + KCB - 1) / KCB;
+    int sk_seg = 0;
+    // stream-K: after draining local chunk ch, flush the partial tile if that chunk closed its tile (or the CTA's range)
+    auto sk_flush = [&](int ch) {
+      if (!SK) return;
+      if (((gc_lo + ch + 1) % p.sk_C) != 0 && ch != nchunks - 1) return;
+      float *prow = p.sk_part + ((size_t)((size_t)blockIdx.x * p.sk_maxseg + sk_seg) * BM + row) * NCOL + half * HC;
+#pragma unroll
+      for (int c0 = 0; c0 < HC; c0 += 4) {
+        *reinterpret_cast<float4 *>(prow + c0) = make_float4(acc[c0], acc[c0 + 1], acc[c0 + 2], acc[c0 + 3]);
+        acc[c0] = 0.f; acc[c0 + 1] = 0.f; acc[c0 + 2] = 0.f; acc[c0 + 3] = 0.f;
+      }
+      ++sk_seg;
+    };
     for (int it = 0; it < total; ++it) {
       convert(it);
-      if (it > 0 && (it % KCB) == 0) drain(it / KCB - 1);
+      if (it > 0 && (it % KCB) == 0) { drain(it / KCB - 1); sk_flush(it / KCB - 1); }
     }
-    drain(nchunks - 1);
-    if (m < p.M) {
+    if (total > 0) { drain(nchunks - 1); sk_flush(nchunks - 1); }
+    if (!SK && m < p.M) {
       const bool partial = gridDim.z > 1;        // split-K: raw partial sums, bias/ReLU applied by the reducer
       const bool vec = (p.Nout & 3) == 0;
       float *yrow = p.out + ((size_t)blockIdx.z * p.M + m) * p.Nout;
@@ -530,6 +558,40 @@ __global__ void k_tc16_splitk_reduce(const float *__restrict__ part, int splits,
   }
 }
 
+// stream-K reducer: one CTA per output tile; sums the partial tiles of the CTAs whose chunk ranges overlap the tile,
+// in ascending CTA order (deterministic), then bias / ReLU.  Partition arithmetic mirrors k_tc16 (lo_c = c*W/G).
+__global__ void k_tc16_streamk_reduce(const float *__restrict__ part, int W, int C, int G, int maxseg, int col_tiles,
+                                      int ncol, int M, int Nout, const float *__restrict__ bias, int relu,
+                                      float *__restrict__ y) {
+  const int t = blockIdx.x;
+  const long long a = (long long)t * C, b = a + C;
+  const int c_first = (int)(((a + 1) * G + W - 1) / W) - 1;
+  const int c_last = (int)((b * G + W - 1) / W) - 1;
+  const int m0 = (t / col_tiles) * BM, j0 = (t % col_tiles) * ncol;
+  const int q4 = ncol / 4;
+  for (int e = threadIdx.x; e < BM * q4; e += blockDim.x) {
+    const int row = e / q4, c4 = (e - row * q4) * 4;
+    const int m = m0 + row, j = j0 + c4;
+    if (m >= M || j >= Nout) continue;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c = c_first; c <= c_last; ++c) {
+      const int lo = (int)((long long)c * W / G);
+      const int seg = t - lo / C;
+      const float4 v = *reinterpret_cast<const float4 *>(part + ((size_t)((size_t)c * maxseg + seg) * BM + row) * ncol + c4);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    float o[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (j + k < Nout) {
+        float v = o[k] + (bias != nullptr ? __ldg(bias + j + k) : 0.f);
+        if (relu) v = fmaxf(v, 0.f);
+        y[(size_t)m * Nout + j + k] = v;
+      }
+    }
+  }
+}
+
 // ------------------------------- host side -------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -584,6 +646,7 @@ static int launch(const Params &p, const Seg *segs, int col_tiles, int splits, c
     if ((rc = make_tmap(&tm[3 * s + 2], g.Blo, g.brows, p.K, NBR, 2))) return rc;
   }
   dim3 grid(col_tiles, (p.M + BM - 1) / BM, splits);
+  if (p.sk_W > 0) grid = dim3(splits, 1, 1);        // stream-K: `splits` carries the CTA count
   k_tc16<NBLK, NBR, NSEG, EPI><<<grid, NTHR, C::SMEM, st>>>(p, tm[0], tm[3], tm[1], tm[2], tm[4], tm[5]);
   SGG_RETURN_IF_LAUNCH_FAILED("k_tc16");
   return 0;
@@ -610,32 +673,45 @@ int debug_timing(long long *host_out, int n_ctas) {
   return 0;
 }
 
-// LINEAR plan: tile width and split-K factor minimising waves x (chunks per CTA + fixed cost), with a penalty per
-// extra split for the partial-sum round trip.  Every split is a whole number of 256-wide accumulation chunks.
-struct LinPlan { int ncol, splits; };
+// LINEAR plan.  Three shapes of work distribution, chosen by a cost model in units of "128-wide chunk times":
+//   plain    : one CTA per output tile, whole K;
+//   split-K  : gridDim.z equal K ranges per tile + fixed-order reducer (every split a whole number of 256-wide chunks);
+//   stream-K : the (tile, chunk) space cut into one equal contiguous range per SM + reducer — removes partial waves
+//              (cfg2's edge-unary GEMM has 76 tiles: plain uses half the SMs, split-K 2 needs 152 CTAs = two waves).
+// The reducer variants pay the partial-sum round trip, the reducer kernel and one more dependent launch.
+struct LinPlan { int ncol, splits, sk_ctas, sk_maxseg; };
 static LinPlan plan_linear(int M, int Nout, int K, bool allow_split) {
   const int sms = sgg_num_sms();
-  static const double split_fixed = getenv("SGG_TC16_SPLIT_COST") ? atof(getenv("SGG_TC16_SPLIT_COST")) : 3.0;   // tuning knob
+  static const double split_fixed = getenv("SGG_TC16_SPLIT_COST") ? atof(getenv("SGG_TC16_SPLIT_COST")) : 3.0;   // tuning knobs
+  static const int allow_sk = getenv("SGG_TC16_STREAMK") ? atoi(getenv("SGG_TC16_STREAMK")) : 1;
   const int chunks = (K + 255) / 256;
   const int rows = (M + BM - 1) / BM;
-  LinPlan best{Nout <= 64 ? 64 : 128, 1};
+  LinPlan best{Nout <= 64 ? 64 : 128, 1, 0, 0};
   double best_cost = 1e30;
   const int widths[2] = {128, 64};
   for (int wi = 0; wi < 2; ++wi) {
     const int ncol = widths[wi];
     if (ncol == 128 && Nout <= 64) continue;
     const long tiles = (long)((Nout + ncol - 1) / ncol) * rows;
+    const double unit = (128.0 + ncol) / 256.0;        // time of one chunk ~ bytes staged per k-block
     const int max_s = allow_split ? (chunks < 32 ? chunks : 32) : 1;
     for (int s = 1; s <= max_s; ++s) {
       const int ch_per = (chunks + s - 1) / s;
       const int s_eff = (chunks + ch_per - 1) / ch_per;
       if (s_eff != s) continue;
       const long waves = (tiles * s + sms - 1) / sms;
-      // per-CTA time ~ chunks x (A rows + B rows) ; fixed prologue/epilogue ~ 1.5 chunks of a 128-wide tile (measured: ~7k of ~1k-cycle k-blocks)
-      const double per = ch_per * (128.0 + ncol) / 256.0 + 1.5;
-      // split-K adds the partial-sum round trip, the reducer kernel and one more dependent launch (~13 us measured)
+      // fixed prologue/epilogue ~ 1.5 chunks of a 128-wide tile (measured: ~7k of ~1k-cycle k-blocks)
+      const double per = ch_per * unit + 1.5;
       const double cost = waves * per + (s > 1 ? 0.3 * s + split_fixed : 0.0);
-      if (cost < best_cost - 1e-9) { best_cost = cost; best.ncol = ncol; best.splits = s; }
+      if (cost < best_cost - 1e-9) { best_cost = cost; best = LinPlan{ncol, s, 0, 0}; }
+    }
+    if (allow_split && allow_sk && (K % 256) == 0 && tiles * chunks > sms / 2) {
+      const long W = tiles * chunks;
+      const int G = (int)(W < sms ? W : sms);
+      const int q = (int)((W + G - 1) / G);
+      const int maxseg = (q + chunks - 2) / chunks + 1;
+      const double cost = q * unit + 1.5 + split_fixed + 0.3 * maxseg;
+      if (cost < best_cost - 1e-9) { best_cost = cost; best = LinPlan{ncol, 1, G, maxseg}; }
     }
   }
   return best;
@@ -644,6 +720,7 @@ static LinPlan plan_linear(int M, int Nout, int K, bool allow_split) {
 size_t linear_workspace_floats(int M, int Nout, int K) {
   if (M <= 0 || Nout <= 0) return 0;
   const LinPlan pl = plan_linear(M, Nout, K, true);
+  if (pl.sk_ctas > 0) return (size_t)pl.sk_ctas * pl.sk_maxseg * BM * pl.ncol;
   return pl.splits > 1 ? (size_t)pl.splits * M * Nout : 0;
 }
 
@@ -653,6 +730,23 @@ int linear(const float *x, const float *w_split, const float *b, float *y, int M
   if ((K & 7) || !ok16(x) || !ok16(w_split)) return sgg_set_err(SGG_E_BADARG, "tc16 linear: K %% 8 / alignment");
   const LinPlan pl = plan_linear(M, Nout, K, ws != nullptr);
   const int kblocks = (K + BK - 1) / BK, kcb = 256 / BK;
+  const __half *wh = reinterpret_cast<const __half *>(w_split);
+  Seg sg[2] = {{x, wh, wh + (size_t)Nout * K, Nout}, {}};
+  Params p{}; p.M = M; p.K = K; p.Nout = Nout; p.relu = relu; p.bias = b; p.dbg = dbg_ptr();
+  int rc;
+  if (pl.sk_ctas > 0) {
+    const int col_tiles = (Nout + pl.ncol - 1) / pl.ncol, rows = (M + BM - 1) / BM;
+    p.kb_per_split = kblocks;
+    p.sk_C = K / 256; p.sk_ct = col_tiles; p.sk_W = col_tiles * rows * p.sk_C; p.sk_maxseg = pl.sk_maxseg; p.sk_part = ws;
+    p.out = y;
+    if (pl.ncol == 64) rc = launch<1, 64, 1, EPI_LINEAR>(p, sg, col_tiles, pl.sk_ctas, st);
+    else rc = launch<1, 128, 1, EPI_LINEAR>(p, sg, col_tiles, pl.sk_ctas, st);
+    if (rc) return rc;
+    k_tc16_streamk_reduce<<<col_tiles * rows, 256, 0, st>>>(ws, p.sk_W, p.sk_C, pl.sk_ctas, pl.sk_maxseg, col_tiles,
+                                                              pl.ncol, M, Nout, b, relu, y);
+    SGG_RETURN_IF_LAUNCH_FAILED("k_tc16_streamk_reduce");
+    return 0;
+  }
   int splits = pl.splits, kb_per = kblocks;
   if (splits > 1) {
     const int chunks = (kblocks + kcb - 1) / kcb;
@@ -660,11 +754,8 @@ int linear(const float *x, const float *w_split, const float *b, float *y, int M
     kb_per = ch_per * kcb;
     splits = (kblocks + kb_per - 1) / kb_per;
   }
-  Params p{}; p.M = M; p.K = K; p.Nout = Nout; p.relu = relu; p.bias = b; p.kb_per_split = kb_per; p.dbg = dbg_ptr();
+  p.kb_per_split = kb_per;
   p.out = splits > 1 ? ws : y;
-  const __half *wh = reinterpret_cast<const __half *>(w_split);
-  Seg sg[2] = {{x, wh, wh + (size_t)Nout * K, Nout}, {}};
-  int rc;
   if (pl.ncol == 64) rc = launch<1, 64, 1, EPI_LINEAR>(p, sg, (Nout + 63) / 64, splits, st);
   else rc = launch<1, 128, 1, EPI_LINEAR>(p, sg, (Nout + 127) / 128, splits, st);
   if (rc) return rc;

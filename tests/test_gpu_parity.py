@@ -188,6 +188,33 @@ def test_full_size_properties_cfg4_shard(ops):
     assert torch.isfinite(v).all() and torch.isfinite(e).all()
 
 
+def test_full_size_properties_cfg5_dense_stress(ops):
+    """BASELINE cfg5 per-GPU shape (8 images, 64 boxes, 2000 candidate edges, 6 MP iterations; N=512, E=16000):
+    edge-permutation equivariance, image independence, determinism (bit-identical reruns: no float atomics) and
+    agreement of the L1 entry points, plus the numpy oracle on the first image."""
+    from sgg_b200 import synth
+    T = 6
+    g = synth.synth_graph(8, 64, 2000, 1238)
+    N, E = g['boxes'].shape[0], g['rel_inds'].shape[0]
+    assert (N, E) == (512, 16000)
+    obj, rel = synth.synth_l0_states(N, E, 1238)
+    pn = synth.synth_params(1238, scale=2.0, level='l0')
+    p = pdev(pn)
+    ri = dev(g['rel_inds'])
+    gr = ops.build_graph(ri[:, 1:3], N, validate=True)
+    v, e = ops.message_pass(dev(rel), dev(obj), gr, p, T)
+    v_again, e_again = ops.message_pass(dev(rel), dev(obj), gr, p, T)
+    assert torch.equal(v, v_again) and torch.equal(e, e_again)
+    perm = torch.randperm(E, generator=torch.Generator().manual_seed(5)).cuda()
+    gr2 = ops.build_graph(ri[perm][:, 1:3].contiguous(), N)
+    v2, e2 = ops.message_pass(dev(rel)[perm].contiguous(), dev(obj), gr2, p, T)
+    assert (v - v2).abs().max().item() <= 5e-5 and (e[perm] - e2).abs().max().item() <= 5e-5
+    n0 = 64; m0 = int((g['rel_inds'][:, 0] == 0).sum())
+    vo, eo = O.message_pass(rel[:m0], obj[:n0], g['rel_inds'][:m0, 1:3], pn, T)       # oracle on image 0 (block-diagonal graph)
+    assert np.abs(v[:n0].cpu().numpy() - vo).max() <= TOL and np.abs(e[:m0].cpu().numpy() - eo).max() <= TOL
+    assert torch.isfinite(v).all() and torch.isfinite(e).all()
+
+
 def test_edge_gru_kernel_vs_numpy(ops):
     """The dominant kernel in isolation (fused gather + GRU epilogue) against the numpy GRUCell."""
     from sgg_b200 import synth

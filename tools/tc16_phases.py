@@ -37,7 +37,7 @@ o, e = torch.from_numpy(of).cuda(), torch.from_numpy(ef).cuda()
 obj_rep = ops.linear(o, p['obj_unary.weight'], p['obj_unary.bias'])
 for _ in range(3):
     rel_rep = ops.linear(e, p['edge_unary.weight'], p['edge_unary.bias'], relu=True)
-report('edge unary LINEAR 2400x512x4096 (grid 4x19x3)', 228, gru=False)
+report('edge unary LINEAR 2400x512x4096 (stream-K, 148 CTAs)', 148, gru=False)
 P_t = ops.linear(obj_rep, p['edge_gru.weight_ih'])
 report('P LINEAR 240x1536x512', 48, gru=False)
 gates = torch.rand(E, 4, device='cuda')
