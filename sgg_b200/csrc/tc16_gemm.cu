@@ -558,8 +558,9 @@ __global__ void k_tc16_splitk_reduce(const float *__restrict__ part, int splits,
   }
 }
 
-// stream-K reducer: one CTA per output tile; sums the partial tiles of the CTAs whose chunk ranges overlap the tile,
-// in ascending CTA order (deterministic), then bias / ReLU.  Partition arithmetic mirrors k_tc16 (lo_c = c*W/G).
+// stream-K reducer: grid (tiles, BM / rows-per-CTA), one float4 of one output row per thread; sums the partial tiles
+// of the CTAs whose chunk ranges overlap the tile in ascending CTA order (deterministic), then bias / ReLU.
+// Partition arithmetic mirrors k_tc16 (lo_c = c*W/G).
 __global__ void k_tc16_streamk_reduce(const float *__restrict__ part, int W, int C, int G, int maxseg, int col_tiles,
                                       int ncol, int M, int Nout, const float *__restrict__ bias, int relu,
                                       float *__restrict__ y) {
@@ -567,28 +568,29 @@ __global__ void k_tc16_streamk_reduce(const float *__restrict__ part, int W, int
   const long long a = (long long)t * C, b = a + C;
   const int c_first = (int)(((a + 1) * G + W - 1) / W) - 1;
   const int c_last = (int)((b * G + W - 1) / W) - 1;
-  const int m0 = (t / col_tiles) * BM, j0 = (t % col_tiles) * ncol;
   const int q4 = ncol / 4;
-  for (int e = threadIdx.x; e < BM * q4; e += blockDim.x) {
-    const int row = e / q4, c4 = (e - row * q4) * 4;
-    const int m = m0 + row, j = j0 + c4;
-    if (m >= M || j >= Nout) continue;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int c = c_first; c <= c_last; ++c) {
-      const int lo = (int)((long long)c * W / G);
-      const int seg = t - lo / C;
-      const float4 v = *reinterpret_cast<const float4 *>(part + ((size_t)((size_t)c * maxseg + seg) * BM + row) * ncol + c4);
-      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-    }
-    float o[4] = {acc.x, acc.y, acc.z, acc.w};
+  const int row = blockIdx.y * (blockDim.x / q4) + threadIdx.x / q4, c4 = (threadIdx.x % q4) * 4;
+  const int m = (t / col_tiles) * BM + row, j = (t % col_tiles) * ncol + c4;
+  if (row >= BM || m >= M || j >= Nout) return;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int c = c_first; c <= c_last; ++c) {
+    const int lo = (int)((long long)c * W / G);
+    const int seg = t - lo / C;
+    const float4 v = *reinterpret_cast<const float4 *>(part + ((size_t)((size_t)c * maxseg + seg) * BM + row) * ncol + c4);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  float o[4] = {acc.x, acc.y, acc.z, acc.w};
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      if (j + k < Nout) {
-        float v = o[k] + (bias != nullptr ? __ldg(bias + j + k) : 0.f);
-        if (relu) v = fmaxf(v, 0.f);
-        y[(size_t)m * Nout + j + k] = v;
-      }
-    }
+  for (int k = 0; k < 4; ++k) {
+    if (bias != nullptr && j + k < Nout) o[k] += __ldg(bias + j + k);
+    if (relu) o[k] = fmaxf(o[k], 0.f);
+  }
+  float *yp = y + (size_t)m * Nout + j;
+  if ((Nout & 3) == 0 && j + 4 <= Nout) {
+    *reinterpret_cast<float4 *>(yp) = make_float4(o[0], o[1], o[2], o[3]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) if (j + k < Nout) yp[k] = o[k];
   }
 }
 
@@ -677,7 +679,7 @@ int debug_timing(long long *host_out, int n_ctas) {
 //   plain    : one CTA per output tile, whole K;
 //   split-K  : gridDim.z equal K ranges per tile + fixed-order reducer (every split a whole number of 256-wide chunks);
 //   stream-K : the (tile, chunk) space cut into one equal contiguous range per SM + reducer — removes partial waves
-//              (cfg2's edge-unary GEMM has 76 tiles: plain uses half the SMs, split-K 2 needs 152 CTAs = two waves).
+//              of multi-wave GEMMs (E = 9600 edges: 300 tiles = 2.03 waves; fc6: 2400 tiles).
 // The reducer variants pay the partial-sum round trip, the reducer kernel and one more dependent launch.
 struct LinPlan { int ncol, splits, sk_ctas, sk_maxseg; };
 static LinPlan plan_linear(int M, int Nout, int K, bool allow_split) {
@@ -705,7 +707,10 @@ static LinPlan plan_linear(int M, int Nout, int K, bool allow_split) {
       const double cost = waves * per + (s > 1 ? 0.3 * s + split_fixed : 0.0);
       if (cost < best_cost - 1e-9) { best_cost = cost; best = LinPlan{ncol, s, 0, 0}; }
     }
-    if (allow_split && allow_sk && (K % 256) == 0 && tiles * chunks > sms / 2) {
+    // stream-K only when plain tiling already needs more than one wave: a GEMM with fewer tiles than SMs usually runs
+    // next to other branches of the step (measured at cfg2: giving its 76-tile edge-unary GEMM all 148 SMs made the
+    // GEMM 17 % faster and the step 6 % slower, because the object branch no longer overlapped)
+    if (allow_split && allow_sk && (K % 256) == 0 && tiles > sms) {
       const long W = tiles * chunks;
       const int G = (int)(W < sms ? W : sms);
       const int q = (int)((W + G - 1) / G);
@@ -742,8 +747,9 @@ int linear(const float *x, const float *w_split, const float *b, float *y, int M
     if (pl.ncol == 64) rc = launch<1, 64, 1, EPI_LINEAR>(p, sg, col_tiles, pl.sk_ctas, st);
     else rc = launch<1, 128, 1, EPI_LINEAR>(p, sg, col_tiles, pl.sk_ctas, st);
     if (rc) return rc;
-    k_tc16_streamk_reduce<<<col_tiles * rows, 256, 0, st>>>(ws, p.sk_W, p.sk_C, pl.sk_ctas, pl.sk_maxseg, col_tiles,
-                                                              pl.ncol, M, Nout, b, relu, y);
+    const int rows_per_cta = 256 / (pl.ncol / 4);
+    k_tc16_streamk_reduce<<<dim3(col_tiles * rows, BM / rows_per_cta), 256, 0, st>>>(
+        ws, p.sk_W, p.sk_C, pl.sk_ctas, pl.sk_maxseg, col_tiles, pl.ncol, M, Nout, b, relu, y);
     SGG_RETURN_IF_LAUNCH_FAILED("k_tc16_streamk_reduce");
     return 0;
   }
