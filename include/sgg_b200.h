@@ -215,6 +215,58 @@ SGG_API int sgg_node_edge_features(const float *fmap, int B, int C, int Hf, int 
                            float spatial_scale, int pool, int sampling_ratio,
                            float *node_feat, float *edge_feat, void *ws, size_t ws_bytes, void *stream);
 
+/* ==== training tail: lib/losses.py, lib/pytorch_misc.py grad_clip / get_optim =============== */
+
+/* ---- edge_losses / node_losses: lib/losses.py:5-74 ---------------------------
+ * One call = per-row cross entropy, the reference's row weighting, the summed loss and (optionally) d loss/d logits.
+ *   SGG_LOSS_MEAN       node_losses :73-74       CE(reduction='mean'), rows with label -100 ignored
+ *   SGG_LOSS_BASELINE   edge_losses :40-44       gamma * CE / M          (requires alpha == beta == 1, as :42 asserts)
+ *   SGG_LOSS_DNORM      edge_losses :46-62       FG rows alpha/M_FG, BG rows beta/M_FG (weights stay 1 where M_FG == 0)
+ *   SGG_LOSS_DNORM_FGBG edge_losses :46-64       FG rows alpha/M_FG, BG rows beta/M_BG
+ * logits [M,C] fp32; labels [M] int64; category (nullable) int8 [M]: 1 = FG row, 2 = BG row, 0 = neither — the
+ * explicit idx_fg / idx_bg of :27-31; NULL => FG = label > 0, BG = label == 0.
+ * loss: device float[1]; dlogits (nullable) [M,C]; counts_out (nullable) device int[4] = {M_FG, M_BG, rows counted by
+ * the mean, rows whose label was outside [0,C) and not -100 (an error the caller may check)}. */
+#define SGG_LOSS_MEAN 0
+#define SGG_LOSS_BASELINE 1
+#define SGG_LOSS_DNORM 2
+#define SGG_LOSS_DNORM_FGBG 3
+SGG_API size_t sgg_ce_loss_workspace_bytes(int M);
+SGG_API int sgg_ce_loss(const float *logits, const int64_t *labels, const int8_t *category, int M, int C, int mode,
+                float alpha, float beta, float gamma, float *loss, float *dlogits, int *counts_out,
+                void *ws, size_t ws_bytes, void *stream);
+
+/* ---- multi-tensor gradient norm / clipping / SGD step --------------------------
+ * Replaces clip_grad_norm (lib/pytorch_misc.py:625-664, called by grad_clip :70-73) and optim.SGD(momentum,
+ * weight_decay) built by get_optim (:130-157), main.py:118-120.  One table row per parameter tensor; the caller
+ * fills a HOST array of sgg_mt_tensor and uploads it once (and again whenever a pointer / lr / flag changes). */
+typedef struct {
+  float *p;            /* parameter                                                                    */
+  const float *g;      /* gradient; NULL = no gradient this step (tensor is skipped, as torch does)    */
+  float *m;            /* momentum buffer (same size as p)                                             */
+  void *split;         /* nullable: 2n fp16 [hi | lo*2^11] tensor-core operand of the NEW weight (n % 8 == 0) */
+  long long n;         /* elements                                                                     */
+  float lr, wd;        /* per-group learning rate / weight decay                                       */
+  int flags;           /* bit 0: momentum buffer not initialised yet (first step: m = d)               */
+  int reserved;
+} sgg_mt_tensor;
+SGG_API int sgg_mt_chunk_elems(void);
+SGG_API size_t sgg_mt_table_bytes(int n_tensors);
+SGG_API long long sgg_mt_total_chunks(const sgg_mt_tensor *host_table, int n_tensors);
+SGG_API size_t sgg_mt_workspace_bytes(long long total_chunks);
+SGG_API int sgg_mt_table_upload(const sgg_mt_tensor *host_table, int n_tensors, void *table, size_t table_bytes,
+                        void *stream);
+/* norm_out: device float[4] = {total_norm, clip_coef = max_norm / (total_norm + 1e-6), scale applied
+ * (clip_coef if < 1 else 1; 1 when max_norm <= 0), sum of squares}.  Deterministic (fixed-order partials). */
+SGG_API int sgg_mt_grad_norm(const void *table, int n_tensors, long long total_chunks, float max_norm, float *norm_out,
+                     void *ws, size_t ws_bytes, void *stream);
+/* in-place g *= norm[2] (the reference's clip_grad_norm(..., clip=True) side effect) */
+SGG_API int sgg_mt_scale_grads(const void *table, int n_tensors, long long total_chunks, const float *norm, void *stream);
+/* d = g*norm[2] + wd*p; m = first ? d : momentum*m + d; p -= lr*m (+ optional operand split, + optional write-back of
+ * the clipped gradient).  norm NULL => no clipping. */
+SGG_API int sgg_mt_sgd_step(const void *table, int n_tensors, long long total_chunks, const float *norm, float momentum,
+                    int write_clipped_grads, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

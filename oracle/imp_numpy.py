@@ -332,3 +332,99 @@ def filter_dets(boxes, obj_scores, obj_classes, rel_inds, pred_scores):
     score = pred_scores[:, 1:].max(1) * s0 * s1
     order = np.argsort(-score, kind='stable')
     return boxes, obj_classes, obj_scores, rel_inds[order], pred_scores[order]
+
+
+# --------------------------------------------------------------------------- #
+# training tail: losses, gradient clipping, SGD
+# --------------------------------------------------------------------------- #
+def cross_entropy_rows(logits, labels, ignore_index=-100):
+    """torch.nn.functional.cross_entropy(reduction='none') restated: -log_softmax(x)[label];
+    rows whose label equals ``ignore_index`` give 0."""
+    x = logits.astype(np.float64)
+    m = x.max(1, keepdims=True)
+    lse = np.log(np.exp(x - m).sum(1)) + m[:, 0]
+    keep = labels != ignore_index
+    out = np.zeros(len(labels), np.float64)
+    out[keep] = lse[keep] - x[np.nonzero(keep)[0], labels[keep]]
+    return out
+
+
+def edge_weights(rel_labels, loss_type, loss_weights=(1, 1, 1), idx_fg=None, idx_bg=None):
+    """Row weights of lib/losses.py:36-62 (gamma folded in)."""
+    alpha, beta, gamma = loss_weights
+    if idx_fg is None:
+        idx_fg = np.nonzero(rel_labels > 0)[0]                     # :27-28
+    if idx_bg is None:
+        idx_bg = np.nonzero(rel_labels == 0)[0]                    # :30-31
+    M_FG, M_BG, M = len(idx_fg), len(idx_bg), len(rel_labels)      # :33
+    if loss_type == 'baseline':
+        assert alpha == beta == 1                                  # :42
+        return np.full(M, float(gamma) / M)                        # :43
+    if loss_type not in ('dnorm', 'dnorm-fgbg'):
+        raise NotImplementedError(loss_type)                       # :66
+    w = np.ones(M)                                                 # :48
+    if M_FG > 0:
+        w[idx_fg] = float(alpha) / M_FG                            # :51-52
+    if loss_type == 'dnorm':
+        if M_BG > 0 and M_FG > 0:
+            w[idx_bg] = float(beta) / M_FG                         # :55-58
+    elif M_BG > 0:
+        w[idx_bg] = float(beta) / M_BG                             # :59-61
+    return gamma * w                                               # :63
+
+
+def edge_losses(rel_dists, rel_labels, loss_type='dnorm', loss_weights=(1, 1, 1), idx_fg=None, idx_bg=None,
+                return_grad=False):
+    """lib/losses.py:5-70 -> rel_loss (float64 scalar) [, d rel_loss / d rel_dists]."""
+    w = edge_weights(rel_labels, loss_type, loss_weights, idx_fg, idx_bg)
+    loss = float((w * cross_entropy_rows(rel_dists, rel_labels)).sum())
+    if not return_grad:
+        return loss
+    g = softmax(rel_dists.astype(np.float64), 1)
+    g[np.arange(len(rel_labels)), rel_labels] -= 1.0
+    return loss, g * w[:, None]
+
+
+def node_losses(rm_obj_dists, rm_obj_labels, return_grad=False):
+    """lib/losses.py:73-74: CE with the default 'mean' reduction (mean over rows whose label is not -100)."""
+    keep = rm_obj_labels != -100
+    n = max(int(keep.sum()), 1)
+    loss = float(cross_entropy_rows(rm_obj_dists, rm_obj_labels).sum() / n)
+    if not return_grad:
+        return loss
+    g = softmax(rm_obj_dists.astype(np.float64), 1)
+    g[np.nonzero(keep)[0], rm_obj_labels[keep]] -= 1.0
+    g[~keep] = 0.0
+    return loss, g / n
+
+
+def clip_grad_norm(grads, max_norm, clip=True):
+    """lib/pytorch_misc.py:625-664 on a list of gradient arrays (modified in place when clipped).
+    -> (total_norm, clip_coef)."""
+    total = 0.0
+    for g in grads:
+        total += float(np.sqrt((g.astype(np.float64) ** 2).sum())) ** 2        # :643-644
+    total = total ** 0.5                                                         # :648
+    coef = float(max_norm) / (total + 1e-6)                                      # :649
+    if coef < 1 and clip:
+        for g in grads:
+            g *= np.float32(coef)                                                # :650-653
+    return total, coef
+
+
+def sgd_step(params, grads, bufs, lrs, weight_decay, momentum=0.9):
+    """torch.optim.SGD (dampening 0, no Nesterov), the optimizer lib/pytorch_misc.py:146 builds:
+    d = g + wd * p;  buf = d on the first step else momentum * buf + d;  p -= lr * buf.  float32, in place;
+    ``bufs[i] is None`` marks a first step.  Returns the new buffer list."""
+    out = []
+    for p, g, b, lr in zip(params, grads, bufs, lrs):
+        if g is None:
+            out.append(b)
+            continue
+        d = g.astype(np.float32)
+        if weight_decay != 0:
+            d = d + np.float32(weight_decay) * p
+        b = d.copy() if b is None else np.float32(momentum) * b + d
+        p -= np.float32(lr) * b
+        out.append(b)
+    return out

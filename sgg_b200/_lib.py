@@ -40,6 +40,12 @@ class GeomWeights(C.Structure):
                                           'conv2_w', 'conv2_b', 'bn2_w', 'bn2_b', 'bn2_rm', 'bn2_rv')]
 
 
+class MtTensor(C.Structure):
+    """sgg_mt_tensor: one row of the multi-tensor optimizer table (include/sgg_b200.h)."""
+    _fields_ = [('p', C.c_void_p), ('g', C.c_void_p), ('m', C.c_void_p), ('split', C.c_void_p), ('n', C.c_longlong),
+                ('lr', C.c_float), ('wd', C.c_float), ('flags', C.c_int), ('reserved', C.c_int)]
+
+
 # name -> (restype, argtypes); must list every symbol include/sgg_b200.h declares (tests check this).
 SIGNATURES = {
     'sgg_abi_version': (C.c_int, []),
@@ -88,6 +94,18 @@ SIGNATURES = {
     'sgg_node_edge_features': (C.c_int, [c_f, C.c_int, C.c_int, C.c_int, C.c_int, c_f, C.c_int, c_i64p, C.c_int64,
                                          C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, c_f, c_f,
                                          C.c_void_p, C.c_size_t, C.c_void_p]),
+    'sgg_ce_loss_workspace_bytes': (C.c_size_t, [C.c_int]),
+    'sgg_ce_loss': (C.c_int, [c_f, c_i64p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float,
+                              c_f, c_f, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    'sgg_mt_chunk_elems': (C.c_int, []),
+    'sgg_mt_table_bytes': (C.c_size_t, [C.c_int]),
+    'sgg_mt_total_chunks': (C.c_longlong, [C.POINTER(MtTensor), C.c_int]),
+    'sgg_mt_workspace_bytes': (C.c_size_t, [C.c_longlong]),
+    'sgg_mt_table_upload': (C.c_int, [C.POINTER(MtTensor), C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
+    'sgg_mt_grad_norm': (C.c_int, [C.c_void_p, C.c_int, C.c_longlong, C.c_float, c_f, C.c_void_p, C.c_size_t,
+                                   C.c_void_p]),
+    'sgg_mt_scale_grads': (C.c_int, [C.c_void_p, C.c_int, C.c_longlong, c_f, C.c_void_p]),
+    'sgg_mt_sgd_step': (C.c_int, [C.c_void_p, C.c_int, C.c_longlong, c_f, C.c_float, C.c_int, C.c_void_p]),
 }
 
 

@@ -536,13 +536,26 @@ k_tc16(Params p, const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   if (warp == 1) tc::tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-// w -> fp16 (hi, scaled lo), once per weight version
-__global__ void k_tc16_split(const float *__restrict__ w, size_t n, __half *__restrict__ hi, __half *__restrict__ lo) {
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const float v = w[i];
-    const __half h = __float2half_rn(v);
-    hi[i] = h;
-    lo[i] = __float2half_rn((v - __half2float(h)) * LO_SCALE);
+// w -> fp16 (hi, scaled lo), once per weight version.  Streaming: 8 floats per thread and trip (two 16-byte loads,
+// one 16-byte store per half-plane); n % 8 == 0 is checked at the ABI.
+__global__ void __launch_bounds__(256) k_tc16_split(const float *__restrict__ w, size_t n, __half *__restrict__ hi,
+                                                     __half *__restrict__ lo) {
+  const size_t n8 = n >> 3;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 a = __ldcs(reinterpret_cast<const float4 *>(w) + 2 * i);
+    const float4 b = __ldcs(reinterpret_cast<const float4 *>(w) + 2 * i + 1);
+    const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    uint32_t ph[4], pl[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const __half h0 = __float2half_rn(v[2 * k]), h1 = __float2half_rn(v[2 * k + 1]);
+      const __half l0 = __float2half_rn((v[2 * k] - __half2float(h0)) * LO_SCALE);
+      const __half l1 = __float2half_rn((v[2 * k + 1] - __half2float(h1)) * LO_SCALE);
+      ph[k] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+      pl[k] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+    }
+    reinterpret_cast<uint4 *>(hi)[i] = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+    reinterpret_cast<uint4 *>(lo)[i] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
   }
 }
 
@@ -820,7 +833,9 @@ int gru(int mode, const float *x, const float *h, const float *w_ih_split, const
 }
 
 int split_weights(const float *w, size_t n, void *split, cudaStream_t st) {
-  int blocks = (int)((n + 255) / 256 < 2048 ? (n + 255) / 256 : 2048);
+  const size_t want = (n / 8 + 255) / 256;
+  const int cap = sgg_num_sms() * 8;
+  int blocks = (int)(want < (size_t)cap ? (want > 0 ? want : 1) : (size_t)cap);
   __half *hp = reinterpret_cast<__half *>(split);
   k_tc16_split<<<blocks, 256, 0, st>>>(w, n, hp, hp + n);
   SGG_RETURN_IF_LAUNCH_FAILED("k_tc16_split");

@@ -100,6 +100,22 @@ def split_weight(w):
     return out
 
 
+def split_cache_peek(w):
+    """The cached operand-split buffer of the live tensor object ``w`` (whatever version it was made for), or None.
+    Used by the fused optimizer (sgg_b200.optim), which rewrites the split in the same sweep that updates ``w``."""
+    hit = _SPLIT_CACHE.get(id(w))
+    if hit is None or hit[2]() is not w or hit[0][1:] != (w.data_ptr(), tuple(w.shape), _lib.load().sgg_tc_get_mode()):
+        return None
+    return hit[1]
+
+
+def split_cache_commit(w):
+    """Re-stamp the cached split of ``w`` with its current version (the caller has just rewritten the buffer)."""
+    hit = _SPLIT_CACHE.get(id(w))
+    if hit is not None and hit[2]() is w:
+        _SPLIT_CACHE[id(w)] = ((w._version, w.data_ptr(), tuple(w.shape), _lib.load().sgg_tc_get_mode()), hit[1], hit[2])
+
+
 def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
@@ -194,6 +210,7 @@ def message_pass(rel_rep, obj_rep, graph, params, mp_iter=3, save_states=False):
 def linear(x, weight, bias=None, relu=False):
     """nn.Linear forward (+ReLU) — y = act(x @ weight.T + bias)."""
     lib = _lib.load()
+    w_obj = weight                 # the split cache is keyed by the caller's (long-lived) tensor object, not the detached view
     x = _f32(x, 'x'); weight = _f32(weight, 'weight')
     if x.dim() != 2 or weight.dim() != 2 or x.shape[1] != weight.shape[1]:
         raise _lib.SggError('linear: x %s vs weight %s' % (tuple(x.shape), tuple(weight.shape)))
@@ -203,7 +220,7 @@ def linear(x, weight, bias=None, relu=False):
     Nout = weight.shape[0]
     y = torch.empty((M, Nout), dtype=torch.float32, device=x.device)
     if _use_tc() and _tc_k_ok(K):
-        sp = split_weight(weight)
+        sp = split_weight(w_obj)
         nb = lib.sgg_tc_linear_workspace_bytes(M, Nout, K)
         ws = torch.empty(nb, dtype=torch.uint8, device=x.device) if nb else None
         check(lib.sgg_tc_linear_forward(_ptr(x), _ptr(sp), _ptr(bias), _ptr(y), M, Nout, K, 1 if relu else 0,

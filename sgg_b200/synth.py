@@ -165,3 +165,65 @@ def synth_backbone_params(model_state_shapes, seed):
 def synth_images(sizes, seed):
     rng = np.random.default_rng(seed + 86028121)
     return [rng.random((3, h, w), dtype=np.float32) for (h, w) in sizes]
+
+
+# ---- training tail (losses / clipping / SGD): inputs of tests/golden/train_tail.npz --------------------------
+def synth_logits(M, C, seed, fg=0.15, scale=3.0):
+    """Logits [M,C] ~ scale * N(0,1) and int64 labels with a fraction ``fg`` of foreground rows (label in 1..C-1),
+    the rest background (0) — the shape of rel_labels[:, -1] (proposal_assignments_gtbox.py:70-77)."""
+    rng = np.random.default_rng(9000 + seed)
+    logits = (scale * rng.standard_normal((M, C))).astype(np.float32)
+    labels = np.zeros(M, np.int64)
+    if M > 0 and fg > 0:
+        is_fg = rng.random(M) < fg
+        if fg >= 1.0:
+            is_fg[:] = True
+        labels[is_fg] = rng.integers(1, C, int(is_fg.sum()))
+    return logits, labels
+
+
+def explicit_idx(labels, seed):
+    """Explicit idx_fg / idx_bg (lib/losses.py:27-31 lets the caller pass them): a subset of the FG rows and a
+    subset of the BG rows, so some rows are in neither set and keep weight 1."""
+    rng = np.random.default_rng(9100 + seed)
+    fg = np.nonzero(labels > 0)[0]
+    bg = np.nonzero(labels == 0)[0]
+    return np.sort(rng.choice(fg, max(1, len(fg) // 2), replace=False)), \
+        np.sort(rng.choice(bg, max(1, (2 * len(bg)) // 3), replace=False))
+
+
+def loss_cases():
+    return {
+        'node_cfg2': dict(kind='node', M=240, C=151, seed=1, fg=1.0, w=(1, 1, 1)),
+        'baseline_cfg2': dict(kind='baseline', M=2400, C=51, seed=2, fg=0.02, w=(1, 1, 1)),
+        'baseline_gamma': dict(kind='baseline', M=300, C=51, seed=3, fg=0.1, w=(1, 1, 0.5)),
+        'dnorm_cfg2': dict(kind='dnorm', M=2400, C=51, seed=4, fg=0.02, w=(1, 1, 1)),
+        'dnorm_weights': dict(kind='dnorm', M=777, C=51, seed=5, fg=0.2, w=(0.5, 2.0, 1.5)),
+        'dnorm_no_fg': dict(kind='dnorm', M=64, C=51, seed=6, fg=0.0, w=(1, 1, 1)),       # weights stay 1 (:51,:57)
+        'dnorm_no_bg': dict(kind='dnorm', M=64, C=51, seed=7, fg=1.0, w=(1, 1, 1)),
+        'fgbg_cfg2': dict(kind='dnorm-fgbg', M=2400, C=51, seed=8, fg=0.02, w=(1, 1, 1)),
+        'fgbg_weights': dict(kind='dnorm-fgbg', M=1001, C=51, seed=9, fg=0.3, w=(2.0, 0.25, 3.0)),
+        'fgbg_no_fg': dict(kind='dnorm-fgbg', M=33, C=51, seed=10, fg=0.0, w=(1, 1, 1)),
+        'dnorm_explicit': dict(kind='dnorm', M=500, C=51, seed=11, fg=0.2, w=(1, 1, 1), explicit_idx=True),
+        'one_row': dict(kind='dnorm', M=1, C=51, seed=12, fg=1.0, w=(1, 1, 1)),
+    }
+
+
+def synth_train_tail(seed=5, steps=3):
+    """A small parameter set with the reference's naming (two ``roi_fmap*`` tensors fall in the lr/10 group of
+    get_optim, lib/pytorch_misc.py:135-142), sizes that exercise the vector path, ragged tails, a tiny tensor and a
+    tensor that gets no gradient on some steps; gradients are large enough that clipping at 5.0 engages on step 0
+    and small enough that it does not on step 2."""
+    rng = np.random.default_rng(9200 + seed)
+    shapes = {'roi_fmap.1.0.weight': (8, 1024), 'roi_fmap_obj.0.bias': (4099,), 'edge_gru.weight_ih': (8, 512),
+              'obj_fc.weight': (9, 512), 'obj_fc.bias': (151,), 'sub_vert_w_fc.0.bias': (1,),
+              'union_boxes.conv.0.weight': (16, 2, 7, 7), 'rel_fc.weight': (3, 512)}
+    params = {k: (0.1 * rng.standard_normal(s)).astype(np.float32) for k, s in shapes.items()}
+    gscale = [0.05, 0.01, 0.0005][:steps] + [0.0005] * max(0, steps - 3)
+    grads = []
+    for t in range(steps):
+        g = {k: (gscale[t] * rng.standard_normal(s)).astype(np.float32) for k, s in shapes.items()}
+        if t == 1:
+            g['rel_fc.weight'] = None          # no gradient this step: torch skips the tensor entirely
+        grads.append(g)
+    return dict(params=params, grads=grads, lr=0.12, l2=1e-4, clip=5.0, steps=steps)
