@@ -214,6 +214,14 @@ SGG_API int sgg_node_edge_features(const float *fmap, int B, int C, int Hf, int 
                            const int64_t *union_inds, int64_t row_stride, int col_subj, int col_obj, int E,
                            float spatial_scale, int pool, int sampling_ratio,
                            float *node_feat, float *edge_feat, void *ws, size_t ws_bytes, void *stream);
+/* Same, with the union-box geometry embedding folded into the edge rows: edge_feat[e,c,:,:] = RoIAlign(...) +
+ * edge_add[e,c] (lib/get_union_boxes.py:101, union_pools + conv(rects) broadcast over the bins), so the [E,C,7,7]
+ * tensor is written once instead of written, re-read and re-written.  edge_add [E,C] nullable. */
+SGG_API int sgg_node_edge_features_add(const float *fmap, int B, int C, int Hf, int Wf,
+                               const float *rois, int N,
+                               const int64_t *union_inds, int64_t row_stride, int col_subj, int col_obj, int E,
+                               float spatial_scale, int pool, int sampling_ratio, const float *edge_add,
+                               float *node_feat, float *edge_feat, void *ws, size_t ws_bytes, void *stream);
 
 /* ==== training tail: lib/losses.py, lib/pytorch_misc.py grad_clip / get_optim =============== */
 

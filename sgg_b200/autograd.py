@@ -75,13 +75,14 @@ def message_pass(rel_rep, obj_rep, rel_inds, params, mp_iter=3):
     return ops.message_pass(rel_rep, obj_rep, graph, params, mp_iter)
 
 
-def node_edge_features(fmap, rois, union_inds, spatial_scale, pool=7, sampling_ratio=2):
+def node_edge_features(fmap, rois, union_inds, spatial_scale, pool=7, sampling_ratio=2, edge_add=None):
     """RoIAlign of objects and union boxes.  ``fmap`` is produced under no_grad and detached by the caller
     (rel_model_stanford.py:125-131), so no backward is defined; a differentiable fmap (GAN ``-attachG``
     path, out of scope) is rejected loudly rather than silently dropping its gradient."""
     if torch.is_grad_enabled() and fmap.requires_grad:
         raise NotImplementedError('node_edge_features: gradient w.r.t. fmap (GAN -attachG path) is not implemented')
-    return ops.node_edge_features(fmap.detach(), rois.detach(), union_inds, spatial_scale, pool, sampling_ratio)
+    return ops.node_edge_features(fmap.detach(), rois.detach(), union_inds, spatial_scale, pool, sampling_ratio,
+                                  edge_add=edge_add)
 
 
 def _conv_params(conv):

@@ -15,6 +15,16 @@ k_gemm(const float *__restrict__ A, int lda, const float *__restrict__ B, int ld
   constexpr int TM = BM / 16;
   const int m0 = blockIdx.y * BM;
   const int j0 = blockIdx.x * (NW * BN);
+  if (gridDim.z > 1) {
+    // split-K: slice z reduces k in [z*per, min(K, (z+1)*per)) into its own partial matrix (C = partials, ldc = N,
+    // accumulate = 0); k_splitk_sum adds the slices in a fixed order.  per is a multiple of 16 (loader granularity).
+    const int per = (((K + (int)gridDim.z - 1) / (int)gridDim.z) + 15) & ~15;
+    const int k_lo = blockIdx.z * per;
+    A += A_COL ? (size_t)k_lo * lda : (size_t)k_lo;
+    B += B_COL ? (size_t)k_lo * ldb : (size_t)k_lo;
+    C += (size_t)blockIdx.z * M * ldc;
+    K = K - k_lo < per ? K - k_lo : per;
+  }
   float acc[TM][NW][4];
 #pragma unroll
   for (int i = 0; i < TM; ++i)
@@ -58,54 +68,89 @@ k_gemm(const float *__restrict__ A, int lda, const float *__restrict__ B, int ld
 
 template <int BM, int NW, bool A_COL, bool B_COL>
 static int launch_gemm_t(const float *A, int lda, const float *B, int ldb, float *C, int ldc, int M, int N, int K,
-                         int accumulate, cudaStream_t st) {
+                         int accumulate, cudaStream_t st, int splits = 1) {
   static bool attr_done = false;
   const size_t smem = TileSmem<BM, NW>::bytes;
   if (!attr_done) {
     SGG_CUDA_TRY(cudaFuncSetAttribute(k_gemm<BM, NW, A_COL, B_COL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
-  dim3 grid((N + NW * BN - 1) / (NW * BN), (M + BM - 1) / BM);
+  dim3 grid((N + NW * BN - 1) / (NW * BN), (M + BM - 1) / BM, splits);
   k_gemm<BM, NW, A_COL, B_COL><<<grid, NTHREADS, smem, st>>>(A, lda, B, ldb, C, ldc, M, N, K, accumulate);
   SGG_RETURN_IF_LAUNCH_FAILED("k_gemm");
   return 0;
 }
 
+// C (=|+=) sum over split-K slices, fixed order (deterministic)
+__global__ void k_splitk_sum(const float *__restrict__ part, int splits, int M, int N, float *__restrict__ C, int ldc,
+                             int accumulate) {
+  const size_t mn = (size_t)M * N;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < mn; i += (size_t)gridDim.x * blockDim.x) {
+    float v = 0.f;
+    for (int z = 0; z < splits; ++z) v += part[(size_t)z * mn + i];
+    float *cp = C + (i / N) * (size_t)ldc + (i % N);
+    *cp = accumulate ? *cp + v : v;
+  }
+}
+
 template <bool A_COL, bool B_COL>
 static int launch_gemm_l(const float *A, int lda, const float *B, int ldb, float *C, int ldc, int M, int N, int K,
-                         int accumulate, cudaStream_t st) {
+                         int accumulate, cudaStream_t st, float *skws, size_t skws_floats) {
   const int sms = sgg_num_sms();
-  int best_bm = 64, best_nw = 1;
+  int best_bm = 64, best_nw = 1, best_s = 1;
   double best = 1e30;
   const int bms[2] = {64, 128};
+  // split-K (weight-gradient GEMMs: few output tiles, very long K) needs a partials workspace and slices of >= 256 k
+  int max_s = 1;
+  if (skws != nullptr && A_COL && B_COL) {
+    max_s = K / 256;
+    const size_t fit = skws_floats / ((size_t)M * N);
+    if ((size_t)max_s > fit) max_s = (int)fit;
+    if (max_s > 8) max_s = 8;
+    if (max_s < 1) max_s = 1;
+  }
   for (int bi = 0; bi < 2; ++bi)
-    for (int nw = 1; nw <= 3; ++nw) {
-      const int bm = bms[bi];
-      long tiles = (long)((N + nw * BN - 1) / (nw * BN)) * ((M + bm - 1) / bm);
-      int occ = bm == 64 ? 2 : 1;
-      long waves = (tiles + (long)sms * occ - 1) / ((long)sms * occ);
-      double cost = (double)waves * occ * (bm * nw + 0.35 * (bm + nw * BN));
-      if (cost < best) { best = cost; best_bm = bm; best_nw = nw; }
-    }
+    for (int nw = 1; nw <= 3; ++nw)
+      for (int sp = 1; sp <= max_s; ++sp) {
+        const int bm = bms[bi];
+        long tiles = (long)((N + nw * BN - 1) / (nw * BN)) * ((M + bm - 1) / bm) * sp;
+        int occ = bm == 64 ? 2 : 1;
+        long waves = (tiles + (long)sms * occ - 1) / ((long)sms * occ);
+        // ~microseconds: per-tile cost (FMAs + operand traffic) x slice length, calibrated on B200 (a <128,1> tile
+        // over K = 9600 takes ~690 us); a split adds the reducer launch and its partials traffic
+        double cost = (double)waves * occ * (bm * nw + 0.35 * (bm + nw * BN)) * ((double)K / sp) * 3.7e-4 +
+                      (sp > 1 ? 4.0 + (double)M * N * (sp + 1) * 4.0 / 3.0e6 : 0.0);
+        if (cost < best) { best = cost; best_bm = bm; best_nw = nw; best_s = sp; }
+      }
+  float *Cd = C;
+  int ldd = ldc, accd = accumulate;
+  if (best_s > 1) { Cd = skws; ldd = N; accd = 0; }
+  int rc = -1;
 #define SGG_CASE(BM_, NW_) \
-  if (best_bm == BM_ && best_nw == NW_) return launch_gemm_t<BM_, NW_, A_COL, B_COL>(A, lda, B, ldb, C, ldc, M, N, K, accumulate, st)
+  if (best_bm == BM_ && best_nw == NW_) rc = launch_gemm_t<BM_, NW_, A_COL, B_COL>(A, lda, B, ldb, Cd, ldd, M, N, K, accd, st, best_s)
   SGG_CASE(64, 1); SGG_CASE(64, 2); SGG_CASE(64, 3);
   SGG_CASE(128, 1); SGG_CASE(128, 2); SGG_CASE(128, 3);
 #undef SGG_CASE
-  return sgg_set_err(SGG_E_BADARG, "gemm: no tile config");
+  if (rc == -1) return sgg_set_err(SGG_E_BADARG, "gemm: no tile config");
+  if (rc != 0 || best_s == 1) return rc;
+  const size_t mn = (size_t)M * N;
+  const int blocks = (int)((mn + 255) / 256 < 1184 ? (mn + 255) / 256 : 1184);
+  k_splitk_sum<<<blocks, 256, 0, st>>>(skws, best_s, M, N, C, ldc, accumulate);
+  SGG_RETURN_IF_LAUNCH_FAILED("k_splitk_sum");
+  return 0;
 }
 
 int launch_gemm(const float *A, int lda, bool a_col, const float *B, int ldb, bool b_col, float *C, int ldc, int M,
-                int N, int K, bool accumulate, cudaStream_t st) {
+                int N, int K, bool accumulate, cudaStream_t st, float *skws, size_t skws_floats) {
   if (M <= 0 || N <= 0) return 0;
   if (K <= 0) {
     if (!accumulate) SGG_CUDA_TRY(cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)N * 4, M, st));
     return 0;
   }
-  if (!a_col && !b_col) return launch_gemm_l<false, false>(A, lda, B, ldb, C, ldc, M, N, K, accumulate, st);
-  if (!a_col && b_col) return launch_gemm_l<false, true>(A, lda, B, ldb, C, ldc, M, N, K, accumulate, st);
-  if (a_col && !b_col) return launch_gemm_l<true, false>(A, lda, B, ldb, C, ldc, M, N, K, accumulate, st);
-  return launch_gemm_l<true, true>(A, lda, B, ldb, C, ldc, M, N, K, accumulate, st);
+  if (!a_col && !b_col) return launch_gemm_l<false, false>(A, lda, B, ldb, C, ldc, M, N, K, accumulate, st, skws, skws_floats);
+  if (!a_col && b_col) return launch_gemm_l<false, true>(A, lda, B, ldb, C, ldc, M, N, K, accumulate, st, skws, skws_floats);
+  if (a_col && !b_col) return launch_gemm_l<true, false>(A, lda, B, ldb, C, ldc, M, N, K, accumulate, st, skws, skws_floats);
+  return launch_gemm_l<true, true>(A, lda, B, ldb, C, ldc, M, N, K, accumulate, st, skws, skws_floats);
 }
 
 // column sums: out[c] (=|+=) sum_r X[r*ld + c]   — two deterministic stages (partials, then fixed-order sum)
@@ -113,9 +158,14 @@ __global__ void k_colsum_partial(const float *__restrict__ X, int ld, int rows, 
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= cols) return;
   const int r0 = blockIdx.y * rows_per, r1 = min(rows, r0 + rows_per);
-  float s = 0.f;
-  for (int r = r0; r < r1; ++r) s += X[(size_t)r * ld + c];
-  part[(size_t)blockIdx.y * cols + c] = s;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;          // independent chains: four loads in flight per thread
+  int r = r0;
+  for (; r + 3 < r1; r += 4) {
+    s0 += X[(size_t)r * ld + c]; s1 += X[(size_t)(r + 1) * ld + c];
+    s2 += X[(size_t)(r + 2) * ld + c]; s3 += X[(size_t)(r + 3) * ld + c];
+  }
+  for (; r < r1; ++r) s0 += X[(size_t)r * ld + c];
+  part[(size_t)blockIdx.y * cols + c] = (s0 + s1) + (s2 + s3);
 }
 __global__ void k_colsum_final(const float *__restrict__ part, int nparts, int cols, float *__restrict__ out, int accumulate) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -125,21 +175,66 @@ __global__ void k_colsum_final(const float *__restrict__ part, int nparts, int c
   out[c] = accumulate ? out[c] + s : s;
 }
 
-size_t colsum_workspace_floats(int rows, int cols) {
-  int nparts = (rows + 255) / 256; if (nparts > 128) nparts = 128; if (nparts < 1) nparts = 1;
-  return (size_t)nparts * cols;
+static int colsum_parts(int rows) {          // row slices: 32 rows each, at most 256 slices
+  int nparts = (rows + 31) / 32; if (nparts > 256) nparts = 256; if (nparts < 1) nparts = 1;
+  return nparts;
 }
+size_t colsum_workspace_floats(int rows, int cols) { return (size_t)colsum_parts(rows) * cols; }
 
 int launch_colsum(const float *X, int ld, int rows, int cols, float *out, bool accumulate, float *ws, cudaStream_t st) {
   if (cols <= 0) return 0;
   if (rows <= 0) { if (!accumulate) SGG_CUDA_TRY(cudaMemsetAsync(out, 0, (size_t)cols * 4, st)); return 0; }
-  int nparts = (rows + 255) / 256; if (nparts > 128) nparts = 128;
+  int nparts = colsum_parts(rows);
   const int rows_per = (rows + nparts - 1) / nparts;
   nparts = (rows + rows_per - 1) / rows_per;
   dim3 grid((cols + 127) / 128, nparts);
   k_colsum_partial<<<grid, 128, 0, st>>>(X, ld, rows, cols, rows_per, ws);
   SGG_RETURN_IF_LAUNCH_FAILED("k_colsum_partial");
   k_colsum_final<<<(cols + 127) / 128, 128, 0, st>>>(ws, nparts, cols, out, accumulate ? 1 : 0);
+  SGG_RETURN_IF_LAUNCH_FAILED("k_colsum_final");
+  return 0;
+}
+
+// out[k][c] (+)= sum_r W4[r][k] * X[r][c], k = 0..3 — the scalar-gate weight gradients (a 4 x cols "GEMM" with a
+// very long reduction; as a GEMM it occupied 8 CTAs).  Two deterministic stages like colsum.
+__global__ void __launch_bounds__(128) k_wsum4_partial(const float *__restrict__ W4, const float *__restrict__ X, int rows,
+                                                       int cols, int rows_per, float *__restrict__ part) {
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (c >= cols) return;
+  const int r0 = blockIdx.y * rows_per, r1 = min(rows, r0 + rows_per);
+  float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
+  for (int r = r0; r < r1; ++r) {
+    const float4 w = __ldg(reinterpret_cast<const float4 *>(W4) + r);
+    const float4 x = *reinterpret_cast<const float4 *>(X + (size_t)r * cols + c);
+    a0.x += w.x * x.x; a0.y += w.x * x.y; a0.z += w.x * x.z; a0.w += w.x * x.w;
+    a1.x += w.y * x.x; a1.y += w.y * x.y; a1.z += w.y * x.z; a1.w += w.y * x.w;
+    a2.x += w.z * x.x; a2.y += w.z * x.y; a2.z += w.z * x.z; a2.w += w.z * x.w;
+    a3.x += w.w * x.x; a3.y += w.w * x.y; a3.z += w.w * x.z; a3.w += w.w * x.w;
+  }
+  float *p = part + (size_t)blockIdx.y * 4 * cols + c;
+  *reinterpret_cast<float4 *>(p) = a0;
+  *reinterpret_cast<float4 *>(p + cols) = a1;
+  *reinterpret_cast<float4 *>(p + 2 * (size_t)cols) = a2;
+  *reinterpret_cast<float4 *>(p + 3 * (size_t)cols) = a3;
+}
+static int wsum4_parts(int rows) {
+  int nparts = (rows + 15) / 16; if (nparts > 296) nparts = 296; if (nparts < 1) nparts = 1;
+  return nparts;
+}
+size_t wsum4_workspace_floats(int rows, int cols) { return (size_t)wsum4_parts(rows) * 4 * cols; }
+
+int launch_wsum4(const float *W4, const float *X, int rows, int cols, float *out, bool accumulate, float *ws,
+                 cudaStream_t st) {
+  if (cols <= 0) return 0;
+  if (cols & 3) return sgg_set_err(SGG_E_BADARG, "wsum4: cols must be a multiple of 4");
+  if (rows <= 0) { if (!accumulate) SGG_CUDA_TRY(cudaMemsetAsync(out, 0, (size_t)cols * 16, st)); return 0; }
+  int nparts = wsum4_parts(rows);
+  const int rows_per = (rows + nparts - 1) / nparts;
+  nparts = (rows + rows_per - 1) / rows_per;
+  dim3 grid((cols / 4 + 127) / 128, nparts);
+  k_wsum4_partial<<<grid, 128, 0, st>>>(W4, X, rows, cols, rows_per, ws);
+  SGG_RETURN_IF_LAUNCH_FAILED("k_wsum4_partial");
+  k_colsum_final<<<(4 * cols + 127) / 128, 128, 0, st>>>(ws, nparts, 4 * cols, out, accumulate ? 1 : 0);
   SGG_RETURN_IF_LAUNCH_FAILED("k_colsum_final");
   return 0;
 }

@@ -6,10 +6,19 @@ cudaStream_t side_stream(cudaStream_t main, int idx = 0);
 int stream_order(cudaStream_t from, cudaStream_t to);
 int launch_linear(const float *x, const float *w, const float *b, float *y, int M, int Nout, int K, int relu,
                   cudaStream_t st);
+// skws (nullable): split-K partials for weight-gradient GEMMs (a_col && b_col); up to skws_floats / (M*N) slices
 int launch_gemm(const float *A, int lda, bool a_col, const float *B, int ldb, bool b_col, float *C, int ldc, int M,
-                int N, int K, bool accumulate, cudaStream_t st);
+                int N, int K, bool accumulate, cudaStream_t st, float *skws = nullptr, size_t skws_floats = 0);
+size_t wsum4_workspace_floats(int rows, int cols);
+int launch_wsum4(const float *W4, const float *X, int rows, int cols, float *out, bool accumulate, float *ws,
+                 cudaStream_t st);
 size_t colsum_workspace_floats(int rows, int cols);
 int launch_colsum(const float *X, int ld, int rows, int cols, float *out, bool accumulate, float *ws, cudaStream_t st);
+// 3xTF32 engine (tc_gemm.cu), callable directly: fp32 exponent range, used by the backward GEMMs whatever the
+// forward engine is.  w_split = [hi | lo], each [Nout, K] fp32 (k_tc_split convention: hi = x & 0xffffe000).
+size_t tc32_linear_workspace_floats(int M, int Nout, int K);
+int tc32_linear(const float *x, const float *w_split, const float *b, float *y, int M, int Nout, int K, int relu,
+                float *ws, cudaStream_t st);
 size_t tc_linear_workspace_floats(int M, int Nout, int K);
 int tc_linear(const float *x, const float *w_split, const float *b, float *y, int M, int Nout, int K, int relu,
               float *ws, cudaStream_t st);

@@ -12,6 +12,7 @@
 //   k_node_bwd         CTA per node (CSR, fixed order): dP[n] = sum_out g_sub dgi_e + sum_in g_obj dgi_e;
 //                      da[n,k] = sum of edge dlogits; dV[n] += sum_k da[n,k] w_k[:H]
 // All reductions are deterministic (no float atomics).
+#include <stdlib.h>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -155,9 +156,69 @@ __global__ void k_gate_grad_finish(const float *__restrict__ tV, const float *__
   if (i < 4 && db[i]) db[i][0] += gb[i];
 }
 
+// ---- tensor-core backward GEMMs (3xTF32 engine: fp32 exponent range, so gradients of any magnitude are safe) ----
+// The engine computes y = x w^T with x raw fp32 [M,K] and w pre-split [hi | lo] [Nout,K] (K contiguous), so
+//   dX = dY W        -> x = dY,            w = split(W^T)                       (transpose of a weight, per call)
+//   dW += dY^T X     -> x = dY^T [3H,Mp],  w = split(X^T) [H,Mp], Mp = M padded with zero rows to a multiple of 32
+// Transposes go through 32x32 shared-memory tiles (coalesced both ways); rows in [R, Rpad) are written as zeros.
+template <bool SPLIT>
+__global__ void __launch_bounds__(256) k_transpose32(const float *__restrict__ in, int R, int C, float *__restrict__ hi,
+                                                     float *__restrict__ lo, int Rpad) {
+  __shared__ float tile[32][33];
+  const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < R && c < C) ? in[(size_t)r * C + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (c < C && r < Rpad) {
+      const float v = tile[threadIdx.x][i];
+      if (SPLIT) {
+        const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);     // tc_gemm.cu: k_tc_split
+        hi[(size_t)c * Rpad + r] = h;
+        lo[(size_t)c * Rpad + r] = v - h;
+      } else {
+        hi[(size_t)c * Rpad + r] = v;
+      }
+    }
+  }
+}
+// in [R,C] row-major -> out [C,Rpad]; split = true writes [hi | lo] planes of C*Rpad floats each
+static int launch_transpose(const float *in, int R, int C, float *out, int Rpad, bool split, cudaStream_t st) {
+  dim3 grid((Rpad + 31) / 32, (C + 31) / 32);
+  if (split) k_transpose32<true><<<grid, dim3(32, 8), 0, st>>>(in, R, C, out, out + (size_t)C * Rpad, Rpad);
+  else k_transpose32<false><<<grid, dim3(32, 8), 0, st>>>(in, R, C, out, nullptr, Rpad);
+  SGG_RETURN_IF_LAUNCH_FAILED("k_transpose32");
+  return 0;
+}
+__global__ void k_add_inplace(float *__restrict__ c, const float *__restrict__ t, size_t n4) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 a = reinterpret_cast<float4 *>(c)[i];
+    const float4 b = reinterpret_cast<const float4 *>(t)[i];
+    a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    reinterpret_cast<float4 *>(c)[i] = a;
+  }
+}
+static int launch_add(float *c, const float *t, size_t n, cudaStream_t st) {      // n % 4 == 0 (H is a multiple of 64)
+  const size_t n4 = n / 4;
+  const int blocks = (int)((n4 + 255) / 256 < 1184 ? (n4 + 255) / 256 : 1184);
+  k_add_inplace<<<blocks > 0 ? blocks : 1, 256, 0, st>>>(c, t, n4);
+  SGG_RETURN_IF_LAUNCH_FAILED("k_add_inplace");
+  return 0;
+}
+constexpr int TC_BWD_MIN_ROWS = 256;     // dX-type GEMMs with fewer rows stay on the SIMT tiles
+constexpr int TC_BWD_MIN_K = 2048;       // dW-type GEMMs with a shorter reduction stay on the SIMT tiles (split-K)
+static inline int pad32(int x) { return (x + 31) & ~31; }
+
 struct BwdScratch {
-  float *dV[2], *dE[2], *dgi_n, *dgh_n, *dgi_e, *dgh_e, *dctx, *dP, *dl, *da, *tV, *tE, *gb, *cs;
+  float *dV[2], *dE[2], *dgi_n, *dgh_n, *dgi_e, *dgh_e, *dctx, *dP, *dl, *da, *tV, *tE, *gb, *cs, *ws4, *sk;
+  size_t sk_floats;
+  // tensor-core backward: W^T splits (node_ih, node_hh, edge_ih, edge_hh), transposed operands, GEMM output, split-K partials
+  float *wt[4], *xT, *bT, *tmp, *lin;
 };
+constexpr int SPLITK_MAX = 4;      // split-K slices of the [3H,H] weight-gradient GEMMs (reduction over E or N rows)
 static size_t bwd_layout(BwdScratch *s, void *ws, int N, int E, int H) {
   SggArena ar(ws, (size_t)-1);
   const size_t n1 = N > 0 ? N : 1, e1 = E > 0 ? E : 1;
@@ -168,6 +229,20 @@ static size_t bwd_layout(BwdScratch *s, void *ws, int N, int E, int H) {
   s->dl = ar.take<float>(e1 * 4); s->da = ar.take<float>(n1 * 4);
   s->tV = ar.take<float>((size_t)4 * H); s->tE = ar.take<float>((size_t)4 * H); s->gb = ar.take<float>(4);
   s->cs = ar.take<float>(colsum_workspace_floats((int)(e1 > n1 ? e1 : n1), 3 * H));
+  s->ws4 = ar.take<float>(wsum4_workspace_floats((int)(e1 > n1 ? e1 : n1), H));
+  s->sk_floats = (size_t)SPLITK_MAX * 3 * H * H;
+  s->sk = ar.take<float>(s->sk_floats);
+  const size_t big = e1 > n1 ? e1 : n1;
+  const int mp = pad32((int)big);
+  for (int i = 0; i < 4; ++i) s->wt[i] = ar.take<float>((size_t)2 * 3 * H * H);
+  s->xT = ar.take<float>((size_t)3 * H * mp);
+  s->bT = ar.take<float>((size_t)2 * H * mp);
+  s->tmp = ar.take<float>(big * H > (size_t)3 * H * H ? big * H : (size_t)3 * H * H);
+  size_t lin = tc32_linear_workspace_floats(3 * H, H, mp);                       // dW-type
+  const size_t l1 = tc32_linear_workspace_floats((int)e1, H, 3 * H), l2 = tc32_linear_workspace_floats((int)n1, H, 3 * H);
+  if (l1 > lin) lin = l1;
+  if (l2 > lin) lin = l2;
+  s->lin = ar.take<float>(lin > 0 ? lin : 1);
   return ar.off;
 }
 
@@ -203,7 +278,33 @@ extern "C" int sgg_mp_backward(const float *obj_rep, const float *rel_rep, const
   SGG_CUDA_TRY(cudaMemsetAsync(s.gb, 0, sizeof(float) * 4, st));
   auto ew_blocks = [&](size_t n) { size_t b = (n + 255) / 256; return (int)(b < 4096 ? (b ? b : 1) : 4096); };
   auto gemm = [&](const float *A, int lda, bool ac, const float *B, int ldb, bool bc, float *C, int ldc, int M, int Nn,
-                  int K, bool acc) { return launch_gemm(A, lda, ac, B, ldb, bc, C, ldc, M, Nn, K, acc, st); };
+                  int K, bool acc) { return launch_gemm(A, lda, ac, B, ldb, bc, C, ldc, M, Nn, K, acc, st, s.sk, s.sk_floats); };
+  // tensor-core routes (enabled when the forward ran on tensor cores, i.e. the caller passed operand splits)
+  static const bool tc_env = [] { const char *v = getenv("SGG_BWD_TC"); return v == nullptr || atoi(v) != 0; }();
+  const bool tc_on = tc_env && w->edge_w_hh_split != nullptr && w->node_w_hh_split != nullptr;
+  enum { WT_NODE_IH = 0, WT_NODE_HH = 1, WT_EDGE_IH = 2, WT_EDGE_HH = 3 };
+  if (tc_on) {      // W [3H,H] -> split(W^T) [H,3H], once per backward call (4 x 3 MB)
+    const float *ws4[4] = {w->node_w_ih, w->node_w_hh, w->edge_w_ih, w->edge_w_hh};
+    for (int i = 0; i < 4; ++i)
+      if ((rc = launch_transpose(ws4[i], 3 * H, H, s.wt[i], 3 * H, true, st))) return rc;
+  }
+  // dX[M,H] (=|+=) dY[M,3H] W[3H,H]
+  auto gemm_dx = [&](const float *dY, int wi, const float *W, float *out, int M, bool acc) -> int {
+    if (!tc_on || M < TC_BWD_MIN_ROWS) return gemm(dY, 3 * H, false, W, H, true, out, H, M, H, 3 * H, acc);
+    int r = tc32_linear(dY, s.wt[wi], nullptr, acc ? s.tmp : out, M, H, 3 * H, 0, s.lin, st);
+    if (r == 0 && acc) r = launch_add(out, s.tmp, (size_t)M * H, st);
+    return r;
+  };
+  // dW[3H,H] += dY[M,3H]^T X[M,H]
+  auto gemm_dw = [&](const float *dY, const float *X, float *dW, int M) -> int {
+    if (!tc_on || M < TC_BWD_MIN_K) return gemm(dY, 3 * H, true, X, H, true, dW, H, 3 * H, H, M, true);
+    const int mp = pad32(M);
+    int r = launch_transpose(dY, M, 3 * H, s.xT, mp, false, st);
+    if (r == 0) r = launch_transpose(X, M, H, s.bT, mp, true, st);
+    if (r == 0) r = tc32_linear(s.xT, s.bT, nullptr, s.tmp, 3 * H, H, mp, 0, s.lin, st);
+    if (r == 0) r = launch_add(dW, s.tmp, (size_t)3 * H * H, st);
+    return r;
+  };
   auto colsum = [&](const float *X, int rows, int cols, float *out) -> int {
     return out ? launch_colsum(X, cols, rows, cols, out, true, s.cs, st) : 0;
   };
@@ -216,20 +317,20 @@ extern "C" int sgg_mp_backward(const float *obj_rep, const float *rel_rep, const
     if (N > 0) {
       k_gru_bwd<<<ew_blocks(vN / 4), 256, 0, st>>>(dVn, tp.cacheV + (size_t)(t + 1) * N * 4 * H, V, N, H, s.dgi_n, s.dgh_n, dV);
       SGG_RETURN_IF_LAUNCH_FAILED("k_gru_bwd");
-      if (grads->node_w_ih && (rc = gemm(s.dgi_n, 3 * H, true, ctx, H, true, grads->node_w_ih, H, 3 * H, H, N, true))) return rc;
-      if (grads->node_w_hh && (rc = gemm(s.dgh_n, 3 * H, true, V, H, true, grads->node_w_hh, H, 3 * H, H, N, true))) return rc;
+      if (grads->node_w_ih && (rc = gemm_dw(s.dgi_n, ctx, grads->node_w_ih, N))) return rc;
+      if (grads->node_w_hh && (rc = gemm_dw(s.dgh_n, V, grads->node_w_hh, N))) return rc;
       if ((rc = colsum(s.dgi_n, N, 3 * H, grads->node_b_ih))) return rc;
       if ((rc = colsum(s.dgh_n, N, 3 * H, grads->node_b_hh))) return rc;
-      if ((rc = gemm(s.dgi_n, 3 * H, false, w->node_w_ih, H, true, s.dctx, H, N, H, 3 * H, false))) return rc;
-      if ((rc = gemm(s.dgh_n, 3 * H, false, w->node_w_hh, H, true, dV, H, N, H, 3 * H, true))) return rc;
+      if ((rc = gemm_dx(s.dgi_n, WT_NODE_IH, w->node_w_ih, s.dctx, N, false))) return rc;
+      if ((rc = gemm_dx(s.dgh_n, WT_NODE_HH, w->node_w_hh, dV, N, true))) return rc;
     }
     if (E > 0) {
       k_gru_bwd<<<ew_blocks(eN / 4), 256, 0, st>>>(dEn, tp.cacheE + (size_t)(t + 1) * E * 4 * H, Eh, E, H, s.dgi_e, s.dgh_e, dE);
       SGG_RETURN_IF_LAUNCH_FAILED("k_gru_bwd");
-      if (grads->edge_w_hh && (rc = gemm(s.dgh_e, 3 * H, true, Eh, H, true, grads->edge_w_hh, H, 3 * H, H, E, true))) return rc;
+      if (grads->edge_w_hh && (rc = gemm_dw(s.dgh_e, Eh, grads->edge_w_hh, E))) return rc;
       if ((rc = colsum(s.dgh_e, E, 3 * H, grads->edge_b_hh))) return rc;
       if ((rc = colsum(s.dgi_e, E, 3 * H, grads->edge_b_ih))) return rc;
-      if ((rc = gemm(s.dgh_e, 3 * H, false, w->edge_w_hh, H, true, dE, H, E, H, 3 * H, true))) return rc;
+      if ((rc = gemm_dx(s.dgh_e, WT_EDGE_HH, w->edge_w_hh, dE, E, true))) return rc;
       k_edge_bwd<<<(int)(((size_t)E * 32 + 255) / 256), 256, 0, st>>>(s.dgi_e, P, s.dctx, Eh, gt, g.subj, g.obj, E, H,
                                                                     w->gate_w[0], w->gate_w[1], w->gate_w[2],
                                                                     w->gate_w[3], s.dl, dE);
@@ -243,10 +344,10 @@ extern "C" int sgg_mp_backward(const float *obj_rep, const float *rel_rep, const
         k_node_bwd<<<N, 128, 0, st>>>(s.dgi_e, gt, s.dl, g.out_ptr, g.out_idx, g.in_ptr, g.in_idx, H, w->gate_w[0],
                                       w->gate_w[1], w->gate_w[2], w->gate_w[3], s.dP, s.da, dV);
         SGG_RETURN_IF_LAUNCH_FAILED("k_node_bwd");
-        if (grads->edge_w_ih && (rc = gemm(s.dP, 3 * H, true, V, H, true, grads->edge_w_ih, H, 3 * H, H, N, true))) return rc;
-        if ((rc = gemm(s.dP, 3 * H, false, w->edge_w_ih, H, true, dV, H, N, H, 3 * H, true))) return rc;
-        if ((rc = gemm(s.da, 4, true, V, H, true, s.tV, H, 4, H, N, true))) return rc;
-        if ((rc = gemm(s.dl, 4, true, Eh, H, true, s.tE, H, 4, H, E, true))) return rc;
+        if (grads->edge_w_ih && (rc = gemm_dw(s.dP, V, grads->edge_w_ih, N))) return rc;
+        if ((rc = gemm_dx(s.dP, WT_EDGE_IH, w->edge_w_ih, dV, N, true))) return rc;
+        if ((rc = launch_wsum4(s.da, V, N, H, s.tV, true, s.ws4, st))) return rc;      // tV[k] += sum_n da[n][k] V[n]
+        if ((rc = launch_wsum4(s.dl, Eh, E, H, s.tE, true, s.ws4, st))) return rc;     // tE[k] += sum_e dl[e][k] E[e]
         if ((rc = launch_colsum(s.dl, 4, E, 4, s.gb, true, s.cs, st))) return rc;
       }
     }
@@ -256,18 +357,18 @@ extern "C" int sgg_mp_backward(const float *obj_rep, const float *rel_rep, const
   if (N > 0) {
     k_gru_bwd<<<ew_blocks(vN / 4), 256, 0, st>>>(dVn, tp.cacheV, nullptr, N, H, s.dgi_n, s.dgh_n, nullptr);
     SGG_RETURN_IF_LAUNCH_FAILED("k_gru_bwd");
-    if (grads->node_w_ih && (rc = gemm(s.dgi_n, 3 * H, true, obj_rep, H, true, grads->node_w_ih, H, 3 * H, H, N, true))) return rc;
+    if (grads->node_w_ih && (rc = gemm_dw(s.dgi_n, obj_rep, grads->node_w_ih, N))) return rc;
     if ((rc = colsum(s.dgi_n, N, 3 * H, grads->node_b_ih))) return rc;
     if ((rc = colsum(s.dgh_n, N, 3 * H, grads->node_b_hh))) return rc;
-    if (d_obj_rep && (rc = gemm(s.dgi_n, 3 * H, false, w->node_w_ih, H, true, d_obj_rep, H, N, H, 3 * H, false))) return rc;
+    if (d_obj_rep && (rc = gemm_dx(s.dgi_n, WT_NODE_IH, w->node_w_ih, d_obj_rep, N, false))) return rc;
   }
   if (E > 0) {
     k_gru_bwd<<<ew_blocks(eN / 4), 256, 0, st>>>(dEn, tp.cacheE, nullptr, E, H, s.dgi_e, s.dgh_e, nullptr);
     SGG_RETURN_IF_LAUNCH_FAILED("k_gru_bwd");
-    if (grads->edge_w_ih && (rc = gemm(s.dgi_e, 3 * H, true, rel_rep, H, true, grads->edge_w_ih, H, 3 * H, H, E, true))) return rc;
+    if (grads->edge_w_ih && (rc = gemm_dw(s.dgi_e, rel_rep, grads->edge_w_ih, E))) return rc;
     if ((rc = colsum(s.dgi_e, E, 3 * H, grads->edge_b_ih))) return rc;
     if ((rc = colsum(s.dgh_e, E, 3 * H, grads->edge_b_hh))) return rc;
-    if (d_rel_rep && (rc = gemm(s.dgi_e, 3 * H, false, w->edge_w_ih, H, true, d_rel_rep, H, E, H, 3 * H, false))) return rc;
+    if (d_rel_rep && (rc = gemm_dx(s.dgi_e, WT_EDGE_IH, w->edge_w_ih, d_rel_rep, E, false))) return rc;
   }
   k_gate_grad_finish<<<(4 * H + 255) / 256, 256, 0, st>>>(s.tV, s.tE, s.gb, H, grads->gate_w[0], grads->gate_w[1],
                                                           grads->gate_w[2], grads->gate_w[3], grads->gate_b[0],

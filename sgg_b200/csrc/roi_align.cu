@@ -25,7 +25,8 @@ __device__ __forceinline__ float bilinear(const float *__restrict__ f, int Hf, i
 __global__ void __launch_bounds__(256)
 k_roi_align(const float *__restrict__ fmap, int C, int Hf, int Wf, const float *__restrict__ rois, int N,
             const int64_t *__restrict__ ui, int64_t stride, int cs, int co, int E, float scale, int pool, int sr,
-            float *__restrict__ node_out, float *__restrict__ edge_out, int do_node, int do_edge) {
+            float *__restrict__ node_out, float *__restrict__ edge_out, int do_node, int do_edge,
+            const float *__restrict__ edge_add) {
   const int pp = pool * pool;
   const size_t per = (size_t)C * pp;
   const size_t r_begin = do_node ? 0 : (size_t)N, r_end = do_edge ? (size_t)N + E : (size_t)N;
@@ -59,7 +60,9 @@ k_roi_align(const float *__restrict__ fmap, int C, int Hf, int Wf, const float *
         acc += bilinear(f, Hf, Wf, y, x);
       }
     }
-    *dst = acc / (float)(sr * sr);
+    float v = acc / (float)(sr * sr);
+    if (edge_add != nullptr && r >= (size_t)N) v += edge_add[(r - N) * C + c];
+    *dst = v;
   }
 }
 
@@ -89,7 +92,8 @@ constexpr int RA_MAXS = 32;   // max samples per axis (pool * sampling_ratio)
 __global__ void __launch_bounds__(256)
 k_roi_align_nhwc(const float *__restrict__ fmap /*[B,Hf,Wf,C]*/, int C, int Hf, int Wf, const float *__restrict__ rois,
                  int N, const int64_t *__restrict__ ui, int64_t stride, int cs, int co, int E, float scale, int pool,
-                 int sr, float *__restrict__ node_out, float *__restrict__ edge_out, int r_begin) {
+                 int sr, float *__restrict__ node_out, float *__restrict__ edge_out, int r_begin,
+                 const float *__restrict__ edge_add) {
   extern __shared__ __align__(16) float s_out[];          // [C][pool*pool]
   __shared__ int s_lo[2][RA_MAXS], s_hi[2][RA_MAXS];
   __shared__ float s_l[2][RA_MAXS], s_h[2][RA_MAXS];       // lerp weights (l = frac, h = 1 - frac); 0,0 when invalid
@@ -130,6 +134,7 @@ k_roi_align_nhwc(const float *__restrict__ fmap /*[B,Hf,Wf,C]*/, int C, int Hf, 
   const float *f = fmap + (size_t)b * Hf * Wf * C;
   const float inv = 1.f / (float)(sr * sr);
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float addv = (edge_add != nullptr && r >= N) ? edge_add[(size_t)(r - N) * C + c] : 0.f;
     for (int ph = 0; ph < pool; ++ph)
       for (int pw = 0; pw < pool; ++pw) {
         float acc = 0.f;
@@ -147,7 +152,7 @@ k_roi_align_nhwc(const float *__restrict__ fmap /*[B,Hf,Wf,C]*/, int C, int Hf, 
             acc += hy * hx * v1 + hy * lx * v2 + ly * hx * v3 + ly * lx * v4;
           }
         }
-        s_out[c * pp + ph * pool + pw] = acc * inv;
+        s_out[c * pp + ph * pool + pw] = acc * inv + addv;
       }
   }
   __syncthreads();
@@ -156,6 +161,99 @@ k_roi_align_nhwc(const float *__restrict__ fmap /*[B,Hf,Wf,C]*/, int C, int Hf, 
     const float4 *s4 = reinterpret_cast<const float4 *>(s_out);
     float4 *d4 = reinterpret_cast<float4 *>(dst);
     for (int i = threadIdx.x; i < total / 4; i += blockDim.x) d4[i] = s4[i];
+  } else {
+    for (int i = threadIdx.x; i < total; i += blockDim.x) dst[i] = s_out[i];
+  }
+}
+
+// Same CTA-per-RoI scheme with 16-byte channel-quad fetches: thread = (channel quad q, bin group g); a thread walks
+// the bins g, g + G, ... and for each of the SR x SR samples issues four float4 corner loads (all independent, so
+// up to 16 are in flight per thread).  4x fewer load instructions and 4x the bytes in flight of the scalar kernel;
+// the per-channel arithmetic (and its order) is unchanged.  Needs C % 4 == 0 and C / 4 <= blockDim.x.
+template <int SR>
+__global__ void __launch_bounds__(256)
+k_roi_align_nhwc4(const float *__restrict__ fmap /*[B,Hf,Wf,C]*/, int C, int Hf, int Wf, const float *__restrict__ rois,
+                  int N, const int64_t *__restrict__ ui, int64_t stride, int cs, int co, int E, float scale, int pool,
+                  float *__restrict__ node_out, float *__restrict__ edge_out, int r_begin,
+                  const float *__restrict__ edge_add) {
+  extern __shared__ __align__(16) float s_out[];          // [C][pool*pool]
+  __shared__ int s_lo[2][RA_MAXS], s_hi[2][RA_MAXS];
+  __shared__ float s_l[2][RA_MAXS], s_h[2][RA_MAXS];
+  const int r = r_begin + blockIdx.x;
+  const int pp = pool * pool, ns = pool * SR;
+  float x1, y1, x2, y2; int b;
+  float *dst;
+  if (r < N) {
+    const float *q = rois + (size_t)r * 5;
+    b = (int)q[0]; x1 = q[1]; y1 = q[2]; x2 = q[3]; y2 = q[4];
+    dst = node_out + (size_t)r * C * pp;
+  } else {
+    const size_t e = (size_t)(r - N);
+    const float *qs = rois + (size_t)ui[e * stride + cs] * 5, *qo = rois + (size_t)ui[e * stride + co] * 5;
+    b = (int)qs[0];
+    x1 = fminf(qs[1], qo[1]); y1 = fminf(qs[2], qo[2]); x2 = fmaxf(qs[3], qo[3]); y2 = fmaxf(qs[4], qo[4]);
+    dst = edge_out + e * C * pp;
+  }
+  if (threadIdx.x < 2 * ns) {
+    const int axis = threadIdx.x / ns, i = threadIdx.x % ns;     // axis 0 = y, 1 = x
+    const float start = (axis == 0 ? y1 : x1) * scale;
+    const float len = fmaxf((axis == 0 ? y2 : x2) * scale - start, 1.f);
+    const float bin = len / (float)pool;
+    const int size = axis == 0 ? Hf : Wf;
+    float v = start + (i / SR) * bin + ((i % SR) + 0.5f) * bin / (float)SR;
+    int lo = 0, hi = 0; float l = 0.f, h = 0.f;
+    if (!(v < -1.0f || v > (float)size)) {
+      if (v <= 0.f) v = 0.f;
+      lo = (int)v;
+      if (lo >= size - 1) { hi = lo = size - 1; v = (float)lo; } else hi = lo + 1;
+      l = v - lo; h = 1.f - l;
+    }   // else: sample outside the map contributes 0 — index 0 with both weights 0, so the main loop has no branch
+        // (all 16 corner loads of a bin are issued back to back)
+    s_lo[axis][i] = lo; s_hi[axis][i] = hi; s_l[axis][i] = l; s_h[axis][i] = h;
+  }
+  __syncthreads();
+  const int C4 = C >> 2;
+  const int G = blockDim.x / C4;                           // bin groups working in parallel
+  const int q = threadIdx.x % C4, g = threadIdx.x / C4;
+  const float4 *f4 = reinterpret_cast<const float4 *>(fmap + (size_t)b * Hf * Wf * C) + q;
+  const float inv = 1.f / (float)(SR * SR);
+  if (g < G) {
+    // union-box geometry embedding (lib/get_union_boxes.py:101: union_pools + conv(...), broadcast over the 7x7 bins)
+    const float4 add = (edge_add != nullptr && r >= N)
+                           ? __ldg(reinterpret_cast<const float4 *>(edge_add + (size_t)(r - N) * C) + q)
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int bin = g; bin < pp; bin += G) {
+      const int ph = bin / pool, pw = bin - ph * pool;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int iy = 0; iy < SR; ++iy) {
+        const int sy = ph * SR + iy;
+        const int yl = s_lo[0][sy], yh = s_hi[0][sy];
+        const float ly = s_l[0][sy], hy = s_h[0][sy];
+#pragma unroll
+        for (int ix = 0; ix < SR; ++ix) {
+          const int sx = pw * SR + ix;
+          const int xl = s_lo[1][sx], xh = s_hi[1][sx];
+          const float lx = s_l[1][sx], hx = s_h[1][sx];
+          const float4 v1 = __ldg(f4 + ((size_t)yl * Wf + xl) * C4), v2 = __ldg(f4 + ((size_t)yl * Wf + xh) * C4);
+          const float4 v3 = __ldg(f4 + ((size_t)yh * Wf + xl) * C4), v4 = __ldg(f4 + ((size_t)yh * Wf + xh) * C4);
+          acc.x += hy * hx * v1.x + hy * lx * v2.x + ly * hx * v3.x + ly * lx * v4.x;
+          acc.y += hy * hx * v1.y + hy * lx * v2.y + ly * hx * v3.y + ly * lx * v4.y;
+          acc.z += hy * hx * v1.z + hy * lx * v2.z + ly * hx * v3.z + ly * lx * v4.z;
+          acc.w += hy * hx * v1.w + hy * lx * v2.w + ly * hx * v3.w + ly * lx * v4.w;
+        }
+      }
+      float *so = s_out + (size_t)(4 * q) * pp + bin;
+      so[0] = acc.x * inv + add.x; so[pp] = acc.y * inv + add.y;
+      so[2 * pp] = acc.z * inv + add.z; so[3 * pp] = acc.w * inv + add.w;
+    }
+  }
+  __syncthreads();
+  const int total = C * pp;
+  if ((total & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+    const float4 *s4 = reinterpret_cast<const float4 *>(s_out);
+    float4 *d4 = reinterpret_cast<float4 *>(dst);
+    for (int i = threadIdx.x; i < total / 4; i += blockDim.x) __stcs(d4 + i, s4[i]);
   } else {
     for (int i = threadIdx.x; i < total; i += blockDim.x) dst[i] = s_out[i];
   }
@@ -171,6 +269,16 @@ extern "C" int sgg_node_edge_features(const float *fmap, int B, int C, int Hf, i
                                       const int64_t *union_inds, int64_t row_stride, int col_subj, int col_obj, int E,
                                       float spatial_scale, int pool, int sampling_ratio, float *node_feat,
                                       float *edge_feat, void *ws, size_t ws_bytes, void *stream) {
+  return sgg_node_edge_features_add(fmap, B, C, Hf, Wf, rois, N, union_inds, row_stride, col_subj, col_obj, E,
+                                    spatial_scale, pool, sampling_ratio, nullptr, node_feat, edge_feat, ws, ws_bytes,
+                                    stream);
+}
+
+extern "C" int sgg_node_edge_features_add(const float *fmap, int B, int C, int Hf, int Wf, const float *rois, int N,
+                                          const int64_t *union_inds, int64_t row_stride, int col_subj, int col_obj,
+                                          int E, float spatial_scale, int pool, int sampling_ratio,
+                                          const float *edge_add, float *node_feat, float *edge_feat, void *ws,
+                                          size_t ws_bytes, void *stream) {
   if (B <= 0 || C <= 0 || Hf <= 0 || Wf <= 0 || N < 0 || E < 0 || pool <= 0 || sampling_ratio <= 0)
     return sgg_set_err(SGG_E_BADARG, "node_edge_features: bad shape");
   const int do_node = node_feat != nullptr && N > 0, do_edge = edge_feat != nullptr && E > 0;
@@ -192,9 +300,20 @@ extern "C" int sgg_node_edge_features(const float *fmap, int B, int C, int Hf, i
       attr = true;
     }
     const int r0 = do_node ? 0 : N, r1 = do_edge ? N + E : N;
+    if (sampling_ratio == 2 && (C & 3) == 0 && C / 4 <= 256) {
+      static bool attr4 = false;
+      if (!attr4) {
+        SGG_CUDA_TRY(cudaFuncSetAttribute(sgg::k_roi_align_nhwc4<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr4 = true;
+      }
+      sgg::k_roi_align_nhwc4<2><<<r1 - r0, 256, smem_need, st>>>(nhwc, C, Hf, Wf, rois, N, union_inds, row_stride, col_subj,
+                                                              col_obj, E, spatial_scale, pool, node_feat, edge_feat, r0, edge_add);
+      SGG_RETURN_IF_LAUNCH_FAILED("k_roi_align_nhwc4");
+      return 0;
+    }
     sgg::k_roi_align_nhwc<<<r1 - r0, 256, smem_need, st>>>(nhwc, C, Hf, Wf, rois, N, union_inds, row_stride, col_subj,
                                                           col_obj, E, spatial_scale, pool, sampling_ratio, node_feat,
-                                                          edge_feat, r0);
+                                                          edge_feat, r0, edge_add);
     SGG_RETURN_IF_LAUNCH_FAILED("k_roi_align_nhwc");
     return 0;
   }
@@ -202,7 +321,7 @@ extern "C" int sgg_node_edge_features(const float *fmap, int B, int C, int Hf, i
   int blocks = (int)((total + 255) / 256 < (size_t)sgg_num_sms() * 32 ? (total + 255) / 256 : (size_t)sgg_num_sms() * 32);
   sgg::k_roi_align<<<blocks, 256, 0, (cudaStream_t)stream>>>(fmap, C, Hf, Wf, rois, N, union_inds, row_stride,
                                                              col_subj, col_obj, E, spatial_scale, pool,
-                                                             sampling_ratio, node_feat, edge_feat, do_node, do_edge);
+                                                             sampling_ratio, node_feat, edge_feat, do_node, do_edge, edge_add);
   SGG_RETURN_IF_LAUNCH_FAILED("k_roi_align");
   return 0;
 }

@@ -31,7 +31,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import host
+from . import host, ops
 from . import autograd as K
 from .host import Result, IM_SCALE, BATCHNORM_MOMENTUM
 
@@ -189,12 +189,14 @@ class RelModelBase(nn.Module):
         scales = [2.0 ** round(math.log2(float(fs) / float(os_))) for fs, os_ in ((fmap.shape[-2], mh), (fmap.shape[-1], mw))]
         return scales[0]
 
-    def node_edge_features(self, fmap, rois, union_inds, im_sizes):
-        """rel_model_base.py:245-260: 7x7 RoIAlign features of the objects and of the union box of every pair."""
+    def node_edge_features(self, fmap, rois, union_inds, im_sizes, edge_add=None):
+        """rel_model_base.py:245-260: 7x7 RoIAlign features of the objects and of the union box of every pair.
+        ``edge_add`` [E,C] (internal, eval forward only): geometry embedding folded into the edge rows."""
         assert union_inds.shape[1] == 2, union_inds.shape
         if isinstance(fmap, dict):
             fmap = fmap['0']
-        return K.node_edge_features(fmap, rois, union_inds, self._spatial_scale(fmap, im_sizes), self.pool_sz, 2)
+        return K.node_edge_features(fmap, rois, union_inds, self._spatial_scale(fmap, im_sizes), self.pool_sz, 2,
+                                    edge_add=edge_add)
 
     def get_scaled_boxes(self, boxes, im_inds, im_sizes):
         """rel_model_base.py:263-274: boxes / (w, h, w, h) of their image."""
@@ -248,6 +250,12 @@ class RelModelStanford(RelModelBase):
         """rel_model_stanford.py:97-107."""
         E = edge_feat.shape[0]
         edge_feat = self.union_boxes(edge_feat.view(E, -1, self.pool_sz, self.pool_sz), rois, rel_inds[:, 1:], im_sizes)
+        return self._predict_pooled(node_feat, edge_feat, rel_inds)
+
+    def _predict_pooled(self, node_feat, edge_feat, rel_inds):
+        """rel_model_stanford.py:100-107: everything after ``self.union_boxes`` (edge_feat already carries the
+        union-box geometry)."""
+        E = edge_feat.shape[0]
         fo, fe = self.roi_fmap_obj, self.roi_fmap[1]
         drop = self.training
         n = K.linear(node_feat.reshape(node_feat.shape[0], -1), fo[0].weight, fo[0].bias, relu=True)
@@ -283,10 +291,20 @@ class RelModelStanford(RelModelBase):
         rel_inds = self.get_rel_inds(result.rel_labels if self.training else None, im_inds, boxes)
         result.rel_inds = rel_inds
         rois = torch.cat((im_inds[:, None].float(), boxes), 1)
-        result.node_feat, result.edge_feat = self.node_edge_features(result.fmap, rois, rel_inds[:, 1:],
-                                                                     im_sizes=result.im_sizes)
-        result.rm_obj_dists, result.rel_dists = self.predict(result.node_feat, result.edge_feat, rel_inds,
-                                                             rois=rois, im_sizes=result.im_sizes)
+        ub = self.union_boxes
+        if not self.training and isinstance(ub, UnionBoxesAndFeats) and not ub.concat and ub.use_feats:
+            # eval: nobody reads the raw union-box features (only the train-mode Result exposes them), so the geometry
+            # embedding [E,C] is computed first and added inside the RoIAlign kernel: the [E,C,7,7] tensor is written
+            # once instead of written, re-read and re-written (lib/get_union_boxes.py:101)
+            geom = ops.union_geom(rois, rel_inds[:, 1:], K._conv_params(ub.conv))
+            result.node_feat, result.edge_feat = self.node_edge_features(result.fmap, rois, rel_inds[:, 1:],
+                                                                         im_sizes=result.im_sizes, edge_add=geom)
+            result.rm_obj_dists, result.rel_dists = self._predict_pooled(result.node_feat, result.edge_feat, rel_inds)
+        else:
+            result.node_feat, result.edge_feat = self.node_edge_features(result.fmap, rois, rel_inds[:, 1:],
+                                                                         im_sizes=result.im_sizes)
+            result.rm_obj_dists, result.rel_dists = self.predict(result.node_feat, result.edge_feat, rel_inds,
+                                                                 rois=rois, im_sizes=result.im_sizes)
         if self.use_bias:
             if self.mode == 'predcls':
                 result.obj_preds = gt_classes[:, 1]

@@ -337,19 +337,22 @@ def union_geom(rois, union_inds, params, union_pools=None, prefix='union_boxes.c
 
 
 def node_edge_features(fmap, rois, union_inds, spatial_scale=1.0 / 16, pool=7, sampling_ratio=2,
-                       want_node=True, want_edge=True, fast=True):
-    """RelModelBase.node_edge_features (rel_model_base.py:245-260)."""
+                       want_node=True, want_edge=True, fast=True, edge_add=None):
+    """RelModelBase.node_edge_features (rel_model_base.py:245-260).  ``edge_add`` [E,C] (optional): the union-box
+    geometry embedding, added to every bin of the edge rows in the same kernel (lib/get_union_boxes.py:101)."""
     lib = _lib.load()
     fmap = _f32(fmap, 'fmap'); rois = _f32(rois, 'rois'); ui, stride = _i64_rows(union_inds, 'union_inds')
     B, Cc, Hf, Wf = fmap.shape
     N, E = rois.shape[0], ui.shape[0]
+    if edge_add is not None:
+        edge_add = _f32(edge_add, 'edge_add', (E, Cc))
     node = torch.empty((N, Cc, pool, pool), dtype=torch.float32, device=fmap.device) if want_node else None
     edge = torch.empty((E, Cc, pool, pool), dtype=torch.float32, device=fmap.device) if want_edge else None
     nb = lib.sgg_node_edge_features_workspace_bytes(B, Cc, Hf, Wf) if fast else 0
     ws = torch.empty(nb, dtype=torch.uint8, device=fmap.device) if nb else None
-    check(lib.sgg_node_edge_features(_ptr(fmap), B, Cc, Hf, Wf, _ptr(rois), N, _ptr(ui), stride, 0, 1, E,
-                                     float(spatial_scale), pool, sampling_ratio, _ptr(node), _ptr(edge),
-                                     _ptr(ws), nb, _stream()), 'sgg_node_edge_features')
+    check(lib.sgg_node_edge_features_add(_ptr(fmap), B, Cc, Hf, Wf, _ptr(rois), N, _ptr(ui), stride, 0, 1, E,
+                                         float(spatial_scale), pool, sampling_ratio, _ptr(edge_add), _ptr(node),
+                                         _ptr(edge), _ptr(ws), nb, _stream()), 'sgg_node_edge_features_add')
     return node, edge
 
 

@@ -144,6 +144,11 @@ def test_roi_align_node_and_union(ops):
         nf, ef = ops.node_edge_features(dev(fmap), dev(rois), dev(ui), fast=fast)
         assert np.abs(nf.cpu().numpy() - fx['node_feat']).max() <= 1e-5
         assert np.abs(ef.cpu().numpy() - fx['edge_feat']).max() <= 1e-5
+        # geometry embedding folded into the edge rows (lib/get_union_boxes.py:101): same as adding it afterwards
+        add = torch.randn(ef.shape[0], ef.shape[1], device='cuda', generator=torch.Generator(device='cuda').manual_seed(1))
+        nf2, ef2 = ops.node_edge_features(dev(fmap), dev(rois), dev(ui), fast=fast, edge_add=add)
+        assert torch.equal(nf2, nf)
+        assert float((ef2 - (ef + add[:, :, None, None])).abs().max()) <= 1e-6
 
 
 def test_graph_rejects_out_of_range(ops):
