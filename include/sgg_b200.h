@@ -223,6 +223,21 @@ SGG_API int sgg_node_edge_features_add(const float *fmap, int B, int C, int Hf, 
                                float spatial_scale, int pool, int sampling_ratio, const float *edge_add,
                                float *node_feat, float *edge_feat, void *ws, size_t ws_bytes, void *stream);
 
+/* ==== evaluation tail: lib/surgery.py:17-55 filter_dets ========================================
+ * score[e] = max_{p>=1} prob[e,p] * obj_scores[subj] * obj_scores[obj]; edges are ordered by descending score (ties by
+ * ascending edge id: deterministic, torch.sort in the reference is not) and rels_out [E,2] = (subj, obj) ids,
+ * pred_out [E,P] = probabilities are written in that order.  rel_dists [E,P]: logits when apply_softmax != 0 (the
+ * softmax of rel_model_stanford.py:206 is fused), probabilities otherwise.  col_img >= 0: rel_inds also holds an image
+ * id in that column and the ranking is per image (rows grouped by ascending image id) — batched evaluation; -1: one
+ * image.  score_out [E] / order_out [E] (original row of each output row) are optional. */
+SGG_API size_t sgg_rank_relations_workspace_bytes(int E, int P);
+SGG_API int sgg_rank_relations(const float *rel_dists, int apply_softmax, const float *obj_scores,
+                       const int64_t *rel_inds, int64_t row_stride, int col_img, int col_subj, int col_obj,
+                       int N, int E, int P, int64_t *rels_out, float *pred_out, float *score_out, int *order_out,
+                       void *ws, size_t ws_bytes, void *stream);
+/* host-synchronising: SGG_E_INDEX if an endpoint was outside [0,N) in the last call on this workspace */
+SGG_API int sgg_rank_relations_check(const void *ws, void *stream);
+
 /* ==== training tail: lib/losses.py, lib/pytorch_misc.py grad_clip / get_optim =============== */
 
 /* ---- edge_losses / node_losses: lib/losses.py:5-74 ---------------------------

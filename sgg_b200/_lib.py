@@ -97,6 +97,10 @@ SIGNATURES = {
     'sgg_node_edge_features_add': (C.c_int, [c_f, C.c_int, C.c_int, C.c_int, C.c_int, c_f, C.c_int, c_i64p, C.c_int64,
                                              C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, c_f, c_f, c_f,
                                              C.c_void_p, C.c_size_t, C.c_void_p]),
+    'sgg_rank_relations_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int]),
+    'sgg_rank_relations': (C.c_int, [c_f, C.c_int, c_f, c_i64p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                     C.c_int, c_i64p, c_f, c_f, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    'sgg_rank_relations_check': (C.c_int, [C.c_void_p, C.c_void_p]),
     'sgg_ce_loss_workspace_bytes': (C.c_size_t, [C.c_int]),
     'sgg_ce_loss': (C.c_int, [c_f, c_i64p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float,
                               c_f, c_f, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),

@@ -324,5 +324,6 @@ class RelModelStanford(RelModelBase):
             result.obj_scores, result.obj_preds = sc, idx + 1
         else:
             raise NotImplementedError(self.mode)
-        rel_rep = F.softmax(result.rel_dists, dim=1)
-        return host.filter_dets(result.rm_box_priors_org, result.obj_scores, result.obj_preds, rel_inds[:, 1:], rel_rep)
+        # rel_model_stanford.py:206-207: softmax + filter_dets; the softmax is fused into the ranking kernel
+        return host.filter_dets(result.rm_box_priors_org, result.obj_scores, result.obj_preds, rel_inds[:, 1:],
+                                result.rel_dists.detach(), logits=True)

@@ -356,6 +356,33 @@ def node_edge_features(fmap, rois, union_inds, spatial_scale=1.0 / 16, pool=7, s
     return node, edge
 
 
+def rank_relations(rel_dists, obj_scores, rel_inds, logits=True, per_image=False, validate=False):
+    """Device-side filter_dets core (lib/surgery.py:42-52).  rel_inds: int64 [E,2] (subj, obj) or, with
+    ``per_image``, [E,3] (img, subj, obj) — then every image's edges are ranked separately in one launch.
+    Returns (rels [E,2] int64, pred_scores [E,P] probabilities, scores [E], order [E] int32), all in ranked order."""
+    lib = _lib.load()
+    x = _f32(rel_dists, 'rel_dists'); sc = _f32(obj_scores, 'obj_scores')
+    ri, stride = _i64_rows(rel_inds, 'rel_inds')
+    E, P = x.shape
+    want_cols = 3 if per_image else 2
+    if ri.shape[0] != E or ri.shape[1] != want_cols:
+        raise _lib.SggError('rank_relations: rel_inds %s vs rel_dists %s' % (tuple(ri.shape), tuple(x.shape)))
+    off = 1 if per_image else 0
+    dev = x.device
+    rels = torch.empty((E, 2), dtype=torch.int64, device=dev)
+    pred = torch.empty((E, P), dtype=torch.float32, device=dev)
+    score = torch.empty((E,), dtype=torch.float32, device=dev)
+    order = torch.empty((E,), dtype=torch.int32, device=dev)
+    nb = lib.sgg_rank_relations_workspace_bytes(E, P)
+    ws = torch.empty(nb, dtype=torch.uint8, device=dev)
+    check(lib.sgg_rank_relations(_ptr(x), 1 if logits else 0, _ptr(sc), _ptr(ri), stride, 0 if per_image else -1, off,
+                                 off + 1, sc.shape[0], E, P, _ptr(rels), _ptr(pred), _ptr(score), _ptr(order),
+                                 _ptr(ws), nb, _stream()), 'sgg_rank_relations')
+    if validate and E > 0:
+        check(lib.sgg_rank_relations_check(_ptr(ws), _stream()), 'sgg_rank_relations_check')
+    return rels, pred, score, order
+
+
 # ---- backward entry points -----------------------------------------------------------------------
 def linear_backward(x, weight, dy, need_dx=True, need_dw=True, need_db=True):
     """nn.Linear backward through the C-ABI: returns (dx, dw, db); dy must already carry the ReLU mask."""
