@@ -120,7 +120,7 @@ SGG_API int sgg_linear_forward(const float *x, const float *w, const float *b, f
 
 /* nn.Linear backward.  dy [M,Nout] must already be masked by the ReLU derivative when the forward had
  * relu=1.  dx [M,K] is overwritten (nullable); dw [Nout,K] and db [Nout] are ACCUMULATED into (nullable). */
-SGG_API size_t sgg_linear_backward_workspace_bytes(int M, int Nout);
+SGG_API size_t sgg_linear_backward_workspace_bytes(int M, int Nout, int K);
 SGG_API int sgg_linear_backward(const float *x, const float *w, const float *dy, int M, int Nout, int K,
                         float *dx, float *dw, float *db, void *ws, size_t ws_bytes, void *stream);
 

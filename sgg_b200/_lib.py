@@ -62,7 +62,7 @@ SIGNATURES = {
     'sgg_mp_backward_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     'sgg_mp_backward': (C.c_int, [c_f, c_f, C.c_void_p, C.POINTER(MpWeights), c_f, C.c_int, C.c_int, C.c_int, C.c_int,
                                   c_f, c_f, C.POINTER(MpGrads), c_f, c_f, C.c_void_p, C.c_size_t, C.c_void_p]),
-    'sgg_linear_backward_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int]),
+    'sgg_linear_backward_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     'sgg_linear_backward': (C.c_int, [c_f, c_f, c_f, C.c_int, C.c_int, C.c_int, c_f, c_f, c_f, C.c_void_p, C.c_size_t,
                                       C.c_void_p]),
     'sgg_mp_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),

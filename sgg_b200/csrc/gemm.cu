@@ -175,8 +175,8 @@ __global__ void k_colsum_final(const float *__restrict__ part, int nparts, int c
   out[c] = accumulate ? out[c] + s : s;
 }
 
-static int colsum_parts(int rows) {          // row slices: 32 rows each, at most 256 slices
-  int nparts = (rows + 31) / 32; if (nparts > 256) nparts = 256; if (nparts < 1) nparts = 1;
+static int colsum_parts(int rows) {          // row slices: >= 32 rows each, at most 96 slices (the final stage walks them serially)
+  int nparts = (rows + 31) / 32; if (nparts > 96) nparts = 96; if (nparts < 1) nparts = 1;
   return nparts;
 }
 size_t colsum_workspace_floats(int rows, int cols) { return (size_t)colsum_parts(rows) * cols; }
@@ -242,8 +242,16 @@ int launch_wsum4(const float *W4, const float *X, int rows, int cols, float *out
 }  // namespace sgg
 
 // ---- nn.Linear backward: dx = dy W ; dW += dy^T x ; db += colsum(dy).  dy already masked by ReLU if any. ----
-extern "C" size_t sgg_linear_backward_workspace_bytes(int M, int Nout) {
-  return sgg::colsum_workspace_floats(M, Nout) * sizeof(float) + 256;
+// workspace = column-sum partials (bias gradient) + split-K partials for the weight-gradient GEMM (few output tiles,
+// reduction over all M rows: e.g. rel_fc's [51,512] gradient over 9600 edges occupied 8 CTAs without it)
+static size_t lb_splitk_floats(int M, int Nout, int K) {
+  if (M < 512) return 0;                                   // short reductions are not split (launch_gemm_l: >= 256 per slice)
+  size_t per = (size_t)Nout * K, want = per * 8, cap = (size_t)8 << 20;     // <= 8 slices, <= 32 MB
+  return want < cap ? want : (cap / per) * per;
+}
+extern "C" size_t sgg_linear_backward_workspace_bytes(int M, int Nout, int K) {
+  return sgg_align_up(sgg::colsum_workspace_floats(M, Nout) * sizeof(float)) +
+         sgg_align_up(lb_splitk_floats(M, Nout, K) * sizeof(float)) + 256;
 }
 
 extern "C" int sgg_linear_backward(const float *x, const float *w, const float *dy, int M, int Nout, int K, float *dx,
@@ -251,12 +259,16 @@ extern "C" int sgg_linear_backward(const float *x, const float *w, const float *
   cudaStream_t st = (cudaStream_t)stream;
   int rc;
   if (M < 0 || Nout <= 0 || K <= 0) return sgg_set_err(SGG_E_BADARG, "linear_backward: bad shape");
+  const bool ws_ok = ws != nullptr && ws_bytes >= sgg_linear_backward_workspace_bytes(M, Nout, K);
+  float *cs = (float *)ws;
+  float *sk = ws_ok ? (float *)((char *)ws + sgg_align_up(sgg::colsum_workspace_floats(M, Nout) * sizeof(float))) : nullptr;
+  const size_t sk_floats = ws_ok ? lb_splitk_floats(M, Nout, K) : 0;
   if (dx && (rc = sgg::launch_gemm(dy, Nout, false, w, K, true, dx, K, M, K, Nout, false, st))) return rc;
-  if (dw && (rc = sgg::launch_gemm(dy, Nout, true, x, K, true, dw, K, Nout, K, M, true, st))) return rc;
+  if (dw && (rc = sgg::launch_gemm(dy, Nout, true, x, K, true, dw, K, Nout, K, M, true, st, sk_floats ? sk : nullptr,
+                                   sk_floats))) return rc;
   if (db) {
-    if (!ws || ws_bytes < sgg_linear_backward_workspace_bytes(M, Nout))
-      return sgg_set_err(SGG_E_WORKSPACE, "linear_backward: workspace too small");
-    if ((rc = sgg::launch_colsum(dy, Nout, M, Nout, db, true, (float *)ws, st))) return rc;
+    if (!ws_ok) return sgg_set_err(SGG_E_WORKSPACE, "linear_backward: workspace too small");
+    if ((rc = sgg::launch_colsum(dy, Nout, M, Nout, db, true, cs, st))) return rc;
   }
   return 0;
 }

@@ -394,7 +394,7 @@ def linear_backward(x, weight, dy, need_dx=True, need_dw=True, need_db=True):
     dx = torch.empty((M, K), dtype=torch.float32, device=dev) if need_dx else None
     dw = torch.zeros((Nout, K), dtype=torch.float32, device=dev) if need_dw else None
     db = torch.zeros((Nout,), dtype=torch.float32, device=dev) if need_db else None
-    nbytes = lib.sgg_linear_backward_workspace_bytes(M, Nout)
+    nbytes = lib.sgg_linear_backward_workspace_bytes(M, Nout, K)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
     check(lib.sgg_linear_backward(_ptr(x), _ptr(weight), _ptr(dy), M, Nout, K, _ptr(dx), _ptr(dw), _ptr(db),
                                   _ptr(ws), nbytes, _stream()), 'sgg_linear_backward')

@@ -72,6 +72,7 @@ def ref_step():
         for _, p in named:
             p.grad.data.mul_(coef)
     ref.step()
-res['torch_reference_style'] = {'step_ms': timeit(ref_step, reps=5, warm=2)}
-res['speedup_vs_torch'] = res['torch_reference_style']['step_ms'] / t_step
+if not os.environ.get('OPTIM_BENCH_SKIP_REF'):
+    res['torch_reference_style'] = {'step_ms': timeit(ref_step, reps=5, warm=2)}
+    res['speedup_vs_torch'] = res['torch_reference_style']['step_ms'] / t_step
 print(json.dumps(res))
