@@ -260,3 +260,8 @@ class FrequencyBias(torch.nn.Module):
 
     def index_with_labels(self, labels):
         return self.obj_baseline(labels[:, 0] * self.num_objs + labels[:, 1])
+
+    def forward(self, obj_cands0, obj_cands1):
+        """lib/sparse_targets.py:36-50: expected log-frequency under two class distributions [B,C] -> [B,R]."""
+        joint = obj_cands0[:, :, None] * obj_cands1[:, None]
+        return joint.view(joint.size(0), -1) @ self.obj_baseline.weight
