@@ -130,3 +130,44 @@ def test_frequency_bias_counts_and_lookup():
     out = fb.index_with_labels(torch.tensor([[1, 2], [2, 2]]))
     ref = np.log((np.array([bg[1, 2] + 1, 0, 1, 0]) / (bg[1, 2] + 1 + 1)) + 1e-3)
     assert np.allclose(out[0].detach().numpy(), ref, atol=1e-6)
+
+
+@pytest.mark.skipif(not os.path.exists('/root/reference/lib/pytorch_misc.py'), reason='needs the reference checkout (build container)')
+def test_reference_plumbing_drives_the_drop_in_model(model, tmp_path):
+    """The reference's OWN helpers (lib/pytorch_misc.py: set_mode :76-95, get_optim :130-157, save_checkpoint :214-230,
+    load_checkpoint -> optimistic_restore :160-211), imported from /root/reference and run unmodified on the sgg_b200
+    model class: the drop-in claim of INTEGRATION.md section 1, executed."""
+    import sys, types
+    sys.path.insert(0, '/root/reference')
+    sys.modules.setdefault('h5py', types.ModuleType('h5py'))          # lib/pytorch_misc.py:7 imports it; not installed
+    try:
+        from lib import pytorch_misc as R
+    finally:
+        sys.path.remove('/root/reference')
+    from sgg_b200.model import RelModelStanford
+    from sgg_b200 import optim
+    R.set_mode(model, 'sgcls', is_train=False)
+    assert (model.mode, model.detector.mode, model.training) == ('sgcls', 'gtbox', False)
+    R.set_mode(model, 'sgdet', is_train=True)
+    assert (model.mode, model.detector.mode, model.training) == ('sgdet', 'refinerels', True)
+    R.set_mode(model, 'predcls', is_train=False)
+    conf = types.SimpleNamespace(l2=1e-4, steps=[15], lr_decay=0.1, ckpt='', device='cpu', gan=False, backbone='vgg16',
+                                 mode='predcls')
+    frozen = [p for p in model.detector.parameters() if p.requires_grad]
+    for p in model.detector.parameters():                              # main.py:62-63
+        p.requires_grad = False
+    try:
+        ref_opt, _ = R.get_optim(model, 0.01, conf, -1)                # the reference's grouping on our parameter names
+        ours, _ = optim.get_optim(model, 0.01, conf, -1)
+        assert [len(g['params']) for g in ref_opt.param_groups] == [len(g['params']) for g in ours.param_groups] == [8, 32]
+        assert [g['lr'] for g in ref_opt.param_groups] == [g['lr'] for g in ours.param_groups]
+        path = str(tmp_path / 'vgrel-3.tar')
+        R.save_checkpoint(model, ours, path, {'epoch': 3, 'global_batch_iter': 77})
+        other = RelModelStanford(train_data=FakeData(), mode='predcls')
+        start_epoch, ckpt = R.load_checkpoint(conf, other, path)
+        assert start_epoch == 3 and other.global_batch_iter == 77 and 'optimizer' in ckpt
+        assert all(torch.equal(a, b) for a, b in zip(model.state_dict().values(), other.state_dict().values()))
+        os.remove(path)
+    finally:
+        for p in frozen:
+            p.requires_grad = True
