@@ -5,7 +5,6 @@ behaviour (lib/losses.py:5-74; called from main.py:105-114).  Each call is one C
 row-wise log-softmax, the reference's FG/BG row weighting, the summed loss and d loss / d logits are produced in a
 single pass, so ``backward`` only scales the stored gradient by the incoming scalar.  No CPU path.
 """
-import ctypes as C
 import torch
 
 from . import _lib

@@ -7,7 +7,6 @@ forward + loss (sgg_b200.losses: node CE + 'baseline' edge CE kernels) + CUDA ba
 """
 import json, os, sys, time
 import numpy as np, torch
-import torch.nn.functional as F
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from sgg_b200 import synth, parallel, losses, optim
 from sgg_b200.heads import ImpHeads
