@@ -78,8 +78,9 @@ def get_rel_inds(im_inds, rel_labels=None, training=False, box_priors=None, requ
     if require_overlap:
         same = same & (box_iou(box_priors.float(), box_priors.float()) > 0)
     pairs = same.nonzero()
-    if pairs.numel() == 0:
-        pairs = im_inds.new_zeros((1, 2))
+    # no candidate pair (single-box images): the reference's `rel_cands.dim() == 0` dummy-pair fallback (:160-161) is
+    # torch-0.3 legacy — nonzero() of an all-false mask is [0, 2] on every torch the reference supports — so it returns
+    # an empty [0, 3]; so do we (every kernel accepts E = 0)
     return torch.cat((im_inds[pairs[:, 0]][:, None], pairs), 1)
 
 
