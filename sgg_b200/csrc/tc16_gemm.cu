@@ -27,21 +27,11 @@
 //             of P = V W_ih^T rows, the state read and the state write are fully coalesced.
 // GRU tiles cover hidden units [j0, j0 + NBR) of the r, z, n gates (weight rows j0, H + j0, 2H + j0); NBR is
 // picked per launch from {32, 64, 80} by a wave-quantisation cost model (a ragged last column tile is masked).
-#include <cuda_fp16.h>
 #include <stdlib.h>
-#include "tc_gemm.cuh"
-#include "kernels.h"
+#include "tc16_common.cuh"
 
 namespace sgg {
 namespace tc16 {
-
-constexpr int BM = 128;
-constexpr int BK = 64;                       // fp16 elements per k-block = one 128-byte swizzle span
-constexpr int NTHR = 320;
-constexpr int A_BYTES = BM * BK * 4;         // raw fp32 tile == hi tile + lo tile
-constexpr int A_HALF = A_BYTES / 2;
-constexpr int SMEM_BUDGET = 230000;
-constexpr float LO_SCALE = 2048.0f, LO_INV = 1.0f / 2048.0f;
 
 enum { EPI_LINEAR = 0, EPI_GRU_INIT = 1, EPI_GRU_NODE = 2, EPI_GRU_EDGE = 3 };
 
@@ -82,74 +72,6 @@ struct Cfg {
   static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
   static constexpr int KCB = 256 / BK;                          // k-blocks per accumulation chunk (LINEAR)
 };
-
-__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
-  // c_format = F32 (1) [4,6); a_format = b_format = F16 (0); K-major A and B; N>>3 [17,23); M>>4 [24,29)
-  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-// K-major SWIZZLE_128B tile with 128-byte rows: SBO = 1024 B (8 rows), LBO unused, version 1, layout 2
-__device__ __forceinline__ uint64_t make_sdesc128(const void *smem_tile) {
-  const uint64_t addr = (uint64_t)((tc::smem_u32(smem_tile) & 0x3FFFF) >> 4);
-  return addr | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
-}
-__device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                           uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-__device__ __forceinline__ uint4 lds128u(uint32_t addr) {
-  uint4 v;
-  asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
-  return v;
-}
-__device__ __forceinline__ void sts128u(uint32_t addr, const uint4 &v) {
-  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-// (x0, x1) -> packed fp16 hi pair and packed fp16 scaled-lo pair (x0 in the low half); cvt.rn.f16x2.f32 packs two
-// conversions into one instruction
-__device__ __forceinline__ void split2(float x0, float x1, uint32_t &hi, uint32_t &lo) {
-  const __half2 h = __floats2half2_rn(x0, x1);
-  const float2 hf = __half22float2(h);
-  const __half2 l = __floats2half2_rn((x0 - hf.x) * LO_SCALE, (x1 - hf.y) * LO_SCALE);
-  hi = *reinterpret_cast<const uint32_t *>(&h);
-  lo = *reinterpret_cast<const uint32_t *>(&l);
-}
-
-__device__ __forceinline__ float4 ld4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
-__device__ __forceinline__ float4 ldg4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
-
-// Fast, fp32-grade activations for the epilogue (it is instruction-bound: 3 transcendentals per hidden unit).
-// ex2.approx / rcp.approx carry ~2^-22 relative error => |error| < 3e-7 on sigmoid / tanh values, far inside the
-// 1e-4 parity bar; the accurate expf / tanhf versions cost ~25 instructions each and doubled the epilogue time.
-__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
-__device__ __forceinline__ float fast_tanh(float x) {
-  const float e = __expf(-2.0f * fminf(fmaxf(x, -15.0f), 15.0f));      // clamp: tanh(+-15) == +-1 in fp32, no inf/inf
-  return __fdividef(1.0f - e, 1.0f + e);
-}
-// torch.nn.GRUCell pointwise on 4 hidden units; gi_* / gh_* include the biases
-struct Gru4 { float4 out, r, z, n; };
-__device__ __forceinline__ Gru4 gru4(const float4 &gir, const float4 &ghr, const float4 &giz, const float4 &ghz,
-                                     const float4 &gin, const float4 &ghn, const float4 &h) {
-  Gru4 o;
-  o.r.x = fast_sigmoid(gir.x + ghr.x); o.r.y = fast_sigmoid(gir.y + ghr.y);
-  o.r.z = fast_sigmoid(gir.z + ghr.z); o.r.w = fast_sigmoid(gir.w + ghr.w);
-  o.z.x = fast_sigmoid(giz.x + ghz.x); o.z.y = fast_sigmoid(giz.y + ghz.y);
-  o.z.z = fast_sigmoid(giz.z + ghz.z); o.z.w = fast_sigmoid(giz.w + ghz.w);
-  o.n.x = fast_tanh(gin.x + o.r.x * ghn.x); o.n.y = fast_tanh(gin.y + o.r.y * ghn.y);
-  o.n.z = fast_tanh(gin.z + o.r.z * ghn.z); o.n.w = fast_tanh(gin.w + o.r.w * ghn.w);
-  o.out.x = (1.0f - o.z.x) * o.n.x + o.z.x * h.x; o.out.y = (1.0f - o.z.y) * o.n.y + o.z.y * h.y;
-  o.out.z = (1.0f - o.z.z) * o.n.z + o.z.z * h.z; o.out.w = (1.0f - o.z.w) * o.n.w + o.z.w * h.w;
-  return o;
-}
-__device__ __forceinline__ float4 add4(const float4 &a, const float4 &b) {
-  return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
-}
 
 // NBLK gate blocks of NBR weight rows each (LINEAR: NBLK = 1, NBR = tile width); NSEG K-segments (NODE: 2)
 template <int NBLK, int NBR, int NSEG, int EPI>
@@ -608,40 +530,6 @@ __global__ void k_tc16_streamk_reduce(const float *__restrict__ part, int W, int
 }
 
 // ------------------------------- host side -------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode() {
-  static EncodeTiledFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
-    void *sym = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = (EncodeTiledFn)sym;
-  }
-  return fn;
-}
-
-// row-major [rows, K] of fp32 (elem 4) or fp16 (elem 2) -> boxes of box_rows x 128 bytes, SWIZZLE_128B, zero OOB fill
-static int make_tmap(CUtensorMap *m, const void *base, int rows, int K, int box_rows, int elem) {
-  EncodeTiledFn enc = get_encode();
-  if (!enc) return sgg_set_err(SGG_E_BADARG, "cuTensorMapEncodeTiled unavailable");
-  cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)(rows > 0 ? rows : 1)};
-  cuuint64_t gstr[1] = {(cuuint64_t)K * (cuuint64_t)elem};
-  cuuint32_t box[2] = {(cuuint32_t)(128 / elem), (cuuint32_t)box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(m, elem == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void *)base,
-                   gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS)
-    return sgg_set_err(SGG_E_BADARG, "cuTensorMapEncodeTiled failed (%d) rows=%d K=%d elem=%d", (int)r, rows, K, elem);
-  return 0;
-}
-
 struct Seg { const float *A; const __half *Bhi; const __half *Blo; int brows; };
 
 template <int NBLK, int NBR, int NSEG, int EPI>
@@ -695,6 +583,15 @@ int debug_timing(long long *host_out, int n_ctas) {
 //              of multi-wave GEMMs (E = 9600 edges: 300 tiles = 2.03 waves; fc6: 2400 tiles).
 // The reducer variants pay the partial-sum round trip, the reducer kernel and one more dependent launch.
 struct LinPlan { int ncol, splits, sk_ctas, sk_maxseg; };
+static size_t l2_bytes() {
+  static size_t v = 0;
+  if (v == 0) {
+    int dev = 0, b = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&b, cudaDevAttrL2CacheSize, dev) == cudaSuccess && b > 0) v = (size_t)b;
+    else v = (size_t)126 << 20;
+  }
+  return v;
+}
 static LinPlan plan_linear(int M, int Nout, int K, bool allow_split) {
   const int sms = sgg_num_sms();
   static const double split_fixed = getenv("SGG_TC16_SPLIT_COST") ? atof(getenv("SGG_TC16_SPLIT_COST")) : 3.0;   // tuning knobs
@@ -723,7 +620,12 @@ static LinPlan plan_linear(int M, int Nout, int K, bool allow_split) {
     // stream-K only when plain tiling already needs more than one wave: a GEMM with fewer tiles than SMs usually runs
     // next to other branches of the step (measured at cfg2: giving its 76-tile edge-unary GEMM all 148 SMs made the
     // GEMM 17 % faster and the step 6 % slower, because the object branch no longer overlapped)
-    if (allow_split && allow_sk && (K % 256) == 0 && tiles > sms) {
+    // ... and only while the weight operand stays L2-resident: stream-K hands every CTA a contiguous (tile, chunk) range
+    // that starts at an arbitrary k offset, so concurrently resident CTAs share no operand tiles through L2.  fc6
+    // (9600 x 25088 -> 4096: 411 MB of fp16 [hi|lo] weights) ran 9.32 ms stream-K vs 6.66 ms with plain launch-order
+    // tiling (profiles/r02_fc6_tile_order.md), where a wave walks k in lockstep and reads A and B once per wave.
+    const bool b_resident = 4.0 * (double)Nout * (double)K <= 0.5 * (double)l2_bytes();
+    if (allow_split && allow_sk && b_resident && (K % 256) == 0 && tiles > sms) {
       const long W = tiles * chunks;
       const int G = (int)(W < sms ? W : sms);
       const int q = (int)((W + G - 1) / G);
