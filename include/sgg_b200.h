@@ -124,6 +124,20 @@ SGG_API size_t sgg_linear_backward_workspace_bytes(int M, int Nout, int K);
 SGG_API int sgg_linear_backward(const float *x, const float *w, const float *dy, int M, int Nout, int K,
                         float *dx, float *dw, float *db, void *ws, size_t ws_bytes, void *stream);
 
+/* same; accumulate = 0 overwrites dw / db instead of adding to them (no zero-fill of fresh gradient buffers needed) */
+SGG_API int sgg_linear_backward_ex(const float *x, const float *w, const float *dy, int M, int Nout, int K,
+                           float *dx, float *dw, float *db, int accumulate, void *ws, size_t ws_bytes, void *stream);
+/* Tensor-core building blocks of the nn.Linear backward (3xTF32 engine, fp32 exponent range):
+ * sgg_bwd_transpose: in [R,C] (row stride ldin) -> out [C,Rpad], rows R..Rpad-1 zero; split != 0 writes the engine's
+ * [hi | lo] operand planes (2 * C * Rpad floats).  sgg_tc32_linear_forward = sgg_tc_linear_forward pinned to the 3xTF32
+ * engine (w_split from sgg_bwd_transpose(split = 1) or from sgg_tc_split_weights in mode 0); K % 4 == 0.
+ *   dX = dY W    : y = tc32_linear(x = dY [M,Nout],     w_split = split(W^T) [K,Nout])
+ *   dW = dY^T X  : y = tc32_linear(x = dY^T [Nout,Mp],  w_split = split(X^T) [K,Mp]),  Mp = M rounded up to 32 */
+SGG_API int sgg_bwd_transpose(const float *in, long long ldin, int R, int C, float *out, int Rpad, int split, void *stream);
+SGG_API size_t sgg_tc32_linear_workspace_bytes(int M, int Nout, int K);
+SGG_API int sgg_tc32_linear_forward(const float *x, const float *w_split, const float *b, float *y,
+                            int M, int Nout, int K, int relu, void *ws, size_t ws_bytes, void *stream);
+
 /* ---- tensor-core (tcgen05 / TMEM / TMA) variants -----------------------------------------
  * fp32 in, fp32 out, fp32-grade accuracy through a 3-pass operand split.  Two engines:
  *   mode 0 "3xTF32": x = hi + lo (fp32 words, hi = top 19 bits), kind::tf32;     split buffer = 2n floats
@@ -139,6 +153,8 @@ SGG_API int sgg_tc_get_mode(void);
 /* debug aid: 8 clock64 phase timestamps per CTA of the last 3xFP16 kernel (needs SGG_TC_TIMING=1); host_out holds
  * 8 * n_ctas values; synchronises the device. */
 SGG_API int sgg_tc_debug_timing(long long *host_out, int n_ctas);
+/* same for the last fused message-passing launch (csrc/mp_fused.cu): which = 0 k_mp_gru (launch B / INIT), 1 k_mp_pre (launch A) */
+SGG_API int sgg_mpf_debug_timing(long long *host_out, int n_ctas, int which);
 SGG_API int sgg_tc_split_weights(const float *w, size_t n, float *split, void *stream);
 SGG_API size_t sgg_tc_linear_workspace_bytes(int M, int Nout, int K);   /* split-K partials (0 = none needed) */
 SGG_API int sgg_tc_linear_forward(const float *x, const float *w_split, const float *b, float *y,
@@ -283,6 +299,11 @@ SGG_API int sgg_mt_table_upload(const sgg_mt_tensor *host_table, int n_tensors, 
  * (clip_coef if < 1 else 1; 1 when max_norm <= 0), sum of squares}.  Deterministic (fixed-order partials). */
 SGG_API int sgg_mt_grad_norm(const void *table, int n_tensors, long long total_chunks, float max_norm, float *norm_out,
                      void *ws, size_t ws_bytes, void *stream);
+/* same with a gradient pre-scale: the gradients in memory are the data-parallel SUM and the step means
+ * grad_scale * g (grad_scale = 1 / world): norm_out[0] is the norm of the scaled gradients, norm_out[2] the clip factor
+ * times grad_scale — the factor sgg_mt_sgd_step / sgg_mt_scale_grads apply.  max_norm <= 0: norm_out[2] = grad_scale. */
+SGG_API int sgg_mt_grad_norm_scaled(const void *table, int n_tensors, long long total_chunks, float max_norm,
+                            float grad_scale, float *norm_out, void *ws, size_t ws_bytes, void *stream);
 /* in-place g *= norm[2] (the reference's clip_grad_norm(..., clip=True) side effect) */
 SGG_API int sgg_mt_scale_grads(const void *table, int n_tensors, long long total_chunks, const float *norm, void *stream);
 /* d = g*norm[2] + wd*p; m = first ? d : momentum*m + d; p -= lr*m (+ optional operand split, + optional write-back of

@@ -65,6 +65,12 @@ SIGNATURES = {
     'sgg_linear_backward_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     'sgg_linear_backward': (C.c_int, [c_f, c_f, c_f, C.c_int, C.c_int, C.c_int, c_f, c_f, c_f, C.c_void_p, C.c_size_t,
                                       C.c_void_p]),
+    'sgg_linear_backward_ex': (C.c_int, [c_f, c_f, c_f, C.c_int, C.c_int, C.c_int, c_f, c_f, c_f, C.c_int, C.c_void_p,
+                                         C.c_size_t, C.c_void_p]),
+    'sgg_bwd_transpose': (C.c_int, [c_f, C.c_longlong, C.c_int, C.c_int, c_f, C.c_int, C.c_int, C.c_void_p]),
+    'sgg_tc32_linear_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    'sgg_tc32_linear_forward': (C.c_int, [c_f, c_f, c_f, c_f, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t,
+                                          C.c_void_p]),
     'sgg_mp_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     'sgg_mp_forward': (C.c_int, [c_f, c_f, C.c_void_p, C.POINTER(MpWeights), C.c_int, C.c_int, C.c_int, C.c_int,
                                  c_f, c_f, c_f, C.c_void_p, C.c_size_t, C.c_void_p]),
@@ -72,6 +78,7 @@ SIGNATURES = {
     'sgg_tc_set_mode': (C.c_int, [C.c_int]),
     'sgg_tc_get_mode': (C.c_int, []),
     'sgg_tc_debug_timing': (C.c_int, [C.POINTER(C.c_longlong), C.c_int]),
+    'sgg_mpf_debug_timing': (C.c_int, [C.POINTER(C.c_longlong), C.c_int, C.c_int]),
     'sgg_tc_split_weights': (C.c_int, [c_f, C.c_size_t, c_f, C.c_void_p]),
     'sgg_tc_linear_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     'sgg_tc_linear_forward': (C.c_int, [c_f, c_f, c_f, c_f, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t,
@@ -111,6 +118,8 @@ SIGNATURES = {
     'sgg_mt_table_upload': (C.c_int, [C.POINTER(MtTensor), C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
     'sgg_mt_grad_norm': (C.c_int, [C.c_void_p, C.c_int, C.c_longlong, C.c_float, c_f, C.c_void_p, C.c_size_t,
                                    C.c_void_p]),
+    'sgg_mt_grad_norm_scaled': (C.c_int, [C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_float, c_f, C.c_void_p,
+                                          C.c_size_t, C.c_void_p]),
     'sgg_mt_scale_grads': (C.c_int, [C.c_void_p, C.c_int, C.c_longlong, c_f, C.c_void_p]),
     'sgg_mt_sgd_step': (C.c_int, [C.c_void_p, C.c_int, C.c_longlong, c_f, C.c_float, C.c_int, C.c_void_p]),
 }

@@ -254,9 +254,17 @@ extern "C" size_t sgg_linear_backward_workspace_bytes(int M, int Nout, int K) {
          sgg_align_up(lb_splitk_floats(M, Nout, K) * sizeof(float)) + 256;
 }
 
+extern "C" int sgg_linear_backward_ex(const float *x, const float *w, const float *dy, int M, int Nout, int K, float *dx,
+                                      float *dw, float *db, int accumulate, void *ws, size_t ws_bytes, void *stream);
 extern "C" int sgg_linear_backward(const float *x, const float *w, const float *dy, int M, int Nout, int K, float *dx,
                                    float *dw, float *db, void *ws, size_t ws_bytes, void *stream) {
+  return sgg_linear_backward_ex(x, w, dy, M, Nout, K, dx, dw, db, 1, ws, ws_bytes, stream);
+}
+
+extern "C" int sgg_linear_backward_ex(const float *x, const float *w, const float *dy, int M, int Nout, int K, float *dx,
+                                      float *dw, float *db, int accumulate, void *ws, size_t ws_bytes, void *stream) {
   cudaStream_t st = (cudaStream_t)stream;
+  const bool acc = accumulate != 0;
   int rc;
   if (M < 0 || Nout <= 0 || K <= 0) return sgg_set_err(SGG_E_BADARG, "linear_backward: bad shape");
   const bool ws_ok = ws != nullptr && ws_bytes >= sgg_linear_backward_workspace_bytes(M, Nout, K);
@@ -264,11 +272,34 @@ extern "C" int sgg_linear_backward(const float *x, const float *w, const float *
   float *sk = ws_ok ? (float *)((char *)ws + sgg_align_up(sgg::colsum_workspace_floats(M, Nout) * sizeof(float))) : nullptr;
   const size_t sk_floats = ws_ok ? lb_splitk_floats(M, Nout, K) : 0;
   if (dx && (rc = sgg::launch_gemm(dy, Nout, false, w, K, true, dx, K, M, K, Nout, false, st))) return rc;
-  if (dw && (rc = sgg::launch_gemm(dy, Nout, true, x, K, true, dw, K, Nout, K, M, true, st, sk_floats ? sk : nullptr,
+  if (dw && (rc = sgg::launch_gemm(dy, Nout, true, x, K, true, dw, K, Nout, K, M, acc, st, sk_floats ? sk : nullptr,
                                    sk_floats))) return rc;
   if (db) {
     if (!ws_ok) return sgg_set_err(SGG_E_WORKSPACE, "linear_backward: workspace too small");
-    if ((rc = sgg::launch_colsum(dy, Nout, M, Nout, db, true, cs, st))) return rc;
+    if ((rc = sgg::launch_colsum(dy, Nout, M, Nout, db, acc, cs, st))) return rc;
   }
   return 0;
+}
+
+// ---- tensor-core building blocks of the nn.Linear backward (3xTF32 engine: fp32 exponent range, gradients of any
+// magnitude are safe).  The engine computes y = x w^T with x raw fp32 [M,K] and w pre-split [hi | lo] [Nout,K], so
+//   dX = dY W      -> x = dY,             w = split(W^T)  (sgg_bwd_transpose(W, split = 1), cacheable per weight version)
+//   dW = dY^T X    -> x = dY^T [Nout,Mp], w = split(X^T) [K,Mp], Mp = M padded with zero rows to a multiple of 32
+// composed by sgg_b200.ops.linear_backward (which also chunks dW by output rows so that the gradient all-reduce of one
+// chunk overlaps the GEMM of the next).
+extern "C" int sgg_bwd_transpose(const float *in, long long ldin, int R, int C, float *out, int Rpad, int split, void *stream) {
+  if (!in || !out || R < 0 || C <= 0 || Rpad < R || ldin < C) return sgg_set_err(SGG_E_BADARG, "bwd_transpose: bad argument");
+  if (ldin > 0x7fffffffLL) return sgg_set_err(SGG_E_BADARG, "bwd_transpose: ldin too large");
+  return sgg::launch_transpose_ld(in, (int)ldin, R, C, out, Rpad, split != 0, (cudaStream_t)stream);
+}
+extern "C" size_t sgg_tc32_linear_workspace_bytes(int M, int Nout, int K) {
+  return sgg::tc32_linear_workspace_floats(M, Nout, K) * sizeof(float);
+}
+extern "C" int sgg_tc32_linear_forward(const float *x, const float *w_split, const float *b, float *y, int M, int Nout, int K,
+                                       int relu, void *ws, size_t ws_bytes, void *stream) {
+  if ((M > 0 && Nout > 0) && (!x || !w_split || !y)) return sgg_set_err(SGG_E_BADARG, "tc32_linear: null pointer");
+  if (K % 4) return sgg_set_err(SGG_E_BADARG, "tc32_linear: K %% 4");
+  if (sgg_tc32_linear_workspace_bytes(M, Nout, K) > 0 && (!ws || ws_bytes < sgg_tc32_linear_workspace_bytes(M, Nout, K)))
+    return sgg_set_err(SGG_E_WORKSPACE, "tc32_linear: workspace too small");
+  return sgg::tc32_linear(x, w_split, b, y, M, Nout, K, relu, (float *)ws, (cudaStream_t)stream);
 }

@@ -1,5 +1,6 @@
 // Internal launch helpers shared between translation units.
 #pragma once
+#include <cuda_fp16.h>
 #include "common.cuh"
 namespace sgg {
 cudaStream_t side_stream(cudaStream_t main, int idx = 0);
@@ -19,6 +20,8 @@ int launch_colsum(const float *X, int ld, int rows, int cols, float *out, bool a
 size_t tc32_linear_workspace_floats(int M, int Nout, int K);
 int tc32_linear(const float *x, const float *w_split, const float *b, float *y, int M, int Nout, int K, int relu,
                 float *ws, cudaStream_t st);
+// in [R, C] (row stride ldin) -> out [C, Rpad] (rows R..Rpad-1 zero); split: out = [hi | lo] 3xTF32 planes of C*Rpad floats
+int launch_transpose_ld(const float *in, int ldin, int R, int C, float *out, int Rpad, bool split, cudaStream_t st);
 size_t tc_linear_workspace_floats(int M, int Nout, int K);
 int tc_linear(const float *x, const float *w_split, const float *b, float *y, int M, int Nout, int K, int relu,
               float *ws, cudaStream_t st);
@@ -26,6 +29,24 @@ int tc_linear(const float *x, const float *w_split, const float *b, float *y, in
 int tc_gru(int mode, const float *x, const float *h, const float *w_ih_split, const float *w_hh_split,
            const float *b_ih, const float *b_hh, const float *P, const float *gates, const int *subj, const int *obj,
            float *out, float *cache, int M, int H, cudaStream_t st);
+
+namespace tc16 {
+// LINEAR whose epilogue / reducer also writes the fp16 [hi | lo * 2^11] planes of y (nullable; Nout % 4 == 0)
+int linear_planes(const float *x, const float *w_split, const float *b, float *y, __half *y_hi, __half *y_lo, int M,
+                  int Nout, int K, int relu, float *ws, cudaStream_t st);
+}  // namespace tc16
+// Fused message-passing loop of the 3xFP16 engine (mp_fused.cu): 2 launches per iteration.
+namespace mpf {
+struct Planes { __half *hi, *lo; };
+bool supported(const sgg_mp_weights *w, int N, int E, int H);
+size_t workspace_bytes(int N, int E, int H);
+int forward(const float *obj_rep, const float *rel_rep, const Planes *obj_planes, const Planes *rel_planes,
+            const void *graph_ws, const sgg_mp_weights *w, int N, int E, int H, int T, float *V_out, float *E_out,
+            float *saved, void *ws, size_t ws_bytes, cudaStream_t st, Planes *last_planes = nullptr);
+int heads(const Planes &Vp, const Planes &Ep, const sgg_head_weights *hw, int N, int E, int H, int n_cls, int n_rel,
+          float *obj_dists, float *rel_dists, cudaStream_t st);
+int debug_timing(long long *host_out, int n_ctas, int which);
+}  // namespace mpf
 
 struct MpTape {
   int N, E, H, T;

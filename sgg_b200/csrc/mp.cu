@@ -291,6 +291,7 @@ static int launch_gru(const GruArgs &a, cudaStream_t st) {
 
 struct MpScratch {
   float *V[2], *Eh[2], *P, *a, *g, *ctx, *lin_ws;
+  void *fused; size_t fused_bytes;        // mp_fused.cu scratch (3xFP16 engine)
 };
 
 static size_t mp_layout(MpScratch *s, void *ws, int N, int E, int H) {
@@ -302,6 +303,8 @@ static size_t mp_layout(MpScratch *s, void *ws, int N, int E, int H) {
   s->g = ar.take<float>(e1 * 4);
   s->ctx = ar.take<float>(n1 * H);
   s->lin_ws = ar.take<float>(tc_linear_workspace_floats(N, 3 * H, H) + 4);   // split-K partials of P = V W_ih^T
+  s->fused_bytes = mpf::workspace_bytes(N, E, H);
+  s->fused = ar.take<char>(s->fused_bytes);
   return ar.off;
 }
 
@@ -328,7 +331,8 @@ MpTape mp_tape_view(float *base, int N, int E, int H, int T) {
 // stream (L1 entry) so the node-side initial step may start there immediately.
 int mp_forward(const float *obj_rep, const float *rel_rep, const void *graph_ws, const sgg_mp_weights *w, int N,
                int E, int H, int T, float *V_out, float *E_out, float *saved, void *ws, size_t ws_bytes,
-               cudaStream_t st, bool obj_on_side) {
+               cudaStream_t st, bool obj_on_side, const mpf::Planes *obj_planes = nullptr,
+               const mpf::Planes *rel_planes = nullptr, mpf::Planes *last_planes = nullptr) {
   if (N < 0 || E < 0 || T < 0 || H <= 0 || (H % BN) != 0)
     return sgg_set_err(SGG_E_BADARG, "mp_forward: N=%d E=%d H=%d T=%d (H must be a multiple of %d)", N, E, H, T, BN);
   if (!w || !graph_ws || (N > 0 && (!obj_rep || !V_out)) || (E > 0 && (!rel_rep || !E_out)))
@@ -336,6 +340,16 @@ int mp_forward(const float *obj_rep, const float *rel_rep, const void *graph_ws,
   MpScratch s;
   const size_t need = mp_layout(&s, ws, N, E, H);
   if (need > ws_bytes || !ws) return sgg_set_err(SGG_E_WORKSPACE, "mp_forward: workspace %zu < %zu", ws_bytes, need);
+  if (mpf::supported(w, N, E, H)) {
+    // 3xFP16 engine: fused loop on ONE stream (2 launches per iteration, mp_fused.cu); join the object branch first
+    if (obj_on_side) {
+      cudaStream_t sb0 = side_stream(st, 0);
+      int rc0;
+      if (sb0 != nullptr && (rc0 = stream_order(sb0, st))) return rc0;
+    }
+    return mpf::forward(obj_rep, rel_rep, obj_planes, rel_planes, graph_ws, w, N, E, H, T, V_out, E_out, saved, s.fused,
+                        s.fused_bytes, st, last_planes);
+  }
   SggGraphView g = sgg_graph_view(graph_ws, N, E);
   const size_t vN = (size_t)N * H, eN = (size_t)E * H;
   MpTape tape = mp_tape_view(saved, N, E, H, T);
@@ -476,12 +490,17 @@ extern "C" int sgg_mp_forward(const float *obj_rep, const float *rel_rep, const 
 
 // ---- L1: 4096-d features -> dists (rel_model_stanford.py:103-107 without roi_fmap*) ----
 namespace sgg {
-struct L1Scratch { float *obj_rep, *rel_rep, *V, *Eh, *ws_obj, *ws_edge; void *mp; size_t mp_bytes; };
+struct L1Scratch {
+  float *obj_rep, *rel_rep, *V, *Eh, *ws_obj, *ws_edge; void *mp; size_t mp_bytes;
+  mpf::Planes obj_pl, rel_pl;             // fp16 [hi | lo] planes of the unary outputs (fused message passing)
+};
 static size_t l1_layout(L1Scratch *s, void *ws, int N, int E, int H, int D = 4096, int n_cls = 151, int n_rel = 51) {
   SggArena ar(ws, (size_t)-1);
   const size_t n1 = N > 0 ? N : 1, e1 = E > 0 ? E : 1;
   s->obj_rep = ar.take<float>(n1 * H); s->rel_rep = ar.take<float>(e1 * H);
   s->V = ar.take<float>(n1 * H); s->Eh = ar.take<float>(e1 * H);
+  s->obj_pl.hi = ar.take<__half>(n1 * H); s->obj_pl.lo = ar.take<__half>(n1 * H);
+  s->rel_pl.hi = ar.take<__half>(e1 * H); s->rel_pl.lo = ar.take<__half>(e1 * H);
   const size_t o1 = tc_linear_workspace_floats(N, H, D), o2 = tc_linear_workspace_floats(N, n_cls, H);
   const size_t e1w = tc_linear_workspace_floats(E, H, D), e2w = tc_linear_workspace_floats(E, n_rel, H);
   s->ws_obj = ar.take<float>((o1 > o2 ? o1 : o2) + 4);      // object-branch and edge-branch linears may overlap
@@ -521,10 +540,24 @@ static int l1_forward_impl(const float *obj_feat, const float *edge_feat, const 
   // graph index on the object-branch stream: it overlaps the edge-unary GEMM; every consumer is either on that
   // stream (k_ctx) or behind the iteration-0 join of mp_forward (gates, edge GRU)
   if (rel_inds && (rc = sgg_graph_build(rel_inds, row_stride, col_subj, col_obj, N, E, graph_ws, graph_ws_bytes, sn))) return rc;
-  if ((rc = lin(obj_feat, hw->obj_unary_w, hw->obj_unary_w_split, hw->obj_unary_b, s.obj_rep, N, H, D, 0, s.ws_obj, sn))) return rc;
-  if ((rc = lin(edge_feat, hw->edge_unary_w, hw->edge_unary_w_split, hw->edge_unary_b, s.rel_rep, E, H, D, 1, s.ws_edge, st))) return rc;
-  if ((rc = sgg::mp_forward(s.obj_rep, s.rel_rep, graph_ws, w, N, E, H, T, s.V, s.Eh, nullptr, s.mp, s.mp_bytes, st, par)))
+  // fused message passing (3xFP16): the unary epilogues also emit the fp16 operand planes the INIT launch reads via TMA
+  const bool planes = sgg::mpf::supported(w, N, E, H) && hw->obj_unary_w_split && hw->edge_unary_w_split && (D % 8) == 0;
+  if (planes) {
+    if ((rc = sgg::tc16::linear_planes(obj_feat, hw->obj_unary_w_split, hw->obj_unary_b, s.obj_rep, s.obj_pl.hi, s.obj_pl.lo,
+                                       N, H, D, 0, s.ws_obj, sn))) return rc;
+    if ((rc = sgg::tc16::linear_planes(edge_feat, hw->edge_unary_w_split, hw->edge_unary_b, s.rel_rep, s.rel_pl.hi,
+                                       s.rel_pl.lo, E, H, D, 1, s.ws_edge, st))) return rc;
+  } else {
+    if ((rc = lin(obj_feat, hw->obj_unary_w, hw->obj_unary_w_split, hw->obj_unary_b, s.obj_rep, N, H, D, 0, s.ws_obj, sn))) return rc;
+    if ((rc = lin(edge_feat, hw->edge_unary_w, hw->edge_unary_w_split, hw->edge_unary_b, s.rel_rep, E, H, D, 1, s.ws_edge, st))) return rc;
+  }
+  // ... and the classifier heads read the final states through planes emitted by the last GRU launch: one launch
+  const bool fheads = planes && hw->obj_fc_w_split && hw->rel_fc_w_split;
+  sgg::mpf::Planes lastp[2];
+  if ((rc = sgg::mp_forward(s.obj_rep, s.rel_rep, graph_ws, w, N, E, H, T, s.V, s.Eh, nullptr, s.mp, s.mp_bytes, st, par,
+                            planes ? &s.obj_pl : nullptr, planes ? &s.rel_pl : nullptr, fheads ? lastp : nullptr)))
     return rc;
+  if (fheads) return sgg::mpf::heads(lastp[0], lastp[1], hw, N, E, H, n_cls, n_rel, obj_dists, rel_dists, st);
   // heads: mp_forward joined the side stream into `st`; fork again for the two classifiers
   if (par && (rc = sgg::stream_order(st, sb))) return rc;
   if ((rc = lin(s.V, hw->obj_fc_w, hw->obj_fc_w_split, hw->obj_fc_b, obj_dists, N, n_cls, H, 0, s.ws_obj, sn))) return rc;

@@ -162,13 +162,13 @@ __global__ void k_gate_grad_finish(const float *__restrict__ tV, const float *__
 //   dW += dY^T X     -> x = dY^T [3H,Mp],  w = split(X^T) [H,Mp], Mp = M padded with zero rows to a multiple of 32
 // Transposes go through 32x32 shared-memory tiles (coalesced both ways); rows in [R, Rpad) are written as zeros.
 template <bool SPLIT>
-__global__ void __launch_bounds__(256) k_transpose32(const float *__restrict__ in, int R, int C, float *__restrict__ hi,
-                                                     float *__restrict__ lo, int Rpad) {
+__global__ void __launch_bounds__(256) k_transpose32(const float *__restrict__ in, int ldin, int R, int C,
+                                                     float *__restrict__ hi, float *__restrict__ lo, int Rpad) {
   __shared__ float tile[32][33];
   const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   for (int i = threadIdx.y; i < 32; i += 8) {
     const int r = r0 + i, c = c0 + threadIdx.x;
-    tile[i][threadIdx.x] = (r < R && c < C) ? in[(size_t)r * C + c] : 0.f;
+    tile[i][threadIdx.x] = (r < R && c < C) ? in[(size_t)r * ldin + c] : 0.f;
   }
   __syncthreads();
   for (int i = threadIdx.y; i < 32; i += 8) {
@@ -186,12 +186,16 @@ __global__ void __launch_bounds__(256) k_transpose32(const float *__restrict__ i
   }
 }
 // in [R,C] row-major -> out [C,Rpad]; split = true writes [hi | lo] planes of C*Rpad floats each
-static int launch_transpose(const float *in, int R, int C, float *out, int Rpad, bool split, cudaStream_t st) {
+int launch_transpose_ld(const float *in, int ldin, int R, int C, float *out, int Rpad, bool split, cudaStream_t st) {
   dim3 grid((Rpad + 31) / 32, (C + 31) / 32);
-  if (split) k_transpose32<true><<<grid, dim3(32, 8), 0, st>>>(in, R, C, out, out + (size_t)C * Rpad, Rpad);
-  else k_transpose32<false><<<grid, dim3(32, 8), 0, st>>>(in, R, C, out, nullptr, Rpad);
+  if (grid.y > 65535) return sgg_set_err(SGG_E_BADARG, "transpose: too many columns");
+  if (split) k_transpose32<true><<<grid, dim3(32, 8), 0, st>>>(in, ldin, R, C, out, out + (size_t)C * Rpad, Rpad);
+  else k_transpose32<false><<<grid, dim3(32, 8), 0, st>>>(in, ldin, R, C, out, nullptr, Rpad);
   SGG_RETURN_IF_LAUNCH_FAILED("k_transpose32");
   return 0;
+}
+static int launch_transpose(const float *in, int R, int C, float *out, int Rpad, bool split, cudaStream_t st) {
+  return launch_transpose_ld(in, C, R, C, out, Rpad, split, st);
 }
 __global__ void k_add_inplace(float *__restrict__ c, const float *__restrict__ t, size_t n4) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {

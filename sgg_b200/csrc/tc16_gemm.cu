@@ -43,6 +43,7 @@ struct Params {
   // + segment) and k_tc16_streamk_reduce sums them in CTA order.  sk_C = chunks per tile, sk_ct = column tiles.
   int sk_W, sk_C, sk_ct, sk_maxseg;
   float *sk_part;
+  int pf;                     // LINEAR: k-blocks of L2 prefetch distance for the streamed A operand (0 = off)
   const float *bias;          // LINEAR
   float *out;                 // LINEAR: [M,Nout] (or partials [splits,M,Nout]); GRU: [M,H]
   const float *b_ih, *b_hh;   // GRU
@@ -51,6 +52,7 @@ struct Params {
   const float *gates;         // GRU_EDGE: [M,4]
   const int *subj, *obj;      // GRU_EDGE
   float *cache;               // GRU: nullable [M,4,H] (r, z, n, gh_n) for the backward pass
+  __half *out_hi, *out_lo;    // LINEAR: nullable fp16 planes [hi | lo * 2^11] of the final output (consumed via TMA by mp_fused.cu)
   long long *dbg;             // nullable: per-CTA phase timestamps (SGG_TC_TIMING=1, tools/tc16_phases.py)
 };
 
@@ -158,6 +160,10 @@ k_tc16(Params p, const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         const CUtensorMap *tbl = (NSEG > 1 && seg == 1) ? &tmBl1 : &tmBl0;
         tma_load_2d(st, ta, full + s, k0, am0);                      // fp32 k0 .. k0+31
         tma_load_2d(st + A_HALF, ta, full + s, k0 + 32, am0);        // fp32 k0+32 .. k0+63
+        if (CHUNKED && !SK && p.pf > 0 && it + p.pf < total) {       // A comes from HBM (16 KB / row): pull it into L2 early
+          tma_prefetch_2d(ta, k0 + p.pf * BK, am0);
+          tma_prefetch_2d(ta, k0 + p.pf * BK + 32, am0);
+        }
 #pragma unroll
         for (int b = 0; b < NBLK; ++b) {
           const int row = CHUNKED ? bj0 : (b * p.H + j0);
@@ -292,11 +298,15 @@ k_tc16(Params p, const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       }
       ++sk_seg;
     };
+    // Chunk ch is drained while the LAST k-block of chunk ch+1 is being consumed (not right after its own last k-block:
+    // the converters run up to STAGES k-blocks ahead of the MMA issuer, so an early drain made them wait for the tensor
+    // pipe and then starved it — the ring emptied once per chunk).  The MMA issuer needs the buffer back one k-block later.
+    int next_drain = 0;
     for (int it = 0; it < total; ++it) {
       convert(it);
-      if (it > 0 && (it % KCB) == 0) { drain(it / KCB - 1); sk_flush(it / KCB - 1); }
+      if ((it % KCB) == KCB - 1 && it / KCB >= 1) { drain(next_drain); sk_flush(next_drain); ++next_drain; }
     }
-    if (total > 0) { drain(nchunks - 1); sk_flush(nchunks - 1); }
+    for (; next_drain < nchunks; ++next_drain) { drain(next_drain); sk_flush(next_drain); }
     if (!SK && m < p.M) {
       const bool partial = gridDim.z > 1;        // split-K: raw partial sums, bias/ReLU applied by the reducer
       const bool vec = (p.Nout & 3) == 0;
@@ -316,6 +326,13 @@ k_tc16(Params p, const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           }
           if (vec && j + 4 <= p.Nout) {
             *reinterpret_cast<float4 *>(yrow + j) = make_float4(v[0], v[1], v[2], v[3]);
+            if (!partial && p.out_hi != nullptr) {
+              uint2 hi, lo;
+              split2(v[0], v[1], hi.x, lo.x);
+              split2(v[2], v[3], hi.y, lo.y);
+              *reinterpret_cast<uint2 *>(p.out_hi + (size_t)m * p.Nout + j) = hi;
+              *reinterpret_cast<uint2 *>(p.out_lo + (size_t)m * p.Nout + j) = lo;
+            }
           } else {
 #pragma unroll
             for (int cc = 0; cc < 4; ++cc) if (j + cc < p.Nout) yrow[j + cc] = v[cc];
@@ -483,13 +500,19 @@ __global__ void __launch_bounds__(256) k_tc16_split(const float *__restrict__ w,
 
 // split-K reducer: y = act(sum_z part[z] + bias), fixed summation order
 __global__ void k_tc16_splitk_reduce(const float *__restrict__ part, int splits, size_t mn, int Nout,
-                                     const float *__restrict__ bias, int relu, float *__restrict__ y) {
+                                     const float *__restrict__ bias, int relu, float *__restrict__ y,
+                                     __half *__restrict__ y_hi, __half *__restrict__ y_lo) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < mn; i += (size_t)gridDim.x * blockDim.x) {
     float s = 0.f;
     for (int z = 0; z < splits; ++z) s += part[(size_t)z * mn + i];
     if (bias != nullptr) s += __ldg(bias + (int)(i % Nout));
     if (relu) s = fmaxf(s, 0.f);
     y[i] = s;
+    if (y_hi != nullptr) {
+      const __half h = __float2half_rn(s);
+      y_hi[i] = h;
+      y_lo[i] = __float2half_rn((s - __half2float(h)) * LO_SCALE);
+    }
   }
 }
 
@@ -498,7 +521,7 @@ __global__ void k_tc16_splitk_reduce(const float *__restrict__ part, int splits,
 // Partition arithmetic mirrors k_tc16 (lo_c = c*W/G).
 __global__ void k_tc16_streamk_reduce(const float *__restrict__ part, int W, int C, int G, int maxseg, int col_tiles,
                                       int ncol, int M, int Nout, const float *__restrict__ bias, int relu,
-                                      float *__restrict__ y) {
+                                      float *__restrict__ y, __half *__restrict__ y_hi, __half *__restrict__ y_lo) {
   const int t = blockIdx.x;
   const long long a = (long long)t * C, b = a + C;
   const int c_first = (int)(((a + 1) * G + W - 1) / W) - 1;
@@ -523,6 +546,13 @@ __global__ void k_tc16_streamk_reduce(const float *__restrict__ part, int W, int
   float *yp = y + (size_t)m * Nout + j;
   if ((Nout & 3) == 0 && j + 4 <= Nout) {
     *reinterpret_cast<float4 *>(yp) = make_float4(o[0], o[1], o[2], o[3]);
+    if (y_hi != nullptr) {
+      uint2 hi, lo;
+      split2(o[0], o[1], hi.x, lo.x);
+      split2(o[2], o[3], hi.y, lo.y);
+      *reinterpret_cast<uint2 *>(y_hi + (size_t)m * Nout + j) = hi;
+      *reinterpret_cast<uint2 *>(y_lo + (size_t)m * Nout + j) = lo;
+    }
   } else {
 #pragma unroll
     for (int k = 0; k < 4; ++k) if (j + k < Nout) yp[k] = o[k];
@@ -637,6 +667,9 @@ static LinPlan plan_linear(int M, int Nout, int K, bool allow_split) {
   return best;
 }
 
+int linear_planes(const float *x, const float *w_split, const float *b, float *y, __half *y_hi, __half *y_lo, int M,
+                  int Nout, int K, int relu, float *ws, cudaStream_t st);
+
 size_t linear_workspace_floats(int M, int Nout, int K) {
   if (M <= 0 || Nout <= 0) return 0;
   const LinPlan pl = plan_linear(M, Nout, K, true);
@@ -646,13 +679,24 @@ size_t linear_workspace_floats(int M, int Nout, int K) {
 
 int linear(const float *x, const float *w_split, const float *b, float *y, int M, int Nout, int K, int relu, float *ws,
            cudaStream_t st) {
+  return linear_planes(x, w_split, b, y, nullptr, nullptr, M, Nout, K, relu, ws, st);
+}
+
+// same, and the epilogue (or the split-K / stream-K reducer) also writes the fp16 [hi | lo * 2^11] planes of y
+// (Nout % 4 == 0 required when planes are requested)
+int linear_planes(const float *x, const float *w_split, const float *b, float *y, __half *y_hi, __half *y_lo, int M,
+                  int Nout, int K, int relu, float *ws, cudaStream_t st) {
   if (M <= 0 || Nout <= 0) return 0;
+  if (y_hi != nullptr && (Nout & 3)) return sgg_set_err(SGG_E_BADARG, "tc16 linear: planes need Nout %% 4 == 0");
   if ((K & 7) || !ok16(x) || !ok16(w_split)) return sgg_set_err(SGG_E_BADARG, "tc16 linear: K %% 8 / alignment");
   const LinPlan pl = plan_linear(M, Nout, K, ws != nullptr);
   const int kblocks = (K + BK - 1) / BK, kcb = 256 / BK;
   const __half *wh = reinterpret_cast<const __half *>(w_split);
   Seg sg[2] = {{x, wh, wh + (size_t)Nout * K, Nout}, {}};
   Params p{}; p.M = M; p.K = K; p.Nout = Nout; p.relu = relu; p.bias = b; p.dbg = dbg_ptr();
+  p.out_hi = y_hi; p.out_lo = y_lo;
+  static const int pf_env = getenv("SGG_TC16_PF") ? atoi(getenv("SGG_TC16_PF")) : 8;
+  p.pf = kblocks >= 32 ? pf_env : 0;
   int rc;
   if (pl.sk_ctas > 0) {
     const int col_tiles = (Nout + pl.ncol - 1) / pl.ncol, rows = (M + BM - 1) / BM;
@@ -664,7 +708,7 @@ int linear(const float *x, const float *w_split, const float *b, float *y, int M
     if (rc) return rc;
     const int rows_per_cta = 256 / (pl.ncol / 4);
     k_tc16_streamk_reduce<<<dim3(col_tiles * rows, BM / rows_per_cta), 256, 0, st>>>(
-        ws, p.sk_W, p.sk_C, pl.sk_ctas, pl.sk_maxseg, col_tiles, pl.ncol, M, Nout, b, relu, y);
+        ws, p.sk_W, p.sk_C, pl.sk_ctas, pl.sk_maxseg, col_tiles, pl.ncol, M, Nout, b, relu, y, y_hi, y_lo);
     SGG_RETURN_IF_LAUNCH_FAILED("k_tc16_streamk_reduce");
     return 0;
   }
@@ -683,7 +727,7 @@ int linear(const float *x, const float *w_split, const float *b, float *y, int M
   if (splits > 1) {
     const size_t mn = (size_t)M * Nout;
     int blocks = (int)((mn + 255) / 256 < 2048 ? (mn + 255) / 256 : 2048);
-    k_tc16_splitk_reduce<<<blocks, 256, 0, st>>>(ws, splits, mn, Nout, b, relu, y);
+    k_tc16_splitk_reduce<<<blocks, 256, 0, st>>>(ws, splits, mn, Nout, b, relu, y, y_hi, y_lo);
     SGG_RETURN_IF_LAUNCH_FAILED("k_tc16_splitk_reduce");
   }
   return 0;

@@ -90,3 +90,10 @@ extern "C" int sgg_tc_debug_timing(long long *host_out, int n_ctas) {
   if (e != cudaSuccess) return sgg_set_err((int)e, "tc_debug_timing: %s", cudaGetErrorString(e));
   return sgg::tc16::debug_timing(host_out, n_ctas);
 }
+
+extern "C" int sgg_mpf_debug_timing(long long *host_out, int n_ctas, int which) {
+  if (!host_out || n_ctas <= 0) return sgg_set_err(SGG_E_BADARG, "mpf_debug_timing: bad argument");
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) return sgg_set_err((int)e, "mpf_debug_timing: %s", cudaGetErrorString(e));
+  return sgg::mpf::debug_timing(host_out, n_ctas, which);
+}

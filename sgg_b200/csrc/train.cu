@@ -98,8 +98,10 @@ __global__ void __launch_bounds__(NT) k_mt_sqnorm(const void *__restrict__ table
 
 // fixed-order reduction of the partials -> norm_out = {total_norm, clip_coef, scale actually applied, sum of squares}
 // (lib/pytorch_misc.py:651-653: clip_coef = max_norm / (total_norm + 1e-6), applied only when < 1)
+// grad_scale: the gradients in memory are grad_scale^-1 times the ones the step means (data-parallel SUM instead of
+// the average): total_norm and the clip factor are those of the scaled gradients, and the applied scale includes it.
 __global__ void __launch_bounds__(1024) k_mt_norm_finish(const float *__restrict__ partials, int total_chunks,
-                                                          float max_norm, float *__restrict__ norm_out) {
+                                                          float max_norm, float grad_scale, float *__restrict__ norm_out) {
   __shared__ double shd[32];
   double s = 0.0;
   for (int i = threadIdx.x; i < total_chunks; i += 1024) s += (double)partials[i];
@@ -112,11 +114,11 @@ __global__ void __launch_bounds__(1024) k_mt_norm_finish(const float *__restrict
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
     if (threadIdx.x == 0) {
-      const float tn = (float)sqrt(r);
+      const float tn = (float)sqrt(r) * grad_scale;
       const float coef = max_norm > 0.f ? max_norm / (tn + 1e-6f) : 1.f;
       norm_out[0] = tn;
       norm_out[1] = coef;
-      norm_out[2] = (max_norm > 0.f && coef < 1.f) ? coef : 1.f;
+      norm_out[2] = ((max_norm > 0.f && coef < 1.f) ? coef : 1.f) * grad_scale;
       norm_out[3] = (float)r;
     }
   }
@@ -391,8 +393,14 @@ extern "C" int sgg_mt_table_upload(const sgg_mt_tensor *host, int n_tensors, voi
   return 0;
 }
 
+extern "C" int sgg_mt_grad_norm_scaled(const void *table, int n_tensors, long long total_chunks, float max_norm,
+                                       float grad_scale, float *norm_out, void *ws, size_t ws_bytes, void *stream);
 extern "C" int sgg_mt_grad_norm(const void *table, int n_tensors, long long total_chunks, float max_norm,
                                 float *norm_out, void *ws, size_t ws_bytes, void *stream) {
+  return sgg_mt_grad_norm_scaled(table, n_tensors, total_chunks, max_norm, 1.0f, norm_out, ws, ws_bytes, stream);
+}
+extern "C" int sgg_mt_grad_norm_scaled(const void *table, int n_tensors, long long total_chunks, float max_norm,
+                                       float grad_scale, float *norm_out, void *ws, size_t ws_bytes, void *stream) {
   if (!table || !norm_out || !ws || n_tensors <= 0 || n_tensors > MAX_TENSORS)
     return sgg_set_err(SGG_E_BADARG, "mt_grad_norm: bad argument");
   if (ws_bytes < sgg_mt_workspace_bytes(total_chunks)) return sgg_set_err(SGG_E_WORKSPACE, "mt_grad_norm: workspace too small");
@@ -401,7 +409,7 @@ extern "C" int sgg_mt_grad_norm(const void *table, int n_tensors, long long tota
     k_mt_sqnorm<<<grid_for((int)total_chunks, 8), NT, 0, st>>>(table, n_tensors, (int)total_chunks, (float *)ws);
     SGG_RETURN_IF_LAUNCH_FAILED("k_mt_sqnorm");
   }
-  k_mt_norm_finish<<<1, 1024, 0, st>>>((const float *)ws, (int)total_chunks, max_norm, norm_out);
+  k_mt_norm_finish<<<1, 1024, 0, st>>>((const float *)ws, (int)total_chunks, max_norm, grad_scale, norm_out);
   SGG_RETURN_IF_LAUNCH_FAILED("k_mt_norm_finish");
   return 0;
 }

@@ -384,20 +384,107 @@ def rank_relations(rel_dists, obj_scores, rel_inds, logits=True, per_image=False
 
 
 # ---- backward entry points -----------------------------------------------------------------------
-def linear_backward(x, weight, dy, need_dx=True, need_dw=True, need_db=True):
-    """nn.Linear backward through the C-ABI: returns (dx, dw, db); dy must already carry the ReLU mask."""
+# Gradient sinks: a data-parallel reducer (sgg_b200.parallel.FlatGradReducer) registers, per weight matrix, the view of
+# its flat gradient buffer the weight gradient should be written INTO (no separate dW tensor, no copy) together with the
+# row chunks it all-reduces separately; linear_backward then produces dW chunk by chunk and notifies after each one.
+_GRAD_SINKS = {}
+
+
+def register_grad_sink(param, view, chunks, notify, owner=None):
+    _GRAD_SINKS[param.data_ptr()] = (weakref.ref(param), view, chunks, notify, owner)
+
+
+def clear_grad_sinks(owner=None):
+    for k in [k for k, v in _GRAD_SINKS.items() if owner is None or v[4] is owner]:
+        del _GRAD_SINKS[k]
+
+
+def grad_sink(weight):
+    hit = _GRAD_SINKS.get(weight.data_ptr())
+    if hit is None:
+        return None
+    p = hit[0]()
+    if p is None or tuple(p.shape) != tuple(weight.shape):
+        return None
+    return hit
+
+
+_TC_BWD = {'min_rows': 256, 'min_red': 1024, 'enabled': True}      # below these the SIMT tiles (split-K) are faster
+
+
+def _pad32(n):
+    return (n + 31) // 32 * 32
+
+
+def _transpose(inp, R, C, ldin, Rpad, split):
+    """inp [R, C] (row stride ldin) -> [C, Rpad] (zero rows beyond R); split: 3xTF32 [hi | lo] planes [2, C, Rpad]."""
     lib = _lib.load()
-    x = _f32(x, 'x'); weight = _f32(weight, 'weight'); dy = _f32(dy, 'dy')
+    out = torch.empty(((2, C, Rpad) if split else (C, Rpad)), dtype=torch.float32, device=inp.device)
+    check(lib.sgg_bwd_transpose(_ptr(inp), ldin, R, C, _ptr(out), Rpad, 1 if split else 0, _stream()), 'sgg_bwd_transpose')
+    return out
+
+
+def _tc32_linear(x, w_split, M, Nout, K, out=None):
+    """y [M, Nout] = x [M, K] @ w^T on the 3xTF32 tcgen05 engine (fp32 exponent range: safe for gradients)."""
+    lib = _lib.load()
+    y = out if out is not None else torch.empty((M, Nout), dtype=torch.float32, device=x.device)
+    nb = lib.sgg_tc32_linear_workspace_bytes(M, Nout, K)
+    ws = torch.empty(nb, dtype=torch.uint8, device=x.device) if nb else None
+    check(lib.sgg_tc32_linear_forward(_ptr(x), _ptr(w_split), None, _ptr(y), M, Nout, K, 0, _ptr(ws), nb, _stream()),
+          'sgg_tc32_linear_forward')
+    return y
+
+
+def linear_backward(x, weight, dy, need_dx=True, need_dw=True, need_db=True):
+    """nn.Linear backward through the C-ABI: returns (dx, dw, db); dy must already carry the ReLU mask.
+
+    Large GEMMs run on the 3xTF32 tcgen05 engine (dX = dY W with x = dY, w = split(W^T); dW = dY^T X with x = dY^T,
+    w = split(X^T)); small ones on the fp32 SIMT tiles.  dW is written (not accumulated) into a fresh tensor or, when a
+    reducer registered a sink for ``weight``, straight into its flat gradient buffer, row chunk by row chunk."""
+    lib = _lib.load()
+    x = _f32(x, 'x'); w_obj = weight; weight = _f32(weight, 'weight'); dy = _f32(dy, 'dy')
     M, K = x.shape
     Nout = weight.shape[0]
     dev = x.device
-    dx = torch.empty((M, K), dtype=torch.float32, device=dev) if need_dx else None
-    dw = torch.zeros((Nout, K), dtype=torch.float32, device=dev) if need_dw else None
-    db = torch.zeros((Nout,), dtype=torch.float32, device=dev) if need_db else None
-    nbytes = lib.sgg_linear_backward_workspace_bytes(M, Nout, K)
-    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-    check(lib.sgg_linear_backward(_ptr(x), _ptr(weight), _ptr(dy), M, Nout, K, _ptr(dx), _ptr(dw), _ptr(db),
-                                  _ptr(ws), nbytes, _stream()), 'sgg_linear_backward')
+    use_tc = _TC_BWD['enabled'] and _use_tc()
+    dx = dw = db = None
+    sink = grad_sink(w_obj) if need_dw else None
+    # ---- dX [M,K] = dY [M,Nout] W [Nout,K]
+    tc_dx = need_dx and use_tc and M >= _TC_BWD['min_rows'] and Nout % 4 == 0 and Nout >= 64 and K >= 64
+    if tc_dx:
+        wT = _transpose(weight, Nout, K, K, Nout, split=True)             # [2, K, Nout]
+        dx = _tc32_linear(dy, wT, M, K, Nout)
+        del wT
+    # ---- dW [Nout,K] = dY^T X (reduction over the M rows)
+    tc_dw = need_dw and use_tc and M >= _TC_BWD['min_red'] and Nout >= 64 and K >= 64
+    if need_dw:
+        dw = sink[1] if sink is not None else torch.empty((Nout, K), dtype=torch.float32, device=dev)
+    if tc_dw:
+        Mp = _pad32(M)
+        xT = _transpose(x, M, K, K, Mp, split=True)                       # [2, K, Mp], shared by every row chunk
+        chunks = sink[2] if (sink is not None and sink[2]) else [(0, Nout)]
+        for r0, r1 in chunks:
+            dyT = _transpose(dy[:, r0:], M, r1 - r0, Nout, Mp, split=False)    # [r1-r0, Mp]
+            _tc32_linear(dyT, xT, r1 - r0, K, Mp, out=dw[r0:r1])
+            if sink is not None:
+                sink[3](sink[0](), r0, r1)
+        del xT
+    # ---- remaining pieces on the SIMT tiles (one call; accumulate = 0: plain stores, no zero-fill)
+    rest_dx, rest_dw = need_dx and not tc_dx, need_dw and not tc_dw
+    if rest_dx or rest_dw or need_db:
+        if rest_dx:
+            dx = torch.empty((M, K), dtype=torch.float32, device=dev)
+        if need_db:
+            db = torch.empty((Nout,), dtype=torch.float32, device=dev)
+        nbytes = lib.sgg_linear_backward_workspace_bytes(M, Nout, K)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        check(lib.sgg_linear_backward_ex(_ptr(x), _ptr(weight), _ptr(dy), M, Nout, K, _ptr(dx) if rest_dx else None,
+                                         _ptr(dw) if rest_dw else None, _ptr(db), 0, _ptr(ws), nbytes, _stream()),
+              'sgg_linear_backward_ex')
+        if rest_dw and sink is not None:
+            sink[3](sink[0](), 0, Nout)
+    if sink is not None:
+        dw = dw.view(Nout, K)      # fresh alias: autograd adopts it as p.grad without a copy (it is the only reference)
     return dx, dw, db
 
 

@@ -129,7 +129,9 @@ class FusedSGD(torch.optim.Optimizer):
         self.last_norm = None
 
     @torch.no_grad()
-    def step(self, closure=None, max_norm=None, write_clipped_grads=False):
+    def step(self, closure=None, max_norm=None, write_clipped_grads=False, grad_scale=1.0):
+        """``grad_scale``: the gradients in memory are the data-parallel SUM; the step uses grad_scale * g
+        (``FlatGradReducer.grad_scale`` = 1 / world), folded into the clip factor — no separate averaging sweep."""
         loss = None
         if closure is not None:
             with torch.enable_grad():
@@ -168,10 +170,16 @@ class FusedSGD(torch.optim.Optimizer):
         tab.sync(rows, device)
         norm_ptr = C.c_void_p(0)
         if max_norm is not None:
-            check(lib.sgg_mt_grad_norm(_ptr(tab.dev), tab.n, tab.chunks, float(max_norm), _ptr(tab.norm), _ptr(tab.ws),
-                                       tab.ws.numel(), _stream()), 'sgg_mt_grad_norm')
+            check(lib.sgg_mt_grad_norm_scaled(_ptr(tab.dev), tab.n, tab.chunks, float(max_norm), float(grad_scale),
+                                              _ptr(tab.norm), _ptr(tab.ws), tab.ws.numel(), _stream()),
+                  'sgg_mt_grad_norm_scaled')
             norm_ptr = _ptr(tab.norm)
             self.last_norm = tab.norm
+        elif grad_scale != 1.0:                    # no clipping: the sweep still applies norm[2] = grad_scale
+            if getattr(self, '_scale_only', None) is None or float(self._scale_only[1]) != float(grad_scale):
+                t = torch.tensor([0.0, 1.0, float(grad_scale), 0.0], dtype=torch.float32, device=device)
+                self._scale_only = (t, float(grad_scale))
+            norm_ptr = _ptr(self._scale_only[0])
         check(lib.sgg_mt_sgd_step(_ptr(tab.dev), tab.n, tab.chunks, norm_ptr, momentum, 1 if write_clipped_grads else 0,
                                   _stream()), 'sgg_mt_sgd_step')
         for p, g in touched:                       # raw-pointer writes: tell autograd / the split cache about them
