@@ -52,6 +52,11 @@ def parse():
     ap.add_argument('--edges', type=int, default=300)
     ap.add_argument('--iters', type=int, default=3)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--workload', default='l1', choices=['l1', 'train'],
+                    help="headline workload: 'l1' = BASELINE.json configs[1] forward (default); 'train' = configs[3] train step")
+    ap.add_argument('--no-train', action='store_true', help='skip the train-step measurement nested under "train_step"')
+    ap.add_argument('--train-batch', type=int, default=32, help='images per GPU of the train step (configs[3]: 256 / 8)')
+    ap.add_argument('--train-steps', type=int, default=8)
     ap.add_argument('--no-graph', action='store_true', help='do not replay the step from a CUDA graph')
     ap.add_argument('--cpu-baseline-only', action='store_true', help='internal: print the cpu_baseline object and exit')
     return ap.parse_args()
@@ -199,6 +204,96 @@ def cpu_reference_run(args, cases, params, steps, warmup, threads):
     return times
 
 
+def measure_train(args, dev, rank, world, dist, barrier):
+    """BASELINE.json configs[3]: the PredCls TRAIN step (sgg_b200/trainstep.py) with ``--train-batch`` images per GPU,
+    sharded over the ranks, gradients all-reduced with NCCL.  Runs on every rank; returns the record (rank 0 prints it)."""
+    from sgg_b200 import trainstep
+
+    def rmax(x):
+        if dist is None:
+            return float(x)
+        t = torch.tensor([float(x)], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    K = max(2, args.train_steps)
+    ts = trainstep.TrainStep(dev, B=args.train_batch, boxes=args.boxes, edges=args.edges, mp_iter=args.iters, rank=rank)
+    log('train: model built (%.1f M trainable parameters), N=%d E=%d per rank' % (ts.trainable / 1e6, ts.N, ts.E))
+    first = float(ts.step(0))                                   # also learns the gradient arrival order (re-layout)
+    ms = rmax(trainstep.timed_steps(ts, K, 3, barrier))
+    last = float(ts.last_loss)
+    log('train: %.2f ms/step' % ms)
+    rec = {'workload': 'PredCls train step from the predict boundary (pooled 512x7x7 object / union-box features -> geometry '
+                       'branch + fc6/fc7 -> unary -> %d x message passing -> heads -> node + edge CE losses -> backward -> '
+                       'gradient all-reduce -> global-norm clip -> SGD momentum), %d images/GPU x %d boxes x %d edges; frozen '
+                       'detector (no gradients, no communication) outside the step'
+                       % (args.iters, args.train_batch, args.boxes, args.edges),
+           'n_gpus': world, 'images_per_gpu': args.train_batch, 'steps': K, 'warmup': 3,
+           'ms_per_step': ms, 'images_per_s': args.train_batch * world / (ms * 1e-3), 'scaling': 'weak',
+           'trainable_params': ts.trainable, 'allreduce_bytes_per_step': ts.trainable * 4 if world > 1 else 0,
+           'buckets': len(ts.red.buckets), 'loss_first': first, 'loss_last': last,
+           'finite': bool(np.isfinite([first, last]).all())}
+    if world > 1:
+        ts.red.comm_enabled = False                             # same step without the collectives: what overlap must hide
+        ms_nc = rmax(trainstep.timed_steps(ts, K, 1, barrier))
+        ts.red.comm_enabled = True
+        ar = trainstep.allreduce_probe(ts.trainable * 4, dev)
+        exposed = max(0.0, ms - ms_nc)
+        rec.update({'ms_per_step_no_collectives': ms_nc, 'exposed_comm_ms': exposed,
+                    'allreduce_standalone': ar,
+                    'comm_hidden_frac': max(0.0, 1.0 - exposed / ar['ms']) if ar['ms'] > 0 else None,
+                    'note': 'buckets are all-reduced in place on the flat gradient buffer while backward runs; fc6 weight '
+                            'gradients are produced and reduced in row chunks'})
+    # ---- end to end: every step uploads its pooled features from pinned host memory (copy stream, double-buffered
+    # device slots) and reads the loss back
+    d0 = ts.batches[0][0]
+    keys = ('node_feat', 'edge_feat', 'rois', 'rel_inds', 'obj_labels', 'rel_labels')
+    host = {k: d0[k].cpu().pin_memory() for k in keys}
+    slots = [{k: torch.empty_like(d0[k]) for k in keys} for _ in range(2)]
+    copy_s = torch.cuda.Stream(device=dev)
+    ready = [torch.cuda.Event() for _ in range(2)]
+    freed = [torch.cuda.Event() for _ in range(2)]
+    h_loss = torch.zeros(1, dtype=torch.float32).pin_memory()
+    h2d = sum(host[k].numel() * host[k].element_size() for k in keys)
+
+    def upload(i):
+        sl = i % 2
+        with torch.cuda.stream(copy_s):
+            copy_s.wait_event(freed[sl])
+            for k in keys:
+                slots[sl][k].copy_(host[k], non_blocking=True)
+            ready[sl].record(copy_s)
+
+    def run(n):
+        cur = torch.cuda.current_stream(dev)
+        for sl in range(2):
+            freed[sl].record(cur)
+        upload(0)
+        for i in range(n):
+            if i + 1 < n:
+                upload(i + 1)
+            cur.wait_event(ready[i % 2])
+            loss = ts.step(i, inputs=slots[i % 2])
+            freed[i % 2].record(cur)
+            h_loss.copy_(loss.reshape(1), non_blocking=True)
+        torch.cuda.synchronize()
+
+    run(2)
+    barrier()
+    t0 = time.perf_counter()
+    run(K)
+    barrier()
+    e2e_s = rmax(time.perf_counter() - t0)
+    rec['e2e'] = {'images_per_s': args.train_batch * world * K / e2e_s, 'ms_per_step': e2e_s * 1e3 / K,
+                  'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4,
+                  'api': 'sgg_b200.trainstep.TrainStep.step on host-resident pooled features (pinned, uploaded on a copy '
+                         'stream one step ahead), loss read back every step'}
+    log('train e2e: %.2f ms/step' % (e2e_s * 1e3 / K))
+    del ts, slots, host
+    torch.cuda.empty_cache()
+    return rec
+
+
 def main():
     args = parse()
     if os.environ.get('SGG_BENCH_WATCHDOG'):
@@ -212,7 +307,9 @@ def main():
                 % (args.batch, args.boxes, args.edges, args.iters))
     config = {'workload': workload, 'batch_per_gpu': args.batch, 'boxes_per_img': args.boxes,
               'edges_per_img': args.edges, 'mp_iter': args.iters, 'boundary': 'L1 (4096-d features -> dists)',
-              'parallelism': 'dp%d (independent image shards, no data-path collective)' % max(world, 1)}
+              'parallelism': 'dp%d (independent image shards, no data-path collective)' % max(world, 1),
+              'l2_policy': 'CUDA arm: inputs cycle through a ring larger than L2 (features are read from HBM every step)'}
+    run_info = {}
     if args.impl == 'native' and not args.cpu_baseline_only:
         torch.set_num_threads(min(8, os.cpu_count() or 1))     # host side of the CUDA arm is plumbing only
     params = synth.synth_params(111, level='l1')
@@ -270,7 +367,7 @@ def main():
     in_bytes = (N + E) * D * 4
     ring = max(2, int(np.ceil(1.5 * l2 / in_bytes)))          # input ring > L2 so features come from HBM
     cases = [c0] + [make_case(args, rank, s) for s in range(1, ring)]
-    config['l2_policy'] = 'input ring of %d x %.1f MB > %.0f MB L2 (features read from HBM every step)' % (
+    run_info['l2_policy'] = 'input ring of %d x %.1f MB > %.0f MB L2 (features read from HBM every step)' % (
         ring, in_bytes / 1e6, l2 / 1e6)
 
     log('synthetic cases ready (ring=%d)' % ring)
@@ -300,13 +397,13 @@ def main():
                     step_eager(i)
                     launches_per_step = lib.sgg_launch_count() - n0
                 cuda_graphs.append(gr)
-            config['launch'] = 'cuda-graph replay (1 graph/step, %d kernels)' % launches_per_step
+            run_info['launch'] = 'cuda-graph replay (1 graph/step, %d kernels)' % launches_per_step
         except Exception as ex:   # capture unsupported: fall back to eager launches (still the CUDA path)
             cuda_graphs = None
-            config['launch'] = 'eager (graph capture failed: %s)' % str(ex)[:80]
+            run_info['launch'] = 'eager (graph capture failed: %s)' % str(ex)[:80]
     if cuda_graphs is None:
         n0 = lib.sgg_launch_count(); step_eager(0); launches_per_step = lib.sgg_launch_count() - n0
-        config.setdefault('launch', 'eager')
+        run_info.setdefault('launch', 'eager')
 
     def step(i):
         if cuda_graphs is not None:
@@ -319,7 +416,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    log('launch mode: %s' % config.get('launch'))
+    log('launch mode: %s' % run_info.get('launch'))
     # ---- device-resident throughput ("value")
     for i in range(max(args.warmup, 3)):
         step(i)
@@ -341,6 +438,7 @@ def main():
 
     # ---- end-to-end through the host-buffer API ("e2e"): pinned host inputs, H2D + D2H inside the timed region
     runner = ImpL1Runner(dparams, N, E, args.iters, slots=3, device=dev)
+    h2d_bytes, d2h_bytes = runner.h2d_bytes, runner.d2h_bytes
     h_in = [(torch.from_numpy(c['obj']).pin_memory(), torch.from_numpy(c['edge']).pin_memory(),
              torch.from_numpy(c['rel']).pin_memory()) for c in cases[:max(2, min(ring, 4))]]
     for i in range(max(args.warmup, 3)):
@@ -363,9 +461,27 @@ def main():
     clocks = sampler.stop() if sampler is not None else None
     log('e2e: %.3f ms/step' % (e2e_s * 1e3 / args.steps))
 
+    # ---- BASELINE.json configs[3]: the train step with the gradient all-reduce (every rank takes part).  It runs LAST
+    # (after rank 0 has taken its single-GPU stage timings) so that a failure in it can never cost the headline line.
+    def run_train():
+        if args.workload != 'train' and args.no_train:
+            return None
+        torch.cuda.empty_cache()
+        try:
+            return measure_train(args, dev, rank, world, dist, barrier)
+        except Exception as ex:
+            if args.workload == 'train':
+                raise
+            log('train step failed: %s: %s' % (type(ex).__name__, str(ex)[:300]))
+            return {'error': '%s: %s' % (type(ex).__name__, str(ex)[:300])}
+
+    del runner
     if rank != 0:
-        if dist is not None:
+        run_train()
+        try:
             dist.destroy_process_group()
+        except Exception:
+            pass
         return 0
 
     # ---- roofline of the dominant stage, timed live with CUDA events on the launching stream
@@ -446,20 +562,38 @@ def main():
         cpu = cpu_baseline_subprocess(args)
         log('cpu baseline done')
 
+    train = run_train()
     images = args.batch * world
     line = {'metric': 'images/sec (PredCls, 3 MP iters)', 'value': images / (ms_step * 1e-3), 'unit': 'images/s',
             'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_step,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': config, 'clocks': clocks,
-            'e2e': {'value': images * args.steps / e2e_s, 'unit': 'images/s', 'h2d_bytes_per_step': runner.h2d_bytes,
-                    'd2h_bytes_per_step': runner.d2h_bytes, 'ms_per_step': e2e_s * 1e3 / args.steps,
+            'e2e': {'value': images * args.steps / e2e_s, 'unit': 'images/s', 'h2d_bytes_per_step': h2d_bytes,
+                    'd2h_bytes_per_step': d2h_bytes, 'ms_per_step': e2e_s * 1e3 / args.steps,
+                    'h2d_gbs_per_rank': h2d_bytes * args.steps / e2e_s / 1e9,
                     'api': 'sgg_b200.runner.ImpL1Runner.submit/wait (3 in-flight slots, pinned host buffers)'},
             'gpu_launches': int(launches_per_step) * args.steps,
             'gpu_launches_per_step': int(launches_per_step),
-            'roofline': roofline, 'cpu_baseline': cpu}
+            'run': run_info, 'roofline': roofline, 'cpu_baseline': cpu, 'train_step': train}
+    if args.workload == 'train':
+        # headline = BASELINE.json configs[3]; the L1 forward numbers stay in the line under 'l1_forward'
+        line['l1_forward'] = {k: line[k] for k in ('value', 'ms_per_step', 'e2e', 'gpu_launches_per_step')}
+        line['config'] = dict(config, workload=train['workload'], batch_per_gpu=args.train_batch,
+                              boundary='predict (pooled features -> dists) + losses + backward + all-reduce + clip + SGD',
+                              parallelism='dp%d (images sharded by rank, NCCL all-reduce on gradients only)' % world)
+        line.update({'value': train['images_per_s'], 'ms_per_step': train['ms_per_step'], 'steps': train['steps'],
+                     'warmup': train['warmup'],
+                     'e2e': {'value': train['e2e']['images_per_s'], 'unit': 'images/s',
+                             'h2d_bytes_per_step': train['e2e']['h2d_bytes_per_step'],
+                             'd2h_bytes_per_step': train['e2e']['d2h_bytes_per_step'],
+                             'ms_per_step': train['e2e']['ms_per_step'], 'api': train['e2e']['api']}})
     print(json.dumps(line))
+    sys.stdout.flush()
     if dist is not None:
-        dist.destroy_process_group()
+        try:
+            dist.destroy_process_group()
+        except Exception:
+            pass
     return 0
 
 

@@ -89,6 +89,13 @@ SGG_API int sgg_mp_forward(const float *obj_rep, const float *rel_rep, const voi
                    float *V_out, float *E_out, float *saved,
                    void *ws, size_t ws_bytes, void *stream);
 
+/* Measurement probe: ONE launch of the fused 3xFP16 message-passing schedule (iteration 0) on a workspace that a
+ * preceding sgg_mp_forward call with the same arguments initialised.  which: 0 = INIT launch, 1 = launch A (P/Q GEMM
+ * tiles + vertex-context gather), 2 = launch B (edge + node GRU tiles).  Used by bench.py for the per-kernel roofline. */
+SGG_API int sgg_mp_probe_launch(int which, const float *obj_rep, const float *rel_rep, const void *graph_ws,
+                        const sgg_mp_weights *w, int N, int E, int H, int T, float *V_out, float *E_out,
+                        void *ws, size_t ws_bytes, void *stream);
+
 /* One edge-GRU update in isolation (rel_model_stanford.py:83 with the gathered, gate-scaled input of :76-81
  * expressed through P = V W_ih^T [N,3H] and gates [E,4] = (g_sub, g_obj, g_out, g_in)):
  * out[E,H] = GRUCell(g_sub P[s] + g_obj P[o] + b_ih, Eh W_hh^T + b_hh, Eh).  w_hh_split (nullable) selects tcgen05. */
@@ -155,6 +162,11 @@ SGG_API int sgg_tc_get_mode(void);
 SGG_API int sgg_tc_debug_timing(long long *host_out, int n_ctas);
 /* same for the last fused message-passing launch (csrc/mp_fused.cu): which = 0 k_mp_gru (launch B / INIT), 1 k_mp_pre (launch A) */
 SGG_API int sgg_mpf_debug_timing(long long *host_out, int n_ctas, int which);
+/* fp16 range guard of mode 1: the split / conversion / plane-emitting kernels raise a sticky device flag when an
+ * operand is outside the fp16 range (|x| >= 65520) or non-finite.  Returns the flag (0 = clean; bit 0 activation operand,
+ * bit 1 emitted plane, bit 2 weight), < 0 on a CUDA error; reset != 0 clears it.  Synchronises the device — call it
+ * where the host waits anyway (the eval tail does) and fall back to mode 0 (3xTF32, fp32 range) when it fires. */
+SGG_API int sgg_tc16_overflow(int reset);
 SGG_API int sgg_tc_split_weights(const float *w, size_t n, float *split, void *stream);
 SGG_API size_t sgg_tc_linear_workspace_bytes(int M, int Nout, int K);   /* split-K partials (0 = none needed) */
 SGG_API int sgg_tc_linear_forward(const float *x, const float *w_split, const float *b, float *y,
@@ -217,6 +229,23 @@ SGG_API int sgg_union_geom_forward(const float *rois, const int64_t *union_inds,
  * patches[E,4,98] (tap = ch*49 + ky*7 + kx; zero over the padding), so conv1 becomes a linear op. */
 SGG_API int sgg_geom_patches(const float *rois, const int64_t *union_inds, int64_t row_stride,
                      int col_subj, int col_obj, int E, float *out, void *stream);
+
+/* ---- a7, training mode: BatchNorm with BATCH statistics (+ running-stat update) and the 2x2 max-pool of the
+ * geometry branch (lib/get_union_boxes.py:51-59: Conv-ReLU-BN-MaxPool-Conv-ReLU-BN; the convolutions are linear maps
+ * here, see sgg_geom_patches).  relu_in != 0 folds the preceding ReLU: y = BN(relu(x)), and the backward returns the
+ * gradient w.r.t. the pre-activation x.  running_mean / running_var (nullable): running = (1 - momentum) * running +
+ * momentum * batch (unbiased variance), as torch.nn.BatchNorm2d.  Deterministic (fixed-order column reductions). */
+SGG_API size_t sgg_bn_workspace_bytes(int M, int C);
+SGG_API int sgg_bn_train_forward(const float *x, int M, int C, int relu_in, const float *gamma, const float *beta,
+                         float *running_mean, float *running_var, float momentum, float eps, float *y,
+                         float *save_mean, float *save_invstd, void *ws, size_t ws_bytes, void *stream);
+SGG_API int sgg_bn_train_backward(const float *x, const float *dy, int M, int C, int relu_in, const float *gamma,
+                          const float *save_mean, const float *save_invstd, float *dx, float *dgamma, float *dbeta,
+                          void *ws, size_t ws_bytes, void *stream);
+/* x [E,4,C] -> y [E,C] = max over the 4 conv positions of an edge (MaxPool2d(3,2,1) on the 2x2 map), idx = arg-max
+ * (first maximum, where the reference's max-pool backward sends the gradient); backward scatters dy to dx [E,4,C]. */
+SGG_API int sgg_max4_forward(const float *x, int E, int C, float *y, unsigned char *idx, void *stream);
+SGG_API int sgg_max4_backward(const float *dy, const unsigned char *idx, int E, int C, float *dx, void *stream);
 
 /* ---- a9: node_edge_features (rel_model_base.py:245-260): torchvision
  * roi_align(aligned=False, sampling_ratio=2, 7x7, scale 1/16) for objects and

@@ -78,6 +78,16 @@ SIGNATURES = {
     'sgg_tc_set_mode': (C.c_int, [C.c_int]),
     'sgg_tc_get_mode': (C.c_int, []),
     'sgg_tc_debug_timing': (C.c_int, [C.POINTER(C.c_longlong), C.c_int]),
+    'sgg_mp_probe_launch': (C.c_int, [C.c_int, c_f, c_f, C.c_void_p, C.POINTER(MpWeights), C.c_int, C.c_int, C.c_int, C.c_int,
+                                      c_f, c_f, C.c_void_p, C.c_size_t, C.c_void_p]),
+    'sgg_tc16_overflow': (C.c_int, [C.c_int]),
+    'sgg_bn_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int]),
+    'sgg_bn_train_forward': (C.c_int, [c_f, C.c_int, C.c_int, C.c_int, c_f, c_f, c_f, c_f, C.c_float, C.c_float, c_f, c_f,
+                                       c_f, C.c_void_p, C.c_size_t, C.c_void_p]),
+    'sgg_bn_train_backward': (C.c_int, [c_f, c_f, C.c_int, C.c_int, C.c_int, c_f, c_f, c_f, c_f, c_f, c_f, C.c_void_p,
+                                        C.c_size_t, C.c_void_p]),
+    'sgg_max4_forward': (C.c_int, [c_f, C.c_int, C.c_int, c_f, C.c_void_p, C.c_void_p]),
+    'sgg_max4_backward': (C.c_int, [c_f, C.c_void_p, C.c_int, C.c_int, c_f, C.c_void_p]),
     'sgg_mpf_debug_timing': (C.c_int, [C.POINTER(C.c_longlong), C.c_int, C.c_int]),
     'sgg_tc_split_weights': (C.c_int, [c_f, C.c_size_t, c_f, C.c_void_p]),
     'sgg_tc_linear_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int, C.c_int]),

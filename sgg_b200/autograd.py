@@ -98,28 +98,59 @@ def _conv_params(conv):
     return p
 
 
+class _ReluBnTrainFn(torch.autograd.Function):
+    """BatchNorm(relu(x)) in training mode (batch statistics over the rows, running-stat update), CUDA fwd + bwd."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, momentum, eps):
+        y, mean, invstd = ops.bn_train_forward(x, gamma, beta, running_mean, running_var, momentum, eps, relu_in=True)
+        ctx.save_for_backward(x, gamma, mean, invstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gamma, mean, invstd = ctx.saved_tensors
+        dx, dgamma, dbeta = ops.bn_train_backward(x, dy.contiguous(), gamma, mean, invstd, relu_in=True)
+        return dx, dgamma, dbeta, None, None, None, None
+
+
+class _Max4Fn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        y, idx = ops.max4_forward(x)
+        ctx.save_for_backward(idx)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (idx,) = ctx.saved_tensors
+        return ops.max4_backward(dy.contiguous(), idx)
+
+
+def relu_bn_train(x, bn):
+    y = _ReluBnTrainFn.apply(x.contiguous(), bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.momentum, bn.eps)
+    if bn.num_batches_tracked is not None:
+        bn.num_batches_tracked += 1
+    return y
+
+
 def union_geom(rois, union_inds, conv, training):
     """Geometry embedding [E, dim] of UnionBoxesAndFeats (lib/get_union_boxes.py:51-59,66-67).
     eval: one fused CUDA pipeline straight from the boxes (running BN statistics).
     train: the conv windows are materialised by a CUDA kernel ([4E, 98] patches of the 27x27 masks), the two
-    convolutions run through the CUDA linear op (fwd+bwd), and BatchNorm batch statistics / running-stat
-    updates go through ATen batch_norm on the tiny [4E, dim/2] and [E, dim] activations."""
+    convolutions run through the CUDA linear op (fwd+bwd), ReLU + BatchNorm with batch statistics (running-stat
+    update, fwd+bwd) and the 2x2 max-pool are CUDA kernels too (csrc/bn.cu)."""
     rois = rois.detach()
     if not training:
         return ops.union_geom(rois, union_inds, _conv_params(conv))
     c0, bn1, c1, bn2 = conv[0], conv[2], conv[4], conv[6]
     patches = ops.geom_patches(rois, union_inds)                                  # [E,4,98]
     E = patches.shape[0]
-    x = linear(patches.view(E * 4, 98), c0.weight.view(c0.weight.shape[0], -1), c0.bias, relu=True)
-    x = F.batch_norm(x, bn1.running_mean, bn1.running_var, bn1.weight, bn1.bias, True, bn1.momentum, bn1.eps)
-    if bn1.num_batches_tracked is not None:
-        bn1.num_batches_tracked += 1
-    x = x.view(E, 4, -1).amax(1)                                                  # MaxPool2d(3,2,1) over the 2x2 map
-    x = linear(x, c1.weight[:, :, 1, 1].contiguous(), c1.bias, relu=True)         # only the centre tap sees data
-    x = F.batch_norm(x, bn2.running_mean, bn2.running_var, bn2.weight, bn2.bias, True, bn2.momentum, bn2.eps)
-    if bn2.num_batches_tracked is not None:
-        bn2.num_batches_tracked += 1
-    return x
+    x = linear(patches.view(E * 4, 98), c0.weight.view(c0.weight.shape[0], -1), c0.bias)      # ReLU folded into the BN op
+    x = relu_bn_train(x, bn1)
+    x = _Max4Fn.apply(x.view(E, 4, -1))                                           # MaxPool2d(3,2,1) over the 2x2 map
+    x = linear(x, c1.weight[:, :, 1, 1].contiguous(), c1.bias)                    # only the centre tap sees data
+    return relu_bn_train(x, bn2)
 
 
 def broadcast_add(union_pools, geom):

@@ -42,7 +42,7 @@ bool supported(const sgg_mp_weights *w, int N, int E, int H);
 size_t workspace_bytes(int N, int E, int H);
 int forward(const float *obj_rep, const float *rel_rep, const Planes *obj_planes, const Planes *rel_planes,
             const void *graph_ws, const sgg_mp_weights *w, int N, int E, int H, int T, float *V_out, float *E_out,
-            float *saved, void *ws, size_t ws_bytes, cudaStream_t st, Planes *last_planes = nullptr);
+            float *saved, void *ws, size_t ws_bytes, cudaStream_t st, Planes *last_planes = nullptr, int only = -1);
 int heads(const Planes &Vp, const Planes &Ep, const sgg_head_weights *hw, int N, int E, int H, int n_cls, int n_rel,
           float *obj_dists, float *rel_dists, cudaStream_t st);
 int debug_timing(long long *host_out, int n_ctas, int which);

@@ -472,6 +472,22 @@ extern "C" int sgg_edge_gru_forward(const float *Eh, const float *P, const float
   return launch_gru<GRU_EDGE>(a, st);
 }
 
+// Measurement probe (bench.py roofline): ONE launch of the fused message-passing schedule, iteration 0, on a workspace
+// that a preceding sgg_mp_forward call with the same arguments has initialised.  which: 0 = INIT launch (k_mp_gru),
+// 1 = launch A (k_mp_pre: P/Q tiles + ctx gather), 2 = launch B (k_mp_gru: edge + node GRU tiles).
+extern "C" int sgg_mp_probe_launch(int which, const float *obj_rep, const float *rel_rep, const void *graph_ws,
+                                   const sgg_mp_weights *w, int N, int E, int H, int T, float *V_out, float *E_out,
+                                   void *ws, size_t ws_bytes, void *stream) {
+  using namespace sgg;
+  if (which < 0 || which > 2 || !w || !graph_ws || !ws) return sgg_set_err(SGG_E_BADARG, "mp_probe_launch: bad argument");
+  if (!mpf::supported(w, N, E, H)) return sgg_set_err(SGG_E_BADARG, "mp_probe_launch: fused path not active for this shape / engine");
+  MpScratch s;
+  const size_t need = mp_layout(&s, ws, N, E, H);
+  if (need > ws_bytes) return sgg_set_err(SGG_E_WORKSPACE, "mp_probe_launch: workspace %zu < %zu", ws_bytes, need);
+  return mpf::forward(obj_rep, rel_rep, nullptr, nullptr, graph_ws, w, N, E, H, T, V_out, E_out, nullptr, s.fused,
+                      s.fused_bytes, (cudaStream_t)stream, nullptr, which);
+}
+
 extern "C" size_t sgg_mp_tape_bytes(int N, int E, int H, int T) {
   return sgg::mp_tape_view(nullptr, N < 0 ? 0 : N, E < 0 ? 0 : E, H, T < 0 ? 0 : T).floats * sizeof(float);
 }

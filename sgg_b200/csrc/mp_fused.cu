@@ -832,7 +832,9 @@ int heads(const Planes &Vp, const Planes &Ep, const sgg_head_weights *hw, int N,
 // last_planes (nullable, [2] = {V_T, E_T}): the last launch also emits the planes of the final states (for heads()).
 int forward(const float *obj_rep, const float *rel_rep, const Planes *obj_planes, const Planes *rel_planes,
             const void *graph_ws, const sgg_mp_weights *w, int N, int E, int H, int T, float *V_out, float *E_out,
-            float *saved, void *ws, size_t ws_bytes, cudaStream_t st, Planes *last_planes) {
+            float *saved, void *ws, size_t ws_bytes, cudaStream_t st, Planes *last_planes, int only) {
+  // only >= 0 (bench probe): issue a single launch of iteration 0 on a workspace a full run has initialised:
+  // 0 = INIT launch, 1 = launch A, 2 = launch B
   Scratch s;
   const size_t need = layout(&s, ws, N, E, H);
   if (!ws || need > ws_bytes) return sgg_set_err(SGG_E_WORKSPACE, "mp_fused: workspace %zu < %zu", ws_bytes, need);
@@ -854,11 +856,11 @@ int forward(const float *obj_rep, const float *rel_rep, const Planes *obj_planes
   int rc;
   // planes of the inputs (the L1 entry gets them from the unary GEMM epilogues)
   Planes op = obj_planes ? *obj_planes : s.ctx, rp = rel_planes ? *rel_planes : s.Eh[1];
-  if (!obj_planes) {
+  if (!obj_planes && only < 0) {
     k_split_planes<<<(int)((vN / 4 + 255) / 256 < 1184 ? (vN / 4 + 255) / 256 : 1184), 256, 0, st>>>(obj_rep, vN / 4, op.hi, op.lo);
     SGG_RETURN_IF_LAUNCH_FAILED("k_split_planes");
   }
-  if (!rel_planes) {
+  if (!rel_planes && only < 0) {
     k_split_planes<<<(int)((eN / 4 + 255) / 256 < 1184 ? (eN / 4 + 255) / 256 : 1184), 256, 0, st>>>(rel_rep, eN / 4, rp.hi, rp.lo);
     SGG_RETURN_IF_LAUNCH_FAILED("k_split_planes");
   }
@@ -874,7 +876,7 @@ int forward(const float *obj_rep, const float *rel_rep, const Planes *obj_planes
     for (int k = 0; k < 4; ++k) r.gw[k] = last ? nullptr : (edge ? w->gate_w[k] + H : w->gate_w[k]);
     r.pa_out = last ? nullptr : (edge ? s.paE[it_out & 1] : s.paN[it_out & 1]);
   };
-  {  // hx = 0 initial step (:68-72)
+  if (only < 0 || only == 0) {  // hx = 0 initial step (:68-72)
     GruParams p{};
     p.r[0].mode = MODE_INIT; p.r[1].mode = MODE_INIT;
     fill_common(p.r[0], true, 0); fill_common(p.r[1], false, 0);
@@ -883,12 +885,12 @@ int forward(const float *obj_rep, const float *rel_rep, const Planes *obj_planes
     if ((rc = launch_gru(p, oe, on, H, false, st))) return rc;
   }
   const size_t wn = (size_t)3 * H * H;
-  for (int it = 0; it < T; ++it) {
+  for (int it = 0; it < (only >= 0 ? (T > 0 ? 1 : 0) : T); ++it) {
     const int cur = it & 1;
     float *P = saved ? tape.P + (size_t)it * N * 3 * H : s.P;
     float *ctxf = saved ? tape.ctx + (size_t)it * N * H : nullptr;
     float *gates = saved ? tape.gates + (size_t)it * E * 4 : nullptr;
-    {  // launch A
+    if (only < 0 || only == 1) {  // launch A
       PreParams a{};
       a.N = N; a.E = E; a.nct_n = nct; a.nct_e = nct; a.pdl = pdl ? 1 : 0;
       a.lp[0] = lin_prob(N, 3 * H, 3 * H, nullptr, P);
@@ -905,7 +907,7 @@ int forward(const float *obj_rep, const float *rel_rep, const Planes *obj_planes
       if (n_ctx > N) n_ctx = N;
       if ((rc = launch_pre(a, lo, H, n_ctx, st))) return rc;
     }
-    {  // launch B
+    if (only < 0 || only == 2) {  // launch B
       GruParams p{};
       GruRole &re = p.r[0], &rn = p.r[1];
       re.mode = MODE_EDGE; rn.mode = MODE_NODE;
@@ -917,9 +919,10 @@ int forward(const float *obj_rep, const float *rel_rep, const Planes *obj_planes
       rn.h = vbuf(it); rn.PQ = s.Q;
       GruOperands oe{s.Eh[cur].hi, s.Eh[cur].lo, reinterpret_cast<const __half *>(w->edge_w_hh_split), E};
       GruOperands on{s.ctx.hi, s.ctx.lo, reinterpret_cast<const __half *>(w->node_w_ih_split), N};
-      if ((rc = launch_gru(p, oe, on, H, pdl, st))) return rc;
+      if ((rc = launch_gru(p, oe, on, H, pdl && only < 0, st))) return rc;
     }
   }
+  if (only >= 0) return 0;
   if (saved) {   // outputs are the last saved slot
     SGG_CUDA_TRY(cudaMemcpyAsync(V_out, vbuf(T), vN * sizeof(float), cudaMemcpyDeviceToDevice, st));
     SGG_CUDA_TRY(cudaMemcpyAsync(E_out, ebuf(T), eN * sizeof(float), cudaMemcpyDeviceToDevice, st));

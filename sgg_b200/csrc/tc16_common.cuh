@@ -56,6 +56,11 @@ __device__ __forceinline__ void split2(float x0, float x1, uint32_t &hi, uint32_
   lo = *reinterpret_cast<const uint32_t *>(&l);
 }
 
+// fp16 range guard: a packed pair of fp16 `hi` words has an all-ones exponent (inf / nan: |x| >= 65520 or a non-finite
+// input) iff bit 15 / 31 of ((h & 0x7fff7fff) + 0x04000400) is set.  Kernels OR this into a register and raise the
+// sticky device flag once per thread at most (sgg_tc16_overflow reads it).
+__device__ __forceinline__ uint32_t f16x2_nonfinite(uint32_t h) { return ((h & 0x7fff7fffu) + 0x04000400u) & 0x80008000u; }
+
 __device__ __forceinline__ float4 ld4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
 __device__ __forceinline__ float4 ldg4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
 

@@ -33,6 +33,8 @@
 namespace sgg {
 namespace tc16 {
 
+__device__ unsigned int g_tc16_overflow = 0;
+
 enum { EPI_LINEAR = 0, EPI_GRU_INIT = 1, EPI_GRU_NODE = 2, EPI_GRU_EDGE = 3 };
 
 struct Params {
@@ -223,6 +225,7 @@ k_tc16(Params p, const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     const int wc = warp - 2;
     const int c = lane & 7, b = c >> 2;                    // output chunk; source box
     const int ca = 2 * (c & 3);                            // first raw chunk (logical) inside the box
+    uint32_t ovf = 0;                                      // fp16 range guard (sticky flag raised after the main loop)
     auto convert = [&](int it) {
       const int s = it % STAGES, ph = (it / STAGES) & 1;
       mbar_wait(full + s, ph);
@@ -246,6 +249,7 @@ k_tc16(Params p, const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         split2(__uint_as_float(f0.z), __uint_as_float(f0.w), hi.y, lo.y);
         split2(__uint_as_float(f1.x), __uint_as_float(f1.y), hi.z, lo.z);
         split2(__uint_as_float(f1.z), __uint_as_float(f1.w), hi.w, lo.w);
+        ovf |= f16x2_nonfinite(hi.x) | f16x2_nonfinite(hi.y) | f16x2_nonfinite(hi.z) | f16x2_nonfinite(hi.w);
         const uint32_t dst = a_addr + (uint32_t)(g * 1024 + r * 128 + (((c ^ r) & 7) << 4));
         sts128u(dst, hi);
         sts128u(dst + A_HALF, lo);
@@ -330,6 +334,7 @@ k_tc16(Params p, const __grid_constant__ CUtensorMap tmA0, const __grid_constant
               uint2 hi, lo;
               split2(v[0], v[1], hi.x, lo.x);
               split2(v[2], v[3], hi.y, lo.y);
+              if (f16x2_nonfinite(hi.x) | f16x2_nonfinite(hi.y)) atomicOr(&g_tc16_overflow, 2u);
               *reinterpret_cast<uint2 *>(p.out_hi + (size_t)m * p.Nout + j) = hi;
               *reinterpret_cast<uint2 *>(p.out_lo + (size_t)m * p.Nout + j) = lo;
             }
@@ -343,6 +348,7 @@ k_tc16(Params p, const __grid_constant__ CUtensorMap tmA0, const __grid_constant
    } else {
     for (int it = 0; it < total; ++it) convert(it);
    }
+   if (ovf) atomicOr(&g_tc16_overflow, 1u);
    if (!CHUNKED && warp >= 6) {
     // ===================== GRU phase 1: TMEM -> shared staging, thread <-> accumulator row =====================
     const int q = warp & 3;
@@ -493,6 +499,8 @@ __global__ void __launch_bounds__(256) k_tc16_split(const float *__restrict__ w,
       ph[k] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
       pl[k] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
     }
+    if (f16x2_nonfinite(ph[0]) | f16x2_nonfinite(ph[1]) | f16x2_nonfinite(ph[2]) | f16x2_nonfinite(ph[3]))
+      atomicOr(&g_tc16_overflow, 4u);
     reinterpret_cast<uint4 *>(hi)[i] = make_uint4(ph[0], ph[1], ph[2], ph[3]);
     reinterpret_cast<uint4 *>(lo)[i] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
   }
@@ -776,6 +784,18 @@ int gru(int mode, const float *x, const float *h, const float *w_ih_split, const
   if (nbr == 80) return launch<3, 80, 1, EPI_GRU_EDGE>(p, sg, ct, 1, st);
   if (nbr == 64) return launch<3, 64, 1, EPI_GRU_EDGE>(p, sg, ct, 1, st);
   return launch<3, 32, 1, EPI_GRU_EDGE>(p, sg, ct, 1, st);
+}
+
+// sticky fp16 range flag: bit 0 = an activation operand, bit 1 = an emitted output plane, bit 2 = a weight left the fp16
+// range (or was non-finite) since the last reset.  Synchronises the device.
+int overflow_flag(int reset, unsigned int *out) {
+  SGG_CUDA_TRY(cudaDeviceSynchronize());
+  SGG_CUDA_TRY(cudaMemcpyFromSymbol(out, g_tc16_overflow, sizeof(unsigned int)));
+  if (reset) {
+    const unsigned int z = 0;
+    SGG_CUDA_TRY(cudaMemcpyToSymbol(g_tc16_overflow, &z, sizeof(unsigned int)));
+  }
+  return 0;
 }
 
 int split_weights(const float *w, size_t n, void *split, cudaStream_t st) {

@@ -23,6 +23,7 @@ int gru(int mode, const float *x, const float *h, const float *w_ih_split, const
         int M, int H, cudaStream_t st);
 int split_weights(const float *w, size_t n, void *split, cudaStream_t st);
 int debug_timing(long long *host_out, int n_ctas);
+int overflow_flag(int reset, unsigned int *out);
 }  // namespace tc16
 
 static std::atomic<int> g_tc_mode{-1};
@@ -78,7 +79,9 @@ extern "C" size_t sgg_tc_linear_workspace_bytes(int M, int Nout, int K) {
 extern "C" int sgg_tc_linear_forward(const float *x, const float *w_split, const float *b, float *y, int M, int Nout,
                                      int K, int relu, void *ws, size_t ws_bytes, void *stream) {
   if ((M > 0 && Nout > 0) && (!x || !w_split || !y)) return sgg_set_err(SGG_E_BADARG, "tc_linear: null pointer");
-  if (ws && ws_bytes < sgg_tc_linear_workspace_bytes(M, Nout, K)) ws = nullptr;
+  // ws == NULL is allowed (no split-K / stream-K); a workspace that is too small is an error, as the header says
+  if (ws && ws_bytes < sgg_tc_linear_workspace_bytes(M, Nout, K))
+    return sgg_set_err(SGG_E_WORKSPACE, "tc_linear: workspace %zu < %zu", ws_bytes, sgg_tc_linear_workspace_bytes(M, Nout, K));
   return sgg::tc_linear(x, w_split, b, y, M, Nout, K, relu, (float *)ws, (cudaStream_t)stream);
 }
 
@@ -96,4 +99,12 @@ extern "C" int sgg_mpf_debug_timing(long long *host_out, int n_ctas, int which) 
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) return sgg_set_err((int)e, "mpf_debug_timing: %s", cudaGetErrorString(e));
   return sgg::mpf::debug_timing(host_out, n_ctas, which);
+}
+
+/* fp16 range guard of the 3xFP16 engine (|x| must stay below 65504): returns the sticky flag (0 = every operand was in
+ * range since the last reset; bit 0 activations, bit 1 emitted planes, bit 2 weights), negative on error. */
+extern "C" int sgg_tc16_overflow(int reset) {
+  unsigned int v = 0;
+  const int rc = sgg::tc16::overflow_flag(reset, &v);
+  return rc ? -1 : (int)v;
 }

@@ -93,25 +93,16 @@ def union_rois(rois, union_inds):
 def filter_dets(boxes, obj_scores, obj_classes, rel_inds, pred_scores, logits=False):
     """lib/surgery.py:17-55.  Ranks candidate edges by max_{p>=1} P(p) * s_subj * s_obj (descending) and
     returns the reference's 5 numpy arrays.  CUDA tensors: scoring (+ the softmax when ``logits``), sort and gather
-    run in libsgg_b200.so (csrc/eval_tail.cu, ties broken by edge id); CPU tensors (host-side tests of the wire
-    format) go through the same steps in torch."""
+    run in libsgg_b200.so (csrc/eval_tail.cu, ties broken by edge id).  There is no CPU path: CPU tensors raise
+    ``SggError`` (argument validation happens first, as in the reference)."""
     if boxes.dim() != 2:
         raise ValueError('Boxes needs to be [num_box, 4] but its {}'.format(tuple(boxes.shape)))
     assert obj_scores.shape[0] == boxes.shape[0], (obj_scores.shape, boxes.shape)
     assert rel_inds.shape[1] == 2 and pred_scores.shape[0] == rel_inds.shape[0]
-    if pred_scores.is_cuda:
-        from . import ops
-        rels, ps, _, _ = ops.rank_relations(pred_scores, obj_scores.float(), rel_inds, logits=logits)
-        return (boxes.detach().cpu().numpy(), obj_classes.detach().cpu().numpy(), obj_scores.detach().cpu().numpy(),
-                rels.cpu().numpy(), ps.cpu().numpy())
-    if logits:
-        pred_scores = torch.softmax(pred_scores, 1)
-    s0 = obj_scores[rel_inds[:, 0]]; s1 = obj_scores[rel_inds[:, 1]]
-    triple = pred_scores[:, 1:].max(1)[0] * s0 * s1
-    order = torch.sort(triple.view(-1), dim=0, descending=True)[1]
-    rels = rel_inds[order]; ps = pred_scores[order]
+    from . import ops
+    rels, ps, _, _ = ops.rank_relations(pred_scores, obj_scores.float(), rel_inds, logits=logits)   # raises on CPU tensors
     return (boxes.detach().cpu().numpy(), obj_classes.detach().cpu().numpy(), obj_scores.detach().cpu().numpy(),
-            rels.cpu().numpy(), ps.detach().cpu().numpy())
+            rels.cpu().numpy(), ps.cpu().numpy())
 
 
 def random_choose(t, num, p=None):

@@ -78,6 +78,30 @@ def tc_engine():
     return 'tc16' if _lib.load().sgg_tc_get_mode() == 1 else 'tc32'
 
 
+def tc16_overflow(reset=True):
+    """Sticky fp16 range flag of the 3xFP16 engine (0 = clean).  Synchronises the device."""
+    v = _lib.load().sgg_tc16_overflow(1 if reset else 0)
+    if v < 0:
+        raise _lib.SggError('sgg_tc16_overflow failed')
+    return v
+
+
+def run_range_guarded(fn):
+    """Run ``fn()`` on the current engine; if the 3xFP16 engine saw an operand outside the fp16 range (|x| >= 65504,
+    which it would silently turn into inf), re-run it on the 3xTF32 engine (fp32 exponent range) and keep that engine.
+    Costs one device synchronisation: use it where the host waits for the result anyway (the evaluation tail)."""
+    if not _use_tc() or tc_engine() != 'tc16':
+        return fn()
+    tc16_overflow(reset=True)
+    out = fn()
+    if tc16_overflow(reset=True):
+        import warnings
+        warnings.warn('sgg_b200: operand outside the fp16 range; switching the tensor-core engine to 3xTF32')
+        set_gemm_mode('tc32')
+        out = fn()
+    return out
+
+
 def _tc_k_ok(K):
     return K % (8 if _lib.load().sgg_tc_get_mode() == 1 else 4) == 0
 
@@ -207,6 +231,29 @@ def message_pass(rel_rep, obj_rep, graph, params, mp_iter=3, save_states=False):
     return V, Eo
 
 
+class MpProbe(object):
+    """Per-launch timing probe of the fused message-passing schedule (bench.py roofline): runs the whole loop once on a
+    private workspace, then ``launch(which)`` re-issues ONE launch of iteration 0 (0 = INIT, 1 = launch A, 2 = launch B)."""
+
+    def __init__(self, rel_rep, obj_rep, graph, params, mp_iter=3):
+        lib = _lib.load()
+        self.w, self._keep, H = mp_weights(params)
+        self.N, self.E, self.H, self.T, self.graph = graph.N, graph.E, H, mp_iter, graph
+        self.obj = _f32(obj_rep, 'obj_rep', (self.N, H)); self.rel = _f32(rel_rep, 'rel_rep', (self.E, H))
+        dev = self.obj.device
+        self.V = torch.empty((self.N, H), dtype=torch.float32, device=dev)
+        self.Eo = torch.empty((self.E, H), dtype=torch.float32, device=dev)
+        self.nbytes = lib.sgg_mp_workspace_bytes(self.N, self.E, H, mp_iter)
+        self.ws = torch.empty(self.nbytes, dtype=torch.uint8, device=dev)
+        check(lib.sgg_mp_forward(_ptr(self.obj), _ptr(self.rel), _ptr(graph.ws), C.byref(self.w), self.N, self.E, H, mp_iter,
+                                 _ptr(self.V), _ptr(self.Eo), None, _ptr(self.ws), self.nbytes, _stream()), 'sgg_mp_forward')
+
+    def launch(self, which):
+        check(_lib.load().sgg_mp_probe_launch(which, _ptr(self.obj), _ptr(self.rel), _ptr(self.graph.ws), C.byref(self.w),
+                                              self.N, self.E, self.H, self.T, _ptr(self.V), _ptr(self.Eo), _ptr(self.ws),
+                                              self.nbytes, _stream()), 'sgg_mp_probe_launch')
+
+
 def linear(x, weight, bias=None, relu=False):
     """nn.Linear forward (+ReLU) — y = act(x @ weight.T + bias)."""
     lib = _lib.load()
@@ -302,6 +349,59 @@ def geom_patches(rois, union_inds):
     out = torch.empty((E, 4, 98), dtype=torch.float32, device=rois.device)
     check(lib.sgg_geom_patches(_ptr(rois), _ptr(ui), stride, 0, 1, E, _ptr(out), _stream()), 'sgg_geom_patches')
     return out
+
+
+def bn_train_forward(x, gamma, beta, running_mean, running_var, momentum, eps, relu_in=True):
+    """y = BatchNorm(relu(x)) with batch statistics over the rows of x [M, C] (+ in-place running-stat update).
+    Returns (y, save_mean, save_invstd)."""
+    lib = _lib.load()
+    x = _f32(x, 'x')
+    M, Cc = x.shape
+    y = torch.empty_like(x)
+    mean = torch.empty(Cc, dtype=torch.float32, device=x.device); invstd = torch.empty_like(mean)
+    nb = lib.sgg_bn_workspace_bytes(M, Cc)
+    ws = torch.empty(nb, dtype=torch.uint8, device=x.device)
+    check(lib.sgg_bn_train_forward(_ptr(x), M, Cc, 1 if relu_in else 0, _ptr(_f32(gamma, 'gamma', (Cc,))),
+                                   _ptr(_f32(beta, 'beta', (Cc,))), _ptr(running_mean), _ptr(running_var), float(momentum),
+                                   float(eps), _ptr(y), _ptr(mean), _ptr(invstd), _ptr(ws), nb, _stream()),
+          'sgg_bn_train_forward')
+    return y, mean, invstd
+
+
+def bn_train_backward(x, dy, gamma, mean, invstd, relu_in=True):
+    """-> (dx w.r.t. the pre-activation x, dgamma, dbeta)"""
+    lib = _lib.load()
+    x = _f32(x, 'x'); dy = _f32(dy, 'dy', tuple(x.shape))
+    M, Cc = x.shape
+    dx = torch.empty_like(x)
+    dgamma = torch.empty(Cc, dtype=torch.float32, device=x.device); dbeta = torch.empty_like(dgamma)
+    nb = lib.sgg_bn_workspace_bytes(M, Cc)
+    ws = torch.empty(nb, dtype=torch.uint8, device=x.device)
+    check(lib.sgg_bn_train_backward(_ptr(x), _ptr(dy), M, Cc, 1 if relu_in else 0, _ptr(_f32(gamma, 'gamma', (Cc,))),
+                                    _ptr(mean), _ptr(invstd), _ptr(dx), _ptr(dgamma), _ptr(dbeta), _ptr(ws), nb, _stream()),
+          'sgg_bn_train_backward')
+    return dx, dgamma, dbeta
+
+
+def max4_forward(x):
+    """x [E, 4, C] -> (max over the 4 positions [E, C], arg-max uint8 [E, C])"""
+    lib = _lib.load()
+    x = _f32(x, 'x')
+    E, four, Cc = x.shape
+    assert four == 4
+    y = torch.empty((E, Cc), dtype=torch.float32, device=x.device)
+    idx = torch.empty((E, Cc), dtype=torch.uint8, device=x.device)
+    check(lib.sgg_max4_forward(_ptr(x), E, Cc, _ptr(y), _ptr(idx), _stream()), 'sgg_max4_forward')
+    return y, idx
+
+
+def max4_backward(dy, idx):
+    lib = _lib.load()
+    dy = _f32(dy, 'dy')
+    E, Cc = dy.shape
+    dx = torch.empty((E, 4, Cc), dtype=torch.float32, device=dy.device)
+    check(lib.sgg_max4_backward(_ptr(dy), _ptr(idx), E, Cc, _ptr(dx), _stream()), 'sgg_max4_backward')
+    return dx
 
 
 def geom_weights(params, prefix='union_boxes.conv.'):
@@ -513,15 +613,24 @@ def message_pass_backward(rel_rep, obj_rep, graph, params, tape, dV, dE, mp_iter
     obj_rep = _f32(obj_rep, 'obj_rep', (N, H)); rel_rep = _f32(rel_rep, 'rel_rep', (E, H))
     dV = _f32(dV, 'dV', (N, H)); dE = _f32(dE, 'dE', (E, H))
     dev = obj_rep.device
-    grads = {}
+    # the kernels ACCUMULATE over the T iterations: ONE zero-filled slab holds all 16 gradient tensors (one memset
+    # instead of 16 fill launches), each view 256-byte aligned
+    shapes = [(key, tuple(params[key].shape)) for key in MP_KEYS]
+    for k in GATE_KEYS:
+        shapes += [(k + '.0.weight', (1, 2 * H)), (k + '.0.bias', (1,))]
+    offs, total = [], 0
+    for _, shp in shapes:
+        n = 1
+        for d in shp:
+            n *= d
+        offs.append((total, n)); total += (n + 63) // 64 * 64
+    slab = torch.zeros(total, dtype=torch.float32, device=dev)
+    grads = {key: slab[o:o + n].view(shp) for (key, shp), (o, n) in zip(shapes, offs)}
     gs = _lib.MpGrads()
     for field, key in zip(('edge_w_ih', 'edge_w_hh', 'edge_b_ih', 'edge_b_hh',
                            'node_w_ih', 'node_w_hh', 'node_b_ih', 'node_b_hh'), MP_KEYS):
-        grads[key] = torch.zeros_like(params[key], dtype=torch.float32, device=dev)
         setattr(gs, field, grads[key].data_ptr())
     for i, k in enumerate(GATE_KEYS):
-        grads[k + '.0.weight'] = torch.zeros((1, 2 * H), dtype=torch.float32, device=dev)
-        grads[k + '.0.bias'] = torch.zeros((1,), dtype=torch.float32, device=dev)
         gs.gate_w[i] = grads[k + '.0.weight'].data_ptr(); gs.gate_b[i] = grads[k + '.0.bias'].data_ptr()
     d_obj = torch.empty((N, H), dtype=torch.float32, device=dev)
     d_rel = torch.empty((E, H), dtype=torch.float32, device=dev)

@@ -79,7 +79,8 @@ class FlatGradReducer(object):
         for p in self.params:
             if p.device != dev or p.dtype != dt:
                 raise ValueError('FlatGradReducer: parameters must share one device and dtype')
-        self.total = sum(p.numel() for p in self.params)
+        # every tensor starts on a 256-byte boundary of the flat buffer (vectorised optimizer / GEMM stores need 16)
+        self.total = sum(self._pad(p.numel()) for p in self.params)
         self.flat = torch.zeros(self.total, dtype=dt, device=dev)
         self.register_sinks = register_sinks and dev.type == 'cuda'
         self._learned = False
@@ -88,6 +89,10 @@ class FlatGradReducer(object):
         self.hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params]
         self._in_step = False
         self.launched_bytes = 0
+
+    @staticmethod
+    def _pad(n):
+        return (n + 63) // 64 * 64
 
     # ---- layout ----------------------------------------------------------------------------
     def _layout(self, ordered):
@@ -109,12 +114,12 @@ class FlatGradReducer(object):
                 ch = [(r, min(rows, r + per)) for r in range(0, rows, per)]
                 self.chunks[p] = ch
                 for r0, r1 in ch:
-                    self.buckets.append(_Bucket(off + r0 * cols, off + r1 * cols))
-                cur_lo = off + n
-            elif off + n - cur_lo >= self.bucket_elems:
-                self.buckets.append(_Bucket(cur_lo, off + n))
-                cur_lo = off + n
-            off += n
+                    self.buckets.append(_Bucket(off + r0 * cols, off + (r1 * cols if r1 < rows else self._pad(n))))
+                cur_lo = off + self._pad(n)
+            elif off + self._pad(n) - cur_lo >= self.bucket_elems:
+                self.buckets.append(_Bucket(cur_lo, off + self._pad(n)))
+                cur_lo = off + self._pad(n)
+            off += self._pad(n)
         if off > cur_lo:
             self.buckets.append(_Bucket(cur_lo, off))
         self.starts = [b.lo for b in self.buckets]
@@ -142,6 +147,7 @@ class FlatGradReducer(object):
             for p in self.params:
                 p.grad = None
         self._marked = {p: 0 for p in self.params}
+        self._arrived = set()
         for b in self.buckets:
             b.left, b.work = b.hi - b.lo, None
         self._next = 0
@@ -170,9 +176,10 @@ class FlatGradReducer(object):
         """called by the backward GEMM after rows [r0, r1) of p's gradient were written into the flat buffer"""
         if not self._in_step:
             return
-        cols = p.shape[1]
+        rows, cols = p.shape
         self._marked[p] += (r1 - r0) * cols
-        self._mark(self.offset[p] + r0 * cols, self.offset[p] + r1 * cols)
+        hi = r1 * cols if r1 < rows else self._pad(p.numel())      # the last chunk carries the alignment padding
+        self._mark(self.offset[p] + r0 * cols, self.offset[p] + hi)
 
     def _on_grad(self, p):
         if not self._in_step:
@@ -186,18 +193,14 @@ class FlatGradReducer(object):
             p.grad = v
         if not self._learned:
             self._arrival.append(p)
-        n = p.numel()
-        done = self._marked[p]
-        if done > n:
+        if id(p) in self._arrived:
             raise RuntimeError('FlatGradReducer: gradient of a parameter arrived twice in one step (call begin() per backward)')
+        self._arrived.add(id(p))
+        n = p.numel()
+        done = self._marked[p]                 # elements already announced by the producing GEMM (gradient sink)
         if done < n:
             self._marked[p] = n
-            if done == 0:
-                self._mark(self.offset[p], self.offset[p] + n)
-            else:                              # partially notified (should not happen: chunks cover all rows)
-                self._mark(self.offset[p] + done, self.offset[p] + n)
-        elif done == n and p not in self.chunks:
-            raise RuntimeError('FlatGradReducer: gradient of a parameter arrived twice in one step')
+            self._mark(self.offset[p] + done, self.offset[p] + self._pad(n))
 
     def finish(self):
         """After backward: parameters that received no gradient contribute zeros (every rank launches the same
@@ -209,7 +212,7 @@ class FlatGradReducer(object):
                 self.view[p].zero_()
                 p.grad = self.view[p]
                 self._marked[p] = p.numel()
-                self._mark(self.offset[p], self.offset[p] + p.numel())
+                self._mark(self.offset[p], self.offset[p] + self._pad(p.numel()))
         assert self._next == len(self.buckets), 'unlaunched buckets'
         for b in self.buckets:
             if b.work is not None:

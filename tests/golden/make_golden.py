@@ -151,8 +151,12 @@ def main():
              obj_colsum=od.astype(np.float64).sum(0), rel_colsum=rd.astype(np.float64).sum(0))
 
     # ---------------- L1 gradients (torch.autograd through the reference's modules) ------------
+    # grad_l1_cfg2 / grad_l1_shard32: BASELINE cfg2 and the cfg4 per-GPU shard (N = 960, E = 9600) — sizes at which the
+    # CUDA backward runs on the tensor-core GEMMs (round-1 verdict: gradient parity only existed at toy sizes)
     for name, B, nb, ne, ap_, T, scale, seed in [('grad_l1_cfg1', 1, 10, 90, True, 3, 1.0, 7235),
-                                                  ('grad_l1_small_s2', 3, 9, 30, False, 3, 2.0, 7236)]:
+                                                  ('grad_l1_small_s2', 3, 9, 30, False, 3, 2.0, 7236),
+                                                  ('grad_l1_cfg2', 8, 30, 300, False, 3, 1.0, 7237),
+                                                  ('grad_l1_shard32', 32, 30, 300, False, 3, 1.0, 7238)]:
         if not want(name):
             continue
         g = synth.synth_graph(B, nb, ne, seed, all_pairs=ap_)
@@ -219,6 +223,42 @@ def main():
             model.union_boxes.eval()
         save('union_geom', seed=seed, E=E, scale=1.5, digest=synth.digest(g['rois'], g['rel_inds'], p['union_boxes.conv.0.weight']),
              out_eval=ev, out_train=tr, rm1=rm1, rv1=rv1, rm2=rm2, rv2=rv2)
+
+    # ---------------- a7 (train mode): forward with batch statistics + gradients of the conv / BN parameters --------
+    if want('union_geom_train'):
+        seed = 4236
+        g = synth.synth_graph(3, 9, 40, seed)
+        p = synth.synth_params(seed, level='l2', scale=1.5)
+        pg = {k: v for k, v in p.items() if k.startswith('union_boxes.')}
+        load_params(model, pg)
+        rois = tt(g['rois']); ui = tt(g['rel_inds'][:, 1:])
+        E = ui.shape[0]
+        r = np.random.default_rng(seed + 5).standard_normal((E, 512), dtype=np.float32)
+        ub = model.union_boxes
+        ub.train()
+        for q in ub.parameters():
+            q.grad = None
+        out = ub(torch.zeros(E, 512, 7, 7), rois, ui, None)[:, :, 0, 0]
+        loss = (out * tt(r)).sum()
+        loss.backward()
+        rec = dict(seed=seed, E=E, scale=1.5, loss=float(loss), out_train=out.detach().numpy(),
+                   digest=synth.digest(g['rois'], g['rel_inds'], p['union_boxes.conv.0.weight']),
+                   rm1=ub.conv[2].running_mean.numpy().copy(), rv1=ub.conv[2].running_var.numpy().copy(),
+                   rm2=ub.conv[6].running_mean.numpy().copy(), rv2=ub.conv[6].running_var.numpy().copy())
+        for idx in ('0', '2', '4', '6'):
+            for nm in ('weight', 'bias'):
+                gq = getattr(ub.conv[int(idx)], nm).grad.numpy()
+                key = 'g%s_%s' % (idx, nm)
+                if idx == '4' and nm == 'weight':          # only the centre tap of the 3x3 kernel sees data (stride-16 quirk)
+                    rec['g4_offcentre_absmax'] = float(np.abs(np.delete(gq.reshape(512, 256, 9), 4, axis=2)).max())
+                    gq = gq[:, :, 1, 1]
+                    sel = np.sort(np.random.default_rng(seed + 11).choice(gq.size, 4096, replace=False))
+                    rec[key + '_idx'] = sel; rec[key + '_val'] = gq.reshape(-1)[sel]
+                    rec[key + '_asum'] = np.float64(np.abs(gq).astype(np.float64).sum())
+                else:
+                    rec[key] = gq
+        ub.eval()
+        save('union_geom_train', **rec)
 
     # ---------------- a9: node_edge_features (RoIAlign) -----------------------
     if want('roi_align'):

@@ -10,7 +10,7 @@ from tests import cases
 pytestmark = pytest.mark.gpu
 
 
-def _run(name, mode):
+def _run(name, mode, relu_tolerant=False):
     from sgg_b200 import ops, autograd as K
     ops.set_gemm_mode(mode)
     fx = cases.load(name)
@@ -40,9 +40,16 @@ def _run(name, mode):
         flat = gval.detach().cpu().numpy().reshape(-1)
         ref = fx['val__' + kk]; got = flat[fx['idx__' + kk]]
         scale = max(1.0, float(np.abs(ref).max()))
-        err = float(np.abs(got - ref).max()) / scale
+        d = np.abs(got - ref) / scale
+        err = float(d.max())
         worst = max(worst, err)
-        assert err <= 2e-4, '%s: max|d|/scale = %.3e' % (k, err)
+        if relu_tolerant and k in ('edge_unary.weight', 'edge_unary.bias', 'edge_feat'):
+            # relu(edge_unary(x)): a pre-activation within fp32 rounding of 0 can land on the other side of the ReLU than in
+            # the reference's summation order; one such flip (expected: a handful among E x 512 = 4.9 M) moves one row of
+            # the weight gradient by a single sample's contribution (~1e-2 of the row scale).  Everything else must agree.
+            assert float((d > 2e-4).mean()) <= 0.02 and err <= 5e-2, '%s: %.3f of entries off, max %.3e' % (k, float((d > 2e-4).mean()), err)
+        else:
+            assert err <= 2e-4, '%s: max|d|/scale = %.3e' % (k, err)
         asum = float(np.abs(flat).astype(np.float64).sum())
         assert abs(asum - float(fx['asum__' + kk])) <= 2e-4 * max(1.0, float(fx['asum__' + kk])), k
     return worst
@@ -52,6 +59,16 @@ def _run(name, mode):
 @pytest.mark.parametrize('name', ['grad_l1_cfg1', 'grad_l1_small_s2'])
 def test_l1_gradients_vs_reference_autograd(name, mode):
     _run(name, mode)
+
+
+@pytest.mark.parametrize('mode', ['tc', 'simt'])
+@pytest.mark.parametrize('name', ['grad_l1_cfg2', 'grad_l1_shard32'])
+def test_l1_gradients_vs_reference_autograd_at_real_sizes(name, mode):
+    """BASELINE cfg2 (N = 240, E = 2400) and the cfg4 per-GPU shard (N = 960, E = 9600): here the forward runs the fused
+    tcgen05 message passing with the training tape and the backward GEMMs run on the 3xTF32 tensor-core engine
+    (dX-type with >= 256 rows, dW-type with a reduction over >= 1024 rows) — compared with the REFERENCE's autograd
+    (fixtures from tests/golden/make_golden.py), not with another CUDA path."""
+    _run(name, mode, relu_tolerant=True)
 
 
 def test_linear_backward_vs_torch():

@@ -137,6 +137,54 @@ def test_union_geom_eval(ops):
     assert np.abs(full - (pools + fx['out_eval'][:, :, None, None])).max() <= TOL
 
 
+def test_union_geom_train_mode_forward_backward_vs_reference():
+    """a7 in TRAINING mode (lib/get_union_boxes.py:51-59 with batch-statistics BatchNorm, momentum 0.01): outputs, the
+    running-stat update and the gradients of every conv / BN parameter against the reference's own forward + autograd
+    (tests/golden/union_geom_train.npz).  Every stage runs in libsgg_b200.so (patches, linear fwd/bwd, csrc/bn.cu)."""
+    from sgg_b200.model import UnionBoxesAndFeats
+    from sgg_b200 import synth
+    fx = cases.load('union_geom_train')
+    seed = int(fx['seed'])
+    g = synth.synth_graph(3, 9, 40, seed)
+    p = synth.synth_params(seed, level='l2', scale=float(fx['scale']))
+    assert synth.digest(g['rois'], g['rel_inds'], p['union_boxes.conv.0.weight']) == str(fx['digest']), 'generator drift'
+    ub = UnionBoxesAndFeats(pooling_size=7, stride=16, dim=512).cuda()
+    sd = {k[len('union_boxes.'):]: torch.from_numpy(v) for k, v in p.items() if k.startswith('union_boxes.')}
+    missing = ub.load_state_dict(sd, strict=False)
+    assert not missing.unexpected_keys
+    ub.train()
+    rois, ui = dev(g['rois']), dev(g['rel_inds'][:, 1:])
+    E = ui.shape[0]
+    out = ub.geometry(rois, ui)
+    r = dev(np.random.default_rng(seed + 5).standard_normal((E, 512), dtype=np.float32))
+    loss = (out * r).sum()
+    loss.backward()
+    # batch-statistics BN divides by a per-channel std: rounding noise of the conv outputs is amplified, and the outputs
+    # are O(10) here (weights scaled x1.5) — the bar is 1e-4 relative to the output scale
+    oscale = max(1.0, float(np.abs(fx['out_train']).max()))
+    assert np.abs(out.detach().cpu().numpy() - fx['out_train']).max() <= TOL * oscale
+    assert abs(float(loss) - float(fx['loss'])) <= 1e-3 * max(1.0, abs(float(fx['loss'])))
+    for key, t in (('rm1', ub.conv[2].running_mean), ('rv1', ub.conv[2].running_var), ('rm2', ub.conv[6].running_mean),
+                   ('rv2', ub.conv[6].running_var)):
+        assert np.abs(t.cpu().numpy() - fx[key]).max() <= 1e-6 * max(1.0, float(np.abs(fx[key]).max())), key
+    assert int(ub.conv[2].num_batches_tracked) == 1 and int(ub.conv[6].num_batches_tracked) == 1
+
+    def close(got, ref, what):
+        scale = max(1.0, float(np.abs(ref).max()))
+        err = float(np.abs(got - ref).max()) / scale
+        assert err <= 2e-4, '%s: max|d|/scale = %.3e' % (what, err)
+
+    for idx in (0, 2, 6):
+        close(ub.conv[idx].weight.grad.cpu().numpy(), fx['g%d_weight' % idx], 'conv.%d.weight' % idx)
+        close(ub.conv[idx].bias.grad.cpu().numpy(), fx['g%d_bias' % idx], 'conv.%d.bias' % idx)
+    g4 = ub.conv[4].weight.grad.cpu().numpy()
+    assert float(np.abs(np.delete(g4.reshape(512, 256, 9), 4, axis=2)).max()) == 0.0 == float(fx['g4_offcentre_absmax'])
+    c4 = g4[:, :, 1, 1]
+    close(c4.reshape(-1)[fx['g4_weight_idx']], fx['g4_weight_val'], 'conv.4.weight (centre tap)')
+    assert abs(float(np.abs(c4).astype(np.float64).sum()) - float(fx['g4_weight_asum'])) <= 2e-4 * float(fx['g4_weight_asum'])
+    close(ub.conv[4].bias.grad.cpu().numpy(), fx['g4_bias'], 'conv.4.bias')
+
+
 def test_roi_align_node_and_union(ops):
     fx = cases.load('roi_align')
     fmap, rois, ui = cases.roi_inputs(fx)

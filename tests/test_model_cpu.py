@@ -58,18 +58,18 @@ def test_get_rel_inds_eval_and_train():
     assert r2.tolist() == [[0, 0, 1], [0, 1, 0], [1, 3, 4], [1, 4, 3]]
 
 
-def test_filter_dets_matches_oracle():
-    from oracle import imp_numpy as O
+def test_filter_dets_has_no_cpu_path():
+    """Argument validation mirrors lib/surgery.py:17-55 (ValueError first); the ranking itself only exists as CUDA
+    kernels, so CPU tensors are refused loudly instead of silently taking a torch path."""
+    from sgg_b200._lib import SggError
     rng = np.random.default_rng(0)
     N, E = 6, 30
     boxes = rng.random((N, 4)).astype(np.float32); scores = rng.random(N).astype(np.float32)
     cls = rng.integers(1, 151, N); rel = np.stack((rng.integers(0, N, E), rng.integers(0, N, E)), 1)
-    ps = O.softmax(rng.standard_normal((E, 51)).astype(np.float32))
-    out = host.filter_dets(torch.from_numpy(boxes), torch.from_numpy(scores), torch.from_numpy(cls),
-                           torch.from_numpy(rel), torch.from_numpy(ps))
-    ref = O.filter_dets(boxes, scores, cls, rel, ps)
-    for a, b in zip(out, ref):
-        assert np.allclose(a, b)
+    ps = rng.random((E, 51)).astype(np.float32)
+    with pytest.raises(SggError):
+        host.filter_dets(torch.from_numpy(boxes), torch.from_numpy(scores), torch.from_numpy(cls),
+                         torch.from_numpy(rel), torch.from_numpy(ps))
     with pytest.raises(ValueError):
         host.filter_dets(torch.zeros(2, 3, 4), torch.zeros(2), torch.zeros(2), torch.zeros(1, 2).long(), torch.zeros(1, 51))
 
