@@ -54,6 +54,7 @@ def parse():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--workload', default='l1', choices=['l1', 'train'],
                     help="headline workload: 'l1' = BASELINE.json configs[1] forward (default); 'train' = configs[3] train step")
+    ap.add_argument('--no-other-configs', action='store_true', help='skip the cfg3 / cfg5 single-GPU measurements')
     ap.add_argument('--no-train', action='store_true', help='skip the train-step measurement nested under "train_step"')
     ap.add_argument('--train-batch', type=int, default=32, help='images per GPU of the train step (configs[3]: 256 / 8)')
     ap.add_argument('--train-steps', type=int, default=8)
@@ -202,6 +203,87 @@ def cpu_reference_run(args, cases, params, steps, warmup, threads):
             if i >= warmup:
                 times.append(dt)
     return times
+
+
+def measure_other_configs(args, dev, dparams):
+    """BASELINE.json configs[2] and configs[4] on one GPU (rank 0 only, a few hundred ms each), so that the driver's
+    record carries them too:
+      cfg3: SGCls-shaped batch of 32 images with the VGG16 RoIAlign feature head — RoIAlign of objects + union boxes on a
+            [32,512,38,38] feature map, union-box geometry, fc6/fc7 of both heads, then the L1 path (the frozen conv
+            stack in front of it is torchvision/cuDNN library code and is not timed here);
+      cfg5: dense-graph stress, 8 images x 64 boxes x 2000 candidate edges, 6 message-passing iterations (L1 boundary)."""
+    from sgg_b200 import ops
+    out = {}
+
+    def timeit(fn, reps):
+        fn(); torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record(); torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    # ---- cfg5
+    try:
+        g = synth.synth_graph(8, 64, 2000, 1239)
+        N, E = g['boxes'].shape[0], g['rel_inds'].shape[0]
+        of, ef = synth.synth_l1_feats(N, E, 1239)
+        o, e = torch.from_numpy(of).to(dev), torch.from_numpy(ef).to(dev)
+        rel = torch.from_numpy(np.ascontiguousarray(g['rel_inds'][:, 1:3])).to(dev)
+        plan = ops.L1Plan(dparams, N, E, 4096, 6, dev)
+        ms = timeit(lambda: plan.run(o, e, rel), 10)
+        out['cfg5_dense_stress'] = {'workload': 'L1, 8 img x 64 boxes x 2000 edges, 6 MP iters (N=%d, E=%d)' % (N, E),
+                                    'ms_per_step': ms, 'images_per_s': 8 / (ms * 1e-3),
+                                    'fp32_equiv_tflops': alg_flops_l1(N, E, 512, 4096, 6) / (ms * 1e-3) / 1e12}
+        del plan, o, e
+    except Exception as ex:
+        out['cfg5_dense_stress'] = {'error': str(ex)[:200]}
+    # ---- cfg3
+    try:
+        B = 32
+        g = synth.synth_graph(B, 30, 300, 77)
+        N, E = g['boxes'].shape[0], g['rel_inds'].shape[0]
+        gen = torch.Generator(device=dev).manual_seed(0)
+        fmap = torch.relu(torch.randn(B, 512, 38, 38, device=dev, generator=gen))
+        rois = torch.from_numpy(np.ascontiguousarray(g['rois'])).to(dev)
+        rel = torch.from_numpy(np.ascontiguousarray(g['rel_inds'])).to(dev)
+        P = dict(dparams)
+
+        def u(*shape, fan):
+            return (torch.rand(*shape, device=dev, generator=gen) * 2 - 1) / fan ** 0.5
+        for pre in ('roi_fmap.1.', 'roi_fmap_obj.'):
+            P[pre + '0.weight'] = u(4096, 25088, fan=25088); P[pre + '0.bias'] = u(4096, fan=25088)
+            P[pre + '3.weight'] = u(4096, 4096, fan=4096); P[pre + '3.bias'] = u(4096, fan=4096)
+        gp = synth.synth_params(5, level='l2')
+        for k, v in gp.items():
+            if k.startswith('union_boxes.'):
+                P[k] = torch.from_numpy(v).to(dev)
+        gr = ops.build_graph(rel[:, 1:3], N)
+        st = {}
+
+        def step():
+            geom = ops.union_geom(rois, rel[:, 1:3], P)
+            nf, ef2 = ops.node_edge_features(fmap, rois, rel[:, 1:3], edge_add=geom)
+            h = ops.linear(ef2.view(E, -1), P['roi_fmap.1.0.weight'], P['roi_fmap.1.0.bias'], relu=True)
+            e4096 = ops.linear(h, P['roi_fmap.1.3.weight'], P['roi_fmap.1.3.bias'])
+            hn = ops.linear(nf.view(N, -1), P['roi_fmap_obj.0.weight'], P['roi_fmap_obj.0.bias'], relu=True)
+            n4096 = ops.linear(hn, P['roi_fmap_obj.3.weight'], P['roi_fmap_obj.3.bias'], relu=True)
+            return ops.l1_forward(n4096, e4096, gr, P, 3)
+        step()
+        ms = timeit(step, 5)
+        nf, ef2 = ops.node_edge_features(fmap, rois, rel[:, 1:3])
+        st['fc6_edge_ms'] = timeit(lambda: ops.linear(ef2.view(E, -1), P['roi_fmap.1.0.weight'], P['roi_fmap.1.0.bias'], relu=True), 3)
+        st['roi_align_ms'] = timeit(lambda: ops.node_edge_features(fmap, rois, rel[:, 1:3]), 3)
+        out['cfg3_feature_head'] = {'workload': 'B=32 x 30 boxes x 300 edges: RoIAlign (objects + union boxes) + geometry + '
+                                                'fc6/fc7 (both heads) + L1, fmap [32,512,38,38] resident (N=%d, E=%d)' % (N, E),
+                                    'ms_per_step': ms, 'images_per_s': B / (ms * 1e-3), 'stage_ms': st,
+                                    'fc6_edge_fp32_equiv_tflops': 2.0 * E * 25088 * 4096 / (st['fc6_edge_ms'] * 1e-3) / 1e12}
+        del P, fmap, nf, ef2
+    except Exception as ex:
+        out['cfg3_feature_head'] = {'error': str(ex)[:200]}
+    torch.cuda.empty_cache()
+    return out
 
 
 def measure_train(args, dev, rank, world, dist, barrier):
@@ -500,6 +582,25 @@ def main():
         b.record(); torch.cuda.synchronize()
         stages[name] = a.elapsed_time(b) / reps
 
+    def time_stage_graph(name, fn, reps=20):
+        """one kernel launch per fn() call: ``reps`` launches captured into a CUDA graph, so the figure is device time per
+        launch (an eager loop of ~15 us kernels would measure the host's launch path instead)"""
+        fn(); torch.cuda.synchronize()
+        side = torch.cuda.Stream()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr, stream=side):
+            for _ in range(reps):
+                fn()
+        for _ in range(2):
+            gr.replay()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(5):
+            gr.replay()
+        b.record(); torch.cuda.synchronize()
+        stages[name] = a.elapsed_time(b) / (5 * reps)
+
     obj_rep = ops.linear(d_in[0][0], dparams['obj_unary.weight'], dparams['obj_unary.bias'])
     rel_rep = ops.linear(d_in[0][1], dparams['edge_unary.weight'], dparams['edge_unary.bias'], relu=True)
     k = [0]
@@ -512,38 +613,51 @@ def main():
     time_stage('edge_unary_linear', unary)
     time_stage('message_pass_T%d' % args.iters, lambda: ops.message_pass(rel_rep, obj_rep, g0, dparams, args.iters))
     time_stage('graph_build', lambda: ops.build_graph(d_in[0][2], N))
-    # dominant kernel in isolation: one edge-GRU update (k_tc_gemm<EPI_GRU_EDGE>), inputs = live MP state shapes
-    P_t = ops.linear(obj_rep, dparams['edge_gru.weight_ih'])
-    gates_t = torch.rand(E, 4, device=dev)
-    time_stage('edge_gru_kernel', lambda: ops.edge_gru(rel_rep, P_t, gates_t, g0, dparams), reps=30)
+    # dominant kernels in isolation, ONE launch each, CUDA events on the launching stream (sgg_mp_probe_launch):
+    #   launch B = k_mp_gru: the edge-GRU and node-GRU tiles of one message-passing iteration (T launches per step, + INIT)
+    #   launch A = k_mp_pre: P / Q GEMM tiles + vertex-context gather (T launches per step)
     w_mp = 4 * (2 * (2 * 3 * H * H + 2 * 3 * H) + 4 * (2 * H + 1))
     mp_bytes_iter = 4 * H * 2 * (N + E) + 8 * 2 * E      # SURVEY section 8d bytes_iter without weights
     mp_bytes = args.iters * mp_bytes_iter + w_mp + 4 * H * 2 * (N + E)   # + initial-step read/write
     unary_bytes = 4 * D * E + 4 * (H * D + H) + 4 * H * E
-    # edge-GRU launch: read Eh, write Eh', gates, int32 endpoints, P rows, W_hh (+b): algorithmic (fp32, unsplit)
-    edge_bytes = 4 * H * E * 2 + 16 * E + 8 * E + 4 * 3 * H * N + 4 * (3 * H * H + 6 * H)
-    edge_flops = 2 * E * 3 * H * H + 2 * 2 * 3 * H * E       # hidden-side GEMM + gated gather combine
     gru_flops = 2 * (H * 3 * H) * 2
     mp_flops = (gru_flops // 2) * (N + E) + args.iters * (gru_flops * (N + E) + 8 * H * 2 * E)
     unary_flops = 2 * D * H * E
-    traffic = None
-    tpath = os.path.join(ROOT, 'profiles', 'r01_traffic.json')
-    if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get('edge_gru_kernel_dram_bytes_per_launch')
-    t_edge = stages['edge_gru_kernel'] * 1e-3
-    ach = edge_bytes / t_edge / 1e9
     engine = ops.tc_engine()
-    kname = 'sgg::tc16::k_tc16<EPI_GRU_EDGE>' if engine == 'tc16' else 'sgg::tc::k_tc_gemm<EPI_GRU_EDGE>'
-    roofline = {'bound': 'hbm', 'kernel': '%s (one edge-GRU update, %d launches/step)' % (kname, args.iters),
+    fused = True
+    try:
+        probe = ops.MpProbe(rel_rep, obj_rep, g0, dparams, args.iters)
+        time_stage_graph('mp_launch_B_gru', lambda: probe.launch(2))
+        time_stage_graph('mp_launch_A_pre', lambda: probe.launch(1))
+        time_stage_graph('mp_launch_init', lambda: probe.launch(0))
+    except Exception as ex:                     # tc32 / simt engines: the 7-launch schedule, time its edge-GRU kernel
+        fused = False
+        log('fused probe unavailable (%s); timing the stand-alone edge-GRU kernel' % str(ex)[:80])
+        P_t = ops.linear(obj_rep, dparams['edge_gru.weight_ih'])
+        gates_t = torch.rand(E, 4, device=dev)
+        time_stage('mp_launch_B_gru', lambda: ops.edge_gru(rel_rep, P_t, gates_t, g0, dparams), reps=30)
+    # launch B, algorithmic (fp32, unsplit operands): states read + written, int32 endpoints, the P rows
+    # (edge side) and Q rows + ctx (node side), both GRU weight matrices + biases, gate partials
+    gruB_bytes = (4 * H * 2 * (N + E) + 8 * E + 4 * 3 * H * N * 2 + 4 * H * N + 2 * 4 * (3 * H * H + 6 * H) + 2 * 7 * 16 * (N + E))
+    gruB_flops = 2 * 3 * H * H * (N + E) + 2 * 2 * 3 * H * E           # both GEMMs + the gated gather combine
+    traffic = None
+    tpath = os.path.join(ROOT, 'profiles', 'r02_traffic.json')
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get('k_mp_gru_dram_bytes_per_launch')
+    t_b = stages['mp_launch_B_gru'] * 1e-3
+    mma_tf = 3 * gruB_flops / t_b / 1e12                              # 3 MMA passes per fp32-equivalent flop
+    roofline = {'bound': 'tensor',
+                'kernel': ('sgg::mpf::k_mp_gru (launch B: edge + node GRU tiles of one iteration; %d launches/step + the INIT '
+                           'launch)' % args.iters) if fused else 'edge-GRU kernel of the 7-launch schedule',
                 'engine': engine,
-                'achieved': ach, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': ach / hbm_peak, 'traffic': traffic,
-                'peak_source': peak_src, 'algorithmic_bytes': edge_bytes, 'ms_per_launch': stages['edge_gru_kernel'],
-                'tensor': {'fp32_equiv_tflops': edge_flops / t_edge / 1e12, 'mma_pass_tflops': 3 * edge_flops / t_edge / 1e12,
-                           'bf16_peak_tflops': tf_peak, 'frac_of_bf16_peak_3pass': 3 * edge_flops / t_edge / 1e12 / tf_peak if tf_peak else None,
-                           'note': '3-pass split (3xFP16: kind::f16 at the bf16/fp16 rate; 3xTF32: kind::tf32 at half of it): '
-                                   'every fp32-equivalent flop costs 3 MMA passes'},
-                'note': 'the binding term of this kernel is tensor/operand-ingest, not HBM: its compulsory DRAM traffic is ~13 MB '
-                        '(weights + first touch, everything else L2-resident); see DESIGN.md section 5 and profiles/',
+                'achieved': mma_tf, 'peak': tf_peak, 'unit': 'TFLOP/s', 'frac': mma_tf / tf_peak if tf_peak else None,
+                'traffic': traffic, 'peak_source': peak_src,
+                'algorithmic_flops': gruB_flops, 'algorithmic_bytes': gruB_bytes, 'ms_per_launch': stages['mp_launch_B_gru'],
+                'note': 'achieved = fp16 MMA-pass TFLOP/s (3 tcgen05 passes per fp32-equivalent flop: the 3xFP16 operand split '
+                        'that buys fp32-grade results) against the measured dense bf16/fp16 peak; the compulsory DRAM traffic '
+                        'of the launch is ~7 MB (weights + first touch, states are L2-resident), so HBM is not the binding term',
+                'hbm': {'achieved_gbs': gruB_bytes / t_b / 1e9, 'peak_gbs': hbm_peak, 'frac': gruB_bytes / t_b / 1e9 / hbm_peak},
+                'fp32_equiv_tflops': gruB_flops / t_b / 1e12,
                 'stage_ms': stages,
                 'stage_tflops_fp32_equiv': {'edge_unary_linear': unary_flops / (stages['edge_unary_linear'] * 1e-3) / 1e12,
                                             'message_pass': mp_flops / (stages['message_pass_T%d' % args.iters] * 1e-3) / 1e12},
@@ -553,7 +667,8 @@ def main():
                                'achieved_gbs': alg_bytes_l1(N, E, H, D, args.iters) / (ms_step * 1e-3) / 1e9,
                                'frac_of_hbm_peak': alg_bytes_l1(N, E, H, D, args.iters) / (ms_step * 1e-3) / 1e9 / hbm_peak,
                                'algorithmic_flops': alg_flops_l1(N, E, H, D, args.iters),
-                               'fp32_equiv_tflops': alg_flops_l1(N, E, H, D, args.iters) / (ms_step * 1e-3) / 1e12}}
+                               'fp32_equiv_tflops': alg_flops_l1(N, E, H, D, args.iters) / (ms_step * 1e-3) / 1e12,
+                               'mma_pass_tflops_frac_of_peak': 3 * alg_flops_l1(N, E, H, D, args.iters) / (ms_step * 1e-3) / 1e12 / tf_peak if tf_peak else None}}
 
     # ---- CPU baseline: the reference's CPU path (oracle port), bounded sample, rank 0 only at N=1
     log('stage timings done: %s' % {k: round(v, 4) for k, v in stages.items()})
@@ -562,6 +677,10 @@ def main():
         cpu = cpu_baseline_subprocess(args)
         log('cpu baseline done')
 
+    other = None
+    if world == 1 and not args.no_other_configs:
+        other = measure_other_configs(args, dev, dparams)
+        log('other configs: %s' % {k: round(v.get('ms_per_step', -1), 3) for k, v in other.items()})
     train = run_train()
     images = args.batch * world
     line = {'metric': 'images/sec (PredCls, 3 MP iters)', 'value': images / (ms_step * 1e-3), 'unit': 'images/s',
@@ -574,7 +693,7 @@ def main():
                     'api': 'sgg_b200.runner.ImpL1Runner.submit/wait (3 in-flight slots, pinned host buffers)'},
             'gpu_launches': int(launches_per_step) * args.steps,
             'gpu_launches_per_step': int(launches_per_step),
-            'run': run_info, 'roofline': roofline, 'cpu_baseline': cpu, 'train_step': train}
+            'run': run_info, 'roofline': roofline, 'cpu_baseline': cpu, 'train_step': train, 'other_configs': other}
     if args.workload == 'train':
         # headline = BASELINE.json configs[3]; the L1 forward numbers stay in the line under 'l1_forward'
         line['l1_forward'] = {k: line[k] for k in ('value', 'ms_per_step', 'e2e', 'gpu_launches_per_step')}

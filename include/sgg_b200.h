@@ -246,6 +246,12 @@ SGG_API int sgg_bn_train_backward(const float *x, const float *dy, int M, int C,
  * (first maximum, where the reference's max-pool backward sends the gradient); backward scatters dy to dx [E,4,C]. */
 SGG_API int sgg_max4_forward(const float *x, int E, int C, float *y, unsigned char *idx, void *stream);
 SGG_API int sgg_max4_backward(const float *dy, const unsigned char *idx, int E, int C, float *dx, void *stream);
+/* Elementwise / small-reduction helpers of the training path (no ATen on it):
+ * sgg_bcast_add: out[r,s] = pools[r,s] + geom[r], r < rows = E*C, s < S = 49 (lib/get_union_boxes.py:101);
+ * sgg_relu_backward: dx = y > 0 ? dy : 0;  sgg_group_sum: out[g] = sum_s x[g,s] (e.g. the 7x7 taps of fc6's weight). */
+SGG_API int sgg_bcast_add(const float *pools, const float *geom, long long rows, int S, float *out, void *stream);
+SGG_API int sgg_relu_backward(const float *dy, const float *y, long long n, float *dx, void *stream);
+SGG_API int sgg_group_sum(const float *x, long long groups, int S, float *out, void *stream);
 
 /* ---- a9: node_edge_features (rel_model_base.py:245-260): torchvision
  * roi_align(aligned=False, sampling_ratio=2, 7x7, scale 1/16) for objects and

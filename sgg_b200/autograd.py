@@ -29,7 +29,7 @@ class _LinearFn(torch.autograd.Function):
         x, weight, y = ctx.saved_tensors
         dy = dy.contiguous()
         if ctx.relu:
-            dy = dy * (y > 0)                       # elementwise ReLU mask
+            dy = ops.relu_backward(dy, y)           # elementwise ReLU mask (CUDA)
         dx, dw, db = ops.linear_backward(x, weight, dy, ctx.needs_input_grad[0], ctx.needs_input_grad[1],
                                          ctx.has_bias and ctx.needs_input_grad[2])
         return dx, dw, db, None
@@ -153,6 +153,56 @@ def union_geom(rois, union_inds, conv, training):
     return relu_bn_train(x, bn2)
 
 
+class _BcastAddFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pools, geom):
+        ctx.S = pools.shape[2] * pools.shape[3]
+        return ops.bcast_add(pools, geom)
+
+    @staticmethod
+    def backward(ctx, d):
+        d = d.contiguous()
+        dgeom = ops.group_sum(d.view(d.shape[0], d.shape[1], ctx.S), ctx.S) if ctx.needs_input_grad[1] else None
+        return (d if ctx.needs_input_grad[0] else None), dgeom
+
+
 def broadcast_add(union_pools, geom):
-    """union_pools [E,C,7,7] + geom [E,C] (lib/get_union_boxes.py:101)."""
-    return union_pools + geom[:, :, None, None]
+    """union_pools [E,C,7,7] + geom [E,C] (lib/get_union_boxes.py:101), CUDA forward and backward."""
+    return _BcastAddFn.apply(union_pools.contiguous(), geom.contiguous())
+
+
+class _FcBroadcastFn(torch.autograd.Function):
+    """relu(fc6(pools + geom broadcast over the 7x7 positions)) — rel_model_stanford.py:100-101 in training mode, where
+    only ``geom`` (the union-box geometry embedding) needs a gradient on the input side.  The generic backward would form
+    dX [E, C*49] = dY W (a 2 TFLOP GEMM at 9600 edges) just to sum it over the 49 positions; since the sum commutes,
+    dgeom = dY (sum_p W[:, c*49 + p]) is a [E,4096] x [4096,C] GEMM, 49x cheaper, exact up to fp32 reassociation."""
+
+    @staticmethod
+    def forward(ctx, pools, geom, weight, bias):
+        E = pools.shape[0]
+        x = ops.bcast_add(pools, geom).view(E, -1)
+        y = ops.linear(x, weight, bias, relu=True)
+        ctx.S = pools.shape[2] * pools.shape[3]
+        ctx.save_for_backward(x, weight, y)
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, y = ctx.saved_tensors
+        dym = ops.relu_backward(dy.contiguous(), y)
+        _, dw, db = ops.linear_backward(x, weight, dym, False, ctx.needs_input_grad[2], ctx.has_bias and ctx.needs_input_grad[3])
+        dgeom = None
+        if ctx.needs_input_grad[1]:
+            Nout, K = weight.shape
+            Cc = K // ctx.S
+            wsum = ops.group_sum(weight.detach().view(Nout, Cc, ctx.S), ctx.S)       # [Nout, C]
+            dgeom = ops.matmul_nn(dym, wsum)                                         # [E, C] = dym [E,Nout] @ wsum [Nout,C]
+        return None, dgeom, dw, db
+
+
+def fc_broadcast(pools, geom, weight, bias):
+    """relu(linear(pools + geom[:, :, None, None], weight, bias)); ``pools`` must not require a gradient."""
+    if pools.requires_grad and torch.is_grad_enabled():
+        return linear(broadcast_add(pools, geom).reshape(pools.shape[0], -1), weight, bias, relu=True)
+    return _FcBroadcastFn.apply(pools.contiguous(), geom.contiguous(), weight, bias)

@@ -148,6 +148,38 @@ __global__ void k_max4_bwd(const float *__restrict__ dy, const unsigned char *__
   }
 }
 
+// out[e, c, s] = pools[e, c, s] + geom[e, c]   (lib/get_union_boxes.py:101, the broadcast add of the training path)
+__global__ void k_bcast_add(const float4 *__restrict__ pools, const float *__restrict__ geom, size_t n4, int S4,
+                            float4 *__restrict__ out) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 v = pools[i];
+    // element 4i..4i+3 of [E*C, S]: row = (4i + k) / S
+    const size_t base = 4 * i;
+    const int S = S4;
+    const float g0 = geom[base / S], g1 = geom[(base + 1) / S], g2 = geom[(base + 2) / S], g3 = geom[(base + 3) / S];
+    v.x += g0; v.y += g1; v.z += g2; v.w += g3;
+    out[i] = v;
+  }
+}
+// dx = dy where y > 0 else 0   (ReLU backward from the saved output)
+__global__ void k_relu_bwd(const float4 *__restrict__ dy, const float4 *__restrict__ y, size_t n4, float4 *__restrict__ dx) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 d = dy[i], v = y[i];
+    dx[i] = make_float4(v.x > 0.f ? d.x : 0.f, v.y > 0.f ? d.y : 0.f, v.z > 0.f ? d.z : 0.f, v.w > 0.f ? d.w : 0.f);
+  }
+}
+// out[g] = sum_{s < S} x[g * S + s]: one warp per 32 groups would be uncoalesced; here a warp walks one group at a time
+__global__ void k_group_sum(const float *__restrict__ x, size_t groups, int S, float *__restrict__ out) {
+  const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  for (size_t g = warp; g < groups; g += nwarps) {
+    float s = 0.f;
+    for (int k = lane; k < S; k += 32) s += x[g * S + k];
+    s = sgg_warp_sum(s);
+    if (lane == 0) out[g] = s;
+  }
+}
+
 static int ew_grid(size_t n) {
   size_t b = (n + 255) / 256;
   const size_t cap = (size_t)sgg_num_sms() * 8;
@@ -232,5 +264,32 @@ extern "C" int sgg_max4_backward(const float *dy, const unsigned char *idx, int 
   const size_t n = (size_t)E * C;
   sgg::k_max4_bwd<<<sgg::ew_grid(n), 256, 0, (cudaStream_t)stream>>>(dy, idx, n, C, dx);
   SGG_RETURN_IF_LAUNCH_FAILED("k_max4_bwd");
+  return 0;
+}
+
+// out [E,C,S] = pools [E,C,S] + geom [E,C] broadcast over the S = 7 x 7 positions (E*C*S % 4 == 0)
+extern "C" int sgg_bcast_add(const float *pools, const float *geom, long long rows, int S, float *out, void *stream) {
+  if (rows <= 0 || S <= 0) return 0;
+  const size_t n = (size_t)rows * S;
+  if (!pools || !geom || !out || (n & 3)) return sgg_set_err(SGG_E_BADARG, "bcast_add: bad argument");
+  sgg::k_bcast_add<<<sgg::ew_grid(n / 4), 256, 0, (cudaStream_t)stream>>>((const float4 *)pools, geom, n / 4, S, (float4 *)out);
+  SGG_RETURN_IF_LAUNCH_FAILED("k_bcast_add");
+  return 0;
+}
+extern "C" int sgg_relu_backward(const float *dy, const float *y, long long n, float *dx, void *stream) {
+  if (n <= 0) return 0;
+  if (!dy || !y || !dx || (n & 3)) return sgg_set_err(SGG_E_BADARG, "relu_backward: bad argument");
+  sgg::k_relu_bwd<<<sgg::ew_grid((size_t)n / 4), 256, 0, (cudaStream_t)stream>>>((const float4 *)dy, (const float4 *)y, (size_t)n / 4,
+                                                                               (float4 *)dx);
+  SGG_RETURN_IF_LAUNCH_FAILED("k_relu_bwd");
+  return 0;
+}
+// out [groups] = sum over S consecutive elements of x [groups, S]
+extern "C" int sgg_group_sum(const float *x, long long groups, int S, float *out, void *stream) {
+  if (groups <= 0 || S <= 0) return 0;
+  if (!x || !out) return sgg_set_err(SGG_E_BADARG, "group_sum: null pointer");
+  const size_t threads = (size_t)groups * 32;
+  sgg::k_group_sum<<<sgg::ew_grid(threads), 256, 0, (cudaStream_t)stream>>>(x, (size_t)groups, S, out);
+  SGG_RETURN_IF_LAUNCH_FAILED("k_group_sum");
   return 0;
 }

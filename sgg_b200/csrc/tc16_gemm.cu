@@ -638,13 +638,18 @@ static LinPlan plan_linear(int M, int Nout, int K, bool allow_split) {
   const int rows = (M + BM - 1) / BM;
   LinPlan best{Nout <= 64 ? 64 : 128, 1, 0, 0};
   double best_cost = 1e30;
-  const int widths[2] = {128, 64};
-  for (int wi = 0; wi < 2; ++wi) {
+  // 96-wide tiles (plain tiling only): an option when 128-wide tiles leave half of the SMs idle, e.g. the cfg2 edge-unary
+  // GEMM (19 row blocks): 4 x 19 = 76 CTAs at 128, 6 x 19 = 114 at 96.  The main loop is bound by shared-memory bandwidth
+  // (3 MMA passes re-read the operand tiles), so time per k-block scales with the bytes a CTA moves, ~(128 + ncol).
+  static const int allow96 = getenv("SGG_TC16_W96") ? atoi(getenv("SGG_TC16_W96")) : 1;
+  const int widths[3] = {128, 96, 64};
+  for (int wi = 0; wi < 3; ++wi) {
     const int ncol = widths[wi];
     if (ncol == 128 && Nout <= 64) continue;
+    if (ncol == 96 && (!allow96 || Nout <= 128)) continue;
     const long tiles = (long)((Nout + ncol - 1) / ncol) * rows;
     const double unit = (128.0 + ncol) / 256.0;        // time of one chunk ~ bytes staged per k-block
-    const int max_s = allow_split ? (chunks < 32 ? chunks : 32) : 1;
+    const int max_s = (allow_split && ncol != 96) ? (chunks < 32 ? chunks : 32) : 1;
     for (int s = 1; s <= max_s; ++s) {
       const int ch_per = (chunks + s - 1) / s;
       const int s_eff = (chunks + ch_per - 1) / ch_per;
@@ -663,7 +668,7 @@ static LinPlan plan_linear(int M, int Nout, int K, bool allow_split) {
     // (9600 x 25088 -> 4096: 411 MB of fp16 [hi|lo] weights) ran 9.32 ms stream-K vs 6.66 ms with plain launch-order
     // tiling (profiles/r02_fc6_tile_order.md), where a wave walks k in lockstep and reads A and B once per wave.
     const bool b_resident = 4.0 * (double)Nout * (double)K <= 0.5 * (double)l2_bytes();
-    if (allow_split && allow_sk && b_resident && (K % 256) == 0 && tiles > sms) {
+    if (allow_split && allow_sk && ncol != 96 && b_resident && (K % 256) == 0 && tiles > sms) {
       const long W = tiles * chunks;
       const int G = (int)(W < sms ? W : sms);
       const int q = (int)((W + G - 1) / G);
@@ -730,6 +735,7 @@ int linear_planes(const float *x, const float *w_split, const float *b, float *y
   p.kb_per_split = kb_per;
   p.out = splits > 1 ? ws : y;
   if (pl.ncol == 64) rc = launch<1, 64, 1, EPI_LINEAR>(p, sg, (Nout + 63) / 64, splits, st);
+  else if (pl.ncol == 96) rc = launch<1, 96, 1, EPI_LINEAR>(p, sg, (Nout + 95) / 96, splits, st);
   else rc = launch<1, 128, 1, EPI_LINEAR>(p, sg, (Nout + 127) / 128, splits, st);
   if (rc) return rc;
   if (splits > 1) {

@@ -249,12 +249,20 @@ class RelModelStanford(RelModelBase):
     def predict(self, node_feat, edge_feat, rel_inds, rois, im_sizes):
         """rel_model_stanford.py:97-107."""
         E = edge_feat.shape[0]
-        edge_feat = self.union_boxes(edge_feat.view(E, -1, self.pool_sz, self.pool_sz), rois, rel_inds[:, 1:], im_sizes)
+        ub = self.union_boxes
+        pools = edge_feat.view(E, -1, self.pool_sz, self.pool_sz)
+        if (self.training and isinstance(ub, UnionBoxesAndFeats) and not ub.concat and ub.use_feats
+                and not (pools.requires_grad and torch.is_grad_enabled())):
+            # training: pools + broadcast(geom) feeds fc6 directly; the fused op's backward sends only the 7x7-summed
+            # gradient to the geometry branch (49x cheaper than materialising dX of fc6, autograd.fc_broadcast)
+            geom = ub.geometry(rois, rel_inds[:, 1:])
+            return self._predict_pooled(node_feat, pools, rel_inds, geom=geom)
+        edge_feat = ub(pools, rois, rel_inds[:, 1:], im_sizes)
         return self._predict_pooled(node_feat, edge_feat, rel_inds)
 
-    def _predict_pooled(self, node_feat, edge_feat, rel_inds):
+    def _predict_pooled(self, node_feat, edge_feat, rel_inds, geom=None):
         """rel_model_stanford.py:100-107: everything after ``self.union_boxes`` (edge_feat already carries the
-        union-box geometry)."""
+        union-box geometry, or ``geom`` [E,C] is still to be broadcast-added to it)."""
         E = edge_feat.shape[0]
         fo, fe = self.roi_fmap_obj, self.roi_fmap[1]
         drop = self.training
@@ -262,7 +270,10 @@ class RelModelStanford(RelModelBase):
         n = F.dropout(n, 0.5, drop)
         n = K.linear(n, fo[3].weight, fo[3].bias, relu=True)
         n = F.dropout(n, 0.5, drop)
-        e = K.linear(edge_feat.reshape(E, -1), fe[0].weight, fe[0].bias, relu=True)
+        if geom is not None:
+            e = K.fc_broadcast(edge_feat, geom, fe[0].weight, fe[0].bias)
+        else:
+            e = K.linear(edge_feat.reshape(E, -1), fe[0].weight, fe[0].bias, relu=True)
         e = F.dropout(e, 0.5, drop)
         e = K.linear(e, fe[3].weight, fe[3].bias, relu=False)
         n = K.linear(n, self.obj_unary.weight, self.obj_unary.bias)

@@ -404,6 +404,36 @@ def max4_backward(dy, idx):
     return dx
 
 
+def bcast_add(pools, geom):
+    """pools [E,C,P,P] + geom [E,C] broadcast over the P x P positions (lib/get_union_boxes.py:101)."""
+    lib = _lib.load()
+    pools = _f32(pools, 'pools'); geom = _f32(geom, 'geom', (pools.shape[0], pools.shape[1]))
+    out = torch.empty_like(pools)
+    S = pools.shape[2] * pools.shape[3]
+    check(lib.sgg_bcast_add(_ptr(pools), _ptr(geom), pools.shape[0] * pools.shape[1], S, _ptr(out), _stream()), 'sgg_bcast_add')
+    return out
+
+
+def relu_backward(dy, y):
+    lib = _lib.load()
+    dy = _f32(dy, 'dy'); y = _f32(y, 'y', tuple(dy.shape))
+    if dy.numel() % 4:
+        return dy * (y > 0)
+    dx = torch.empty_like(dy)
+    check(lib.sgg_relu_backward(_ptr(dy), _ptr(y), dy.numel(), _ptr(dx), _stream()), 'sgg_relu_backward')
+    return dx
+
+
+def group_sum(x, S):
+    """x [..., S] contiguous -> sum over the last S elements, shape x.shape[:-1]"""
+    lib = _lib.load()
+    x = _f32(x, 'x')
+    assert x.shape[-1] == S
+    out = torch.empty(x.shape[:-1], dtype=torch.float32, device=x.device)
+    check(lib.sgg_group_sum(_ptr(x), out.numel(), S, _ptr(out), _stream()), 'sgg_group_sum')
+    return out
+
+
 def geom_weights(params, prefix='union_boxes.conv.'):
     gw = GeomWeights()
     keep = []
@@ -533,6 +563,25 @@ def _tc32_linear(x, w_split, M, Nout, K, out=None):
     check(lib.sgg_tc32_linear_forward(_ptr(x), _ptr(w_split), None, _ptr(y), M, Nout, K, 0, _ptr(ws), nb, _stream()),
           'sgg_tc32_linear_forward')
     return y
+
+
+def matmul_nn(a, b):
+    """a [M,K] @ b [K,N] (fp32-grade): 3xTF32 tensor cores through a transposed, split copy of b when large, else the
+    fp32 SIMT tiles."""
+    lib = _lib.load()
+    a = _f32(a, 'a'); b = _f32(b, 'b')
+    M, K = a.shape
+    N = b.shape[1]
+    if _TC_BWD['enabled'] and _use_tc() and M >= _TC_BWD['min_rows'] and K % 4 == 0 and K >= 64 and N >= 64:
+        bT = _transpose(b, K, N, N, K, split=True)                            # [2, N, K]
+        return _tc32_linear(a, bT, M, N, K)
+    out = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    # dX-type SIMT GEMM: out = a @ b with b [K, N] read "column-wise" (the dx route of sgg_linear_backward: dy W)
+    nbytes = lib.sgg_linear_backward_workspace_bytes(M, K, N)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=a.device)
+    check(lib.sgg_linear_backward_ex(None, _ptr(b), _ptr(a), M, K, N, _ptr(out), None, None, 0, _ptr(ws), nbytes, _stream()),
+          'sgg_linear_backward_ex')
+    return out
 
 
 def linear_backward(x, weight, dy, need_dx=True, need_dw=True, need_db=True):
