@@ -37,7 +37,9 @@ _T0 = time.time()
 
 
 def log(msg):
-    """progress line on stderr (stdout carries exactly one JSON line)"""
+    """progress line on stderr (stdout carries exactly one JSON line); rank 0 only"""
+    if os.environ.get('RANK', '0') != '0':
+        return
     sys.stderr.write('[bench %7.1fs] %s\n' % (time.time() - _T0, msg)); sys.stderr.flush()
 
 
@@ -542,6 +544,22 @@ def main():
         e2e_s = float(t.item())
     clocks = sampler.stop() if sampler is not None else None
     log('e2e: %.3f ms/step' % (e2e_s * 1e3 / args.steps))
+    # ---- the box's host->device ceiling: every rank streams a pinned 256 MB buffer with plain cudaMemcpyAsync at the same
+    # time (what the e2e numbers above are bounded by: one PCIe link per GPU, shared host memory / root complexes)
+    hbuf = torch.empty(64 << 20, dtype=torch.float32).pin_memory()
+    dbuf = torch.empty(64 << 20, dtype=torch.float32, device=dev)
+    dbuf.copy_(hbuf, non_blocking=True)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(4):
+        dbuf.copy_(hbuf, non_blocking=True)
+    torch.cuda.synchronize()
+    h2d_plain = 4 * hbuf.numel() * 4 / (time.perf_counter() - t0) / 1e9
+    if dist is not None:
+        t = torch.tensor([h2d_plain], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        h2d_plain = float(t.item())
+    del hbuf, dbuf
 
     # ---- BASELINE.json configs[3]: the train step with the gradient all-reduce (every rank takes part).  It runs LAST
     # (after rank 0 has taken its single-GPU stage timings) so that a failure in it can never cost the headline line.
@@ -690,6 +708,10 @@ def main():
             'e2e': {'value': images * args.steps / e2e_s, 'unit': 'images/s', 'h2d_bytes_per_step': h2d_bytes,
                     'd2h_bytes_per_step': d2h_bytes, 'ms_per_step': e2e_s * 1e3 / args.steps,
                     'h2d_gbs_per_rank': h2d_bytes * args.steps / e2e_s / 1e9,
+                    'h2d_plain_memcpy_gbs_per_rank': h2d_plain,
+                    'h2d_note': 'h2d_plain_memcpy = all ranks copying a pinned 256 MB buffer concurrently with cudaMemcpyAsync '
+                                '(slowest rank): the host->device ceiling of this box at this rank count; the e2e step is '
+                                'bound by it (%.0f %% of it reached)' % (100.0 * h2d_bytes * args.steps / e2e_s / 1e9 / h2d_plain),
                     'api': 'sgg_b200.runner.ImpL1Runner.submit/wait (3 in-flight slots, pinned host buffers)'},
             'gpu_launches': int(launches_per_step) * args.steps,
             'gpu_launches_per_step': int(launches_per_step),

@@ -253,6 +253,20 @@ SGG_API int sgg_bcast_add(const float *pools, const float *geom, long long rows,
 SGG_API int sgg_relu_backward(const float *dy, const float *y, long long n, float *dx, void *stream);
 SGG_API int sgg_group_sum(const float *x, long long groups, int S, float *out, void *stream);
 
+/* ---- a10 / f2: the frozen VGG16 conv stack (rel_model_base.py:184, :310-321) as tcgen05 implicit GEMMs (3xFP16) ----
+ * Activations between layers are NHWC fp16 planes [hi | lo * 2^11] (2 * B*H*W*C halves: hi plane then lo plane).
+ * sgg_conv_weight_planes: w [Cout,Cin,3,3] fp32 -> planes in implicit-GEMM order [Cout][tap][Cin] (2 * Cout*9*Cin halves);
+ * sgg_conv3x3_first: img [B,3,H,W] fp32 NCHW -> relu(conv(img)) planes, Cout = 64 (SIMT, K = 27);
+ * sgg_conv3x3_tc: 3x3 / pad 1 / stride 1 conv + bias (+ReLU) (+fused 2x2 max-pool, H and W even) -> planes of
+ *   [B,Ho,Wo,Cout], or fp32 NCHW [B,Cout,Ho,Wo] when out_f32_nchw != NULL (the fmap layout of the reference).
+ *   Cin % 64 == 0, Cout % 64 == 0.  sgg_conv_overflow: sticky fp16 range flag of the emitted activations. */
+SGG_API int sgg_conv_weight_planes(const float *w, int Cout, int Cin, void *planes, void *stream);
+SGG_API int sgg_conv3x3_first(const float *img, const float *w, const float *bias, int B, int H, int W, int Cout,
+                      void *out_planes, void *stream);
+SGG_API int sgg_conv3x3_tc(const void *in_planes, const void *w_planes, const float *bias, int B, int H, int W, int Cin,
+                   int Cout, int relu, int pool, void *out_planes, float *out_f32_nchw, void *stream);
+SGG_API int sgg_conv_overflow(int reset);
+
 /* ---- a9: node_edge_features (rel_model_base.py:245-260): torchvision
  * roi_align(aligned=False, sampling_ratio=2, 7x7, scale 1/16) for objects and
  * for union boxes computed on the fly from (rois, union_inds).

@@ -80,6 +80,11 @@ SIGNATURES = {
     'sgg_tc_debug_timing': (C.c_int, [C.POINTER(C.c_longlong), C.c_int]),
     'sgg_mp_probe_launch': (C.c_int, [C.c_int, c_f, c_f, C.c_void_p, C.POINTER(MpWeights), C.c_int, C.c_int, C.c_int, C.c_int,
                                       c_f, c_f, C.c_void_p, C.c_size_t, C.c_void_p]),
+    'sgg_conv_weight_planes': (C.c_int, [c_f, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    'sgg_conv3x3_first': (C.c_int, [c_f, c_f, c_f, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    'sgg_conv3x3_tc': (C.c_int, [C.c_void_p, C.c_void_p, c_f, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                 C.c_void_p, c_f, C.c_void_p]),
+    'sgg_conv_overflow': (C.c_int, [C.c_int]),
     'sgg_tc16_overflow': (C.c_int, [C.c_int]),
     'sgg_bn_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int]),
     'sgg_bn_train_forward': (C.c_int, [c_f, C.c_int, C.c_int, C.c_int, c_f, c_f, c_f, c_f, C.c_float, C.c_float, c_f, c_f,

@@ -149,8 +149,7 @@ class RelModelBase(nn.Module):
             imgs.append(x[i].to(dev).squeeze())
             org_sizes.append(tuple(x[i].shape[-2:]))
         images, targets = self.detector.transform(imgs, targets)
-        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):     # fp32 parity with the reference (1e-4)
-            fmaps = self.detector.backbone(images.tensors)
+        fmaps = self._backbone(images.tensors)
         if isinstance(fmaps, torch.Tensor):
             fmaps = OrderedDict([('0', fmaps)])
         if self.mode != 'sgdet':
@@ -180,6 +179,22 @@ class RelModelBase(nn.Module):
         result.fmap = fmaps[list(fmaps.keys())[-1]]
         result.rois = torch.cat((result.im_inds.float()[:, None], result.rm_box_priors), 1)
         return result
+
+    def _backbone(self, x):
+        """The frozen conv stack (rel_model_base.py:184).  With the 3xFP16 tensor-core engine active, the VGG16 stack
+        runs as tcgen05 implicit GEMMs (csrc/conv_tc.cu, fp32-grade results); otherwise torchvision / cuDNN in fp32
+        (TF32 off: the 1e-4 parity bar).  SGG_BACKBONE=cudnn forces the library path."""
+        import os
+        bb = self.detector.backbone
+        if (x.is_cuda and os.environ.get('SGG_BACKBONE', 'tc') != 'cudnn' and isinstance(bb, nn.Sequential)
+                and ops._use_tc() and ops.tc_engine() == 'tc16'):
+            layers = getattr(self, '_vgg_layers', None)
+            if layers is None:
+                layers = self._vgg_layers = ops.vgg_layers(bb) or False
+            if layers and x.shape[2] % 16 == 0 and x.shape[3] % 16 == 0:
+                return ops.vgg_features(x, layers)
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):     # fp32 parity with the reference (1e-4)
+            return bb(x)
 
     def _spatial_scale(self, fmap, im_sizes):
         """MultiScaleRoIAlign's scale inference: 2 ** round(log2(feature size / padded-input size))."""

@@ -231,6 +231,90 @@ def message_pass(rel_rep, obj_rep, graph, params, mp_iter=3, save_states=False):
     return V, Eo
 
 
+# ---- VGG16 conv stack on tensor cores (csrc/conv_tc.cu) -------------------------------------------------------
+_CONV_W_CACHE = {}
+
+
+def conv_weight_planes(w):
+    """[Cout,Cin,3,3] fp32 -> fp16 [hi | lo] planes in implicit-GEMM order, cached per (tensor object, version)."""
+    key = id(w)
+    ver = (w._version, w.data_ptr(), tuple(w.shape))
+    hit = _CONV_W_CACHE.get(key)
+    if hit is not None and hit[0] == ver and hit[2]() is w:
+        return hit[1]
+    wc = _f32(w, 'conv weight')
+    Cout, Cin = wc.shape[0], wc.shape[1]
+    out = torch.empty((2, Cout, 9, Cin), dtype=torch.float16, device=wc.device)
+    check(_lib.load().sgg_conv_weight_planes(_ptr(wc), Cout, Cin, _ptr(out), _stream()), 'sgg_conv_weight_planes')
+    if len(_CONV_W_CACHE) > 64:
+        _CONV_W_CACHE.clear()
+    _CONV_W_CACHE[key] = (ver, out, weakref.ref(w))
+    return out
+
+
+def vgg_layers(features):
+    """torchvision VGG ``features`` Sequential (Conv2d 3x3 pad 1, ReLU, MaxPool2d(2,2)) -> [(weight, bias, pool_after)],
+    or None if the module is not of that form."""
+    import torch.nn as nn
+    mods = list(features.children())
+    out, i = [], 0
+    while i < len(mods):
+        m = mods[i]
+        if not (isinstance(m, nn.Conv2d) and m.kernel_size == (3, 3) and m.padding == (1, 1) and m.stride == (1, 1)
+                and m.dilation == (1, 1) and m.groups == 1 and m.bias is not None):
+            return None
+        if i + 1 >= len(mods) or not isinstance(mods[i + 1], nn.ReLU):
+            return None
+        i += 2
+        pool = False
+        if i < len(mods) and isinstance(mods[i], nn.MaxPool2d):
+            mp = mods[i]
+            if not (mp.kernel_size in (2, (2, 2)) and mp.stride in (2, (2, 2)) and mp.padding in (0, (0, 0)) and not mp.ceil_mode):
+                return None
+            pool = True
+            i += 1
+        out.append((m.weight, m.bias, pool))
+    if not out or out[0][0].shape[1] != 3 or out[0][0].shape[0] != 64 or out[0][2]:
+        return None
+    if any(w.shape[1] % 64 or w.shape[0] % 64 for w, _, _ in out[1:]):
+        return None
+    return out
+
+
+def vgg_features(images, layers):
+    """images [B,3,H,W] fp32 (normalised, padded: GeneralizedRCNNTransform output) -> fmap [B,Cout,H',W'] fp32 NCHW.
+    ``layers`` from ``vgg_layers``.  Every convolution after the first runs on tcgen05 (3xFP16, fp32-grade)."""
+    lib = _lib.load()
+    x = _f32(images, 'images')
+    B, C3, H, W = x.shape
+    if C3 != 3:
+        raise _lib.SggError('vgg_features: images must be [B,3,H,W]')
+    npool = sum(1 for _, _, p in layers if p)
+    if H % (1 << npool) or W % (1 << npool):
+        raise _lib.SggError('vgg_features: H and W must be multiples of %d' % (1 << npool))
+    dev = x.device
+    w0, b0, _ = layers[0]
+    cur = torch.empty((2, B, H, W, 64), dtype=torch.float16, device=dev)
+    check(lib.sgg_conv3x3_first(_ptr(x), _ptr(_f32(w0, 'w0')), _ptr(_f32(b0, 'b0')), B, H, W, 64, _ptr(cur), _stream()),
+          'sgg_conv3x3_first')
+    h, w_, cin = H, W, 64
+    fmap = None
+    for li, (wt, bs, pool) in enumerate(layers[1:], start=1):
+        cout = wt.shape[0]
+        wp = conv_weight_planes(wt)
+        ho, wo = (h // 2, w_ // 2) if pool else (h, w_)
+        last = li == len(layers) - 1
+        if last:
+            fmap = torch.empty((B, cout, ho, wo), dtype=torch.float32, device=dev)
+            nxt = None
+        else:
+            nxt = torch.empty((2, B, ho, wo, cout), dtype=torch.float16, device=dev)
+        check(lib.sgg_conv3x3_tc(_ptr(cur), _ptr(wp), _ptr(_f32(bs, 'bias')), B, h, w_, cin, cout, 1, 1 if pool else 0,
+                                 _ptr(nxt), _ptr(fmap) if last else None, _stream()), 'sgg_conv3x3_tc')
+        cur, h, w_, cin = nxt, ho, wo, cout
+    return fmap
+
+
 class MpProbe(object):
     """Per-launch timing probe of the fused message-passing schedule (bench.py roofline): runs the whole loop once on a
     private workspace, then ``launch(which)`` re-issues ONE launch of iteration 0 (0 = INIT, 1 = launch A, 2 = launch B)."""
