@@ -284,6 +284,40 @@ def measure_other_configs(args, dev, dparams):
         del P, fmap, nf, ef2
     except Exception as ex:
         out['cfg3_feature_head'] = {'error': str(ex)[:200]}
+    # ---- cfg3 end to end through the drop-in class: forward(batch) with HOST images in, the 5 numpy arrays out
+    try:
+        from sgg_b200 import trainstep
+        from sgg_b200.model import RelModelStanford
+        B = 8
+        torch.manual_seed(0)
+        with torch.device(dev):
+            m = RelModelStanford(train_data=trainstep.FakeData(), mode='sgcls').eval()
+        g = synth.synth_graph(B, 30, 300, 78)
+        imgs = [torch.rand(3, 592, 592).pin_memory() for _ in range(B)]
+        batch = [(imgs, None, 0, torch.from_numpy(np.ascontiguousarray(g['boxes'])), torch.from_numpy(np.ascontiguousarray(g['gt_classes'])),
+                  None, None, None)]
+        with torch.no_grad():
+            res = m(batch)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            reps = 4
+            for _ in range(reps):
+                res = m(batch)
+            torch.cuda.synchronize()
+            dt = (time.perf_counter() - t0) / reps
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            x = torch.rand(B, 3, 608, 608, device=dev)
+            m._backbone(x); a.record(); m._backbone(x); b.record(); torch.cuda.synchronize()
+        out['cfg3_l3_forward_e2e'] = {
+            'workload': 'RelModelStanford(mode=sgcls).forward(batch), eval: %d host images 3x592x592 -> transform -> VGG16 conv '
+                        'stack (tcgen05) -> RoIAlign -> geometry -> fc6/fc7 -> IMP (all %d ordered pairs) -> ranking -> 5 numpy arrays'
+                        % (B, res[3].shape[0]),
+            'ms_per_batch': dt * 1e3, 'images_per_s': B / dt, 'h2d_bytes_per_batch': B * 3 * 592 * 592 * 4,
+            'd2h_bytes_per_batch': int(sum(np.asarray(r).nbytes for r in res)),
+            'backbone_ms': a.elapsed_time(b), 'backbone_fp32_equiv_tflops': 2 * 15.35e9 * (608 / 224) ** 2 * B / (a.elapsed_time(b) * 1e-3) / 1e12}
+        del m, x
+    except Exception as ex:
+        out['cfg3_l3_forward_e2e'] = {'error': '%s: %s' % (type(ex).__name__, str(ex)[:200])}
     torch.cuda.empty_cache()
     return out
 

@@ -145,6 +145,20 @@ SGG_API size_t sgg_tc32_linear_workspace_bytes(int M, int Nout, int K);
 SGG_API int sgg_tc32_linear_forward(const float *x, const float *w_split, const float *b, float *y,
                             int M, int Nout, int K, int relu, void *ws, size_t ws_bytes, void *stream);
 
+/* Scaled 3xFP16 variants (twice the MMA rate of 3xTF32): gradients are far below fp16's normal range, so the gradient
+ * operand is multiplied by an exact power of two taken from its absolute maximum (sgg_pow2_scale: sc[0] = 2^k with
+ * max|x| 2^k in [1024, 2048), sc[1] = 2^-k, device floats, no synchronisation) and the GEMM epilogue multiplies by sc[1].
+ * sgg_bwd_transpose16: mode 0 = fp32 transposed and scaled by sc[0]; mode 1 = fp16 [hi | lo * 2^11] operand planes.
+ * sgg_scale_by: y = sc[0] * x.  sgg_tc16_linear_scaled: y = out_scale[0] * (x w^T), w as fp16 planes; K % 8 == 0. */
+SGG_API size_t sgg_pow2_scale_workspace_bytes(void);
+SGG_API int sgg_pow2_scale(const float *x, long long n, float *sc, void *ws, size_t ws_bytes, void *stream);
+SGG_API int sgg_bwd_transpose16(const float *in, long long ldin, int R, int C, void *out, int Rpad, int mode,
+                        const float *sc, void *stream);
+SGG_API int sgg_scale_by(const float *x, long long n, const float *sc, float *y, void *stream);
+SGG_API size_t sgg_tc16_linear_workspace_bytes(int M, int Nout, int K);
+SGG_API int sgg_tc16_linear_scaled(const float *x, const void *w_split16, float *y, int M, int Nout, int K,
+                           const float *out_scale, void *ws, size_t ws_bytes, void *stream);
+
 /* ---- tensor-core (tcgen05 / TMEM / TMA) variants -----------------------------------------
  * fp32 in, fp32 out, fp32-grade accuracy through a 3-pass operand split.  Two engines:
  *   mode 0 "3xTF32": x = hi + lo (fp32 words, hi = top 19 bits), kind::tf32;     split buffer = 2n floats

@@ -85,6 +85,13 @@ SIGNATURES = {
     'sgg_conv3x3_tc': (C.c_int, [C.c_void_p, C.c_void_p, c_f, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                  C.c_void_p, c_f, C.c_void_p]),
     'sgg_conv_overflow': (C.c_int, [C.c_int]),
+    'sgg_pow2_scale_workspace_bytes': (C.c_size_t, []),
+    'sgg_pow2_scale': (C.c_int, [c_f, C.c_longlong, c_f, C.c_void_p, C.c_size_t, C.c_void_p]),
+    'sgg_bwd_transpose16': (C.c_int, [c_f, C.c_longlong, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, c_f, C.c_void_p]),
+    'sgg_scale_by': (C.c_int, [c_f, C.c_longlong, c_f, c_f, C.c_void_p]),
+    'sgg_tc16_linear_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    'sgg_tc16_linear_scaled': (C.c_int, [c_f, C.c_void_p, c_f, C.c_int, C.c_int, C.c_int, c_f, C.c_void_p, C.c_size_t,
+                                         C.c_void_p]),
     'sgg_tc16_overflow': (C.c_int, [C.c_int]),
     'sgg_bn_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int]),
     'sgg_bn_train_forward': (C.c_int, [c_f, C.c_int, C.c_int, C.c_int, c_f, c_f, c_f, c_f, C.c_float, C.c_float, c_f, c_f,

@@ -312,6 +312,8 @@ __global__ void __launch_bounds__(256) k_conv_first(const float *__restrict__ im
       uint4 hi, lo;
       split2(o[k], o[k + 1], hi.x, lo.x); split2(o[k + 2], o[k + 3], hi.y, lo.y);
       split2(o[k + 4], o[k + 5], hi.z, lo.z); split2(o[k + 6], o[k + 7], hi.w, lo.w);
+      if (f16x2_nonfinite(hi.x) | f16x2_nonfinite(hi.y) | f16x2_nonfinite(hi.z) | f16x2_nonfinite(hi.w))
+        atomicOr(&g_conv_overflow, 1u);
       *reinterpret_cast<uint4 *>(out_hi + off + k) = hi;
       *reinterpret_cast<uint4 *>(out_lo + off + k) = lo;
     }

@@ -2,6 +2,7 @@
 //   C[M,N] (=|+=) A(m,k) * B(n,k),  A(m,k) = a_col ? A[k*lda+m] : A[m*lda+k],  B(n,k) = b_col ? B[k*ldb+n] : B[n*ldb+k]
 //   dX = dY W      : A = dY  (row), B = W (col: reduce over W's rows)
 //   dW += dY^T X   : A = dY  (col), B = X (col), accumulate
+#include <cuda_fp16.h>
 #include "gemm_core.cuh"
 #include "kernels.h"
 
@@ -302,4 +303,127 @@ extern "C" int sgg_tc32_linear_forward(const float *x, const float *w_split, con
   if (sgg_tc32_linear_workspace_bytes(M, Nout, K) > 0 && (!ws || ws_bytes < sgg_tc32_linear_workspace_bytes(M, Nout, K)))
     return sgg_set_err(SGG_E_WORKSPACE, "tc32_linear: workspace too small");
   return sgg::tc32_linear(x, w_split, b, y, M, Nout, K, relu, (float *)ws, (cudaStream_t)stream);
+}
+
+// ---- scaled 3xFP16 variants of the backward building blocks (twice the MMA rate of 3xTF32) -------------------------
+// The 3xFP16 split (x = hi + lo / 2^11, both fp16) is fp32-grade only while |x| stays in fp16's normal range; gradients do
+// not (1e-6 .. 1e-9 is typical).  Multiplying the gradient operand by s = 2^k with max |s dY| in [1024, 2048) is exact in
+// fp32, brings everything within 2^-24 of the maximum into the normal range, and is undone exactly in the GEMM epilogue
+// (out_scale = 1 / s).  The scale lives in device memory: nothing synchronises.
+namespace sgg {
+constexpr int P2_PARTS = 1184;
+__global__ void __launch_bounds__(256) k_absmax_partial(const float *__restrict__ x, size_t n, float *__restrict__ part) {
+  __shared__ float sh[8];
+  float m = 0.f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float v = fabsf(x[i]);
+    if (v < INFINITY) m = fmaxf(m, v);          // NaN / inf do not take part (they poison the product anyway)
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    m = sh[threadIdx.x];
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffu, m, o));
+    if (threadIdx.x == 0) part[blockIdx.x] = m;
+  }
+}
+// sc[0] = s = 2^(10 - floor(log2 amax)), sc[1] = 1 / s; s = 1 when amax == 0
+__global__ void k_pow2_scale(const float *__restrict__ part, int nparts, float *__restrict__ sc) {
+  float m = 0.f;
+  for (int i = threadIdx.x; i < nparts; i += 32) m = fmaxf(m, part[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (threadIdx.x == 0) {
+    int k = 0;
+    if (m > 0.f) {
+      k = 10 - ilogbf(m);
+      k = k > 100 ? 100 : (k < -100 ? -100 : k);
+    }
+    sc[0] = ldexpf(1.0f, k);
+    sc[1] = ldexpf(1.0f, -k);
+  }
+}
+// in [R,C] (row stride ldin) -> out [C,Rpad] (rows >= R zero).  MODE 0: fp32 out scaled by sc[0] (sc nullable = 1);
+// MODE 1: fp16 [hi | lo * 2^11] planes (operand split of the 3xFP16 engine)
+template <int MODE>
+__global__ void __launch_bounds__(256) k_transpose16(const float *__restrict__ in, int ldin, int R, int C, void *__restrict__ out,
+                                                     int Rpad, const float *__restrict__ sc) {
+  __shared__ float tile[32][33];
+  const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const float s = (MODE == 0 && sc != nullptr) ? sc[0] : 1.f;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < R && c < C) ? in[(size_t)r * ldin + c] * s : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (c < C && r < Rpad) {
+      const float v = tile[threadIdx.x][i];
+      if (MODE == 0) {
+        reinterpret_cast<float *>(out)[(size_t)c * Rpad + r] = v;
+      } else {
+        __half *hi = reinterpret_cast<__half *>(out), *lo = hi + (size_t)C * Rpad;
+        const __half h = __float2half_rn(v);
+        hi[(size_t)c * Rpad + r] = h;
+        lo[(size_t)c * Rpad + r] = __float2half_rn((v - __half2float(h)) * 2048.0f);
+      }
+    }
+  }
+}
+// y = x * sc[0] elementwise (A operand of a dX-type GEMM: dY stays row-major, only the scale is applied)
+__global__ void k_scale_by(const float4 *__restrict__ x, size_t n4, const float *__restrict__ sc, float4 *__restrict__ y) {
+  const float s = sc[0];
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 v = x[i];
+    v.x *= s; v.y *= s; v.z *= s; v.w *= s;
+    y[i] = v;
+  }
+}
+}  // namespace sgg
+
+/* sc[0] = 2^k with max|x| * 2^k in [1024, 2048), sc[1] = 2^-k (device floats; ws: sgg_pow2_scale_workspace_bytes()) */
+extern "C" size_t sgg_pow2_scale_workspace_bytes(void) { return sgg::P2_PARTS * sizeof(float); }
+extern "C" int sgg_pow2_scale(const float *x, long long n, float *sc, void *ws, size_t ws_bytes, void *stream) {
+  if (!x || !sc || !ws || n <= 0 || ws_bytes < sgg_pow2_scale_workspace_bytes()) return sgg_set_err(SGG_E_BADARG, "pow2_scale: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int parts = (int)(((size_t)n + 255) / 256 < (size_t)sgg::P2_PARTS ? ((size_t)n + 255) / 256 : (size_t)sgg::P2_PARTS);
+  sgg::k_absmax_partial<<<parts, 256, 0, st>>>(x, (size_t)n, (float *)ws);
+  SGG_RETURN_IF_LAUNCH_FAILED("k_absmax_partial");
+  sgg::k_pow2_scale<<<1, 32, 0, st>>>((const float *)ws, parts, sc);
+  SGG_RETURN_IF_LAUNCH_FAILED("k_pow2_scale");
+  return 0;
+}
+/* in [R,C] (row stride ldin) -> out [C,Rpad]: mode 0 = fp32, multiplied by sc[0] (sc nullable); mode 1 = fp16 [hi | lo] planes */
+extern "C" int sgg_bwd_transpose16(const float *in, long long ldin, int R, int C, void *out, int Rpad, int mode, const float *sc,
+                                   void *stream) {
+  if (!in || !out || R < 0 || C <= 0 || Rpad < R || ldin < C || ldin > 0x7fffffffLL || (mode != 0 && mode != 1))
+    return sgg_set_err(SGG_E_BADARG, "bwd_transpose16: bad argument");
+  dim3 grid((Rpad + 31) / 32, (C + 31) / 32);
+  if (grid.y > 65535) return sgg_set_err(SGG_E_BADARG, "bwd_transpose16: too many columns");
+  if (mode == 0) sgg::k_transpose16<0><<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(in, (int)ldin, R, C, out, Rpad, sc);
+  else sgg::k_transpose16<1><<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(in, (int)ldin, R, C, out, Rpad, nullptr);
+  SGG_RETURN_IF_LAUNCH_FAILED("k_transpose16");
+  return 0;
+}
+extern "C" int sgg_scale_by(const float *x, long long n, const float *sc, float *y, void *stream) {
+  if (!x || !y || !sc || n <= 0 || (n & 3)) return sgg_set_err(SGG_E_BADARG, "scale_by: bad argument");
+  const size_t n4 = (size_t)n / 4;
+  const int blocks = (int)((n4 + 255) / 256 < 2368 ? (n4 + 255) / 256 : 2368);
+  sgg::k_scale_by<<<blocks, 256, 0, (cudaStream_t)stream>>>((const float4 *)x, n4, sc, (float4 *)y);
+  SGG_RETURN_IF_LAUNCH_FAILED("k_scale_by");
+  return 0;
+}
+/* y = out_scale[0] * x w^T on the 3xFP16 engine (w_split16: fp16 [hi | lo] planes [Nout,K]); K % 8 == 0 */
+extern "C" size_t sgg_tc16_linear_workspace_bytes(int M, int Nout, int K) {
+  return sgg::tc16::linear_workspace_floats(M, Nout, K) * sizeof(float);
+}
+extern "C" int sgg_tc16_linear_scaled(const float *x, const void *w_split16, float *y, int M, int Nout, int K,
+                                      const float *out_scale, void *ws, size_t ws_bytes, void *stream) {
+  if ((M > 0 && Nout > 0) && (!x || !w_split16 || !y)) return sgg_set_err(SGG_E_BADARG, "tc16_linear_scaled: null pointer");
+  if (ws && ws_bytes < sgg_tc16_linear_workspace_bytes(M, Nout, K)) return sgg_set_err(SGG_E_WORKSPACE, "tc16_linear_scaled: workspace too small");
+  return sgg::tc16::linear_scaled(x, (const float *)w_split16, y, M, Nout, K, out_scale, (float *)ws, (cudaStream_t)stream);
 }

@@ -54,6 +54,7 @@ struct Params {
   const float *gates;         // GRU_EDGE: [M,4]
   const int *subj, *obj;      // GRU_EDGE
   float *cache;               // GRU: nullable [M,4,H] (r, z, n, gh_n) for the backward pass
+  const float *out_scale;     // LINEAR: nullable device scalar multiplied into the result before bias / ReLU (backward GEMMs)
   __half *out_hi, *out_lo;    // LINEAR: nullable fp16 planes [hi | lo * 2^11] of the final output (consumed via TMA by mp_fused.cu)
   long long *dbg;             // nullable: per-CTA phase timestamps (SGG_TC_TIMING=1, tools/tc16_phases.py)
 };
@@ -324,6 +325,7 @@ k_tc16(Params p, const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           for (int cc = 0; cc < 4; ++cc) {
             v[cc] = acc[c0 + cc];
             if (!partial) {
+              if (p.out_scale != nullptr) v[cc] *= __ldg(p.out_scale);
               if (p.bias != nullptr && j + cc < p.Nout) v[cc] += __ldg(p.bias + j + cc);
               if (p.relu) v[cc] = fmaxf(v[cc], 0.f);
             }
@@ -509,10 +511,11 @@ __global__ void __launch_bounds__(256) k_tc16_split(const float *__restrict__ w,
 // split-K reducer: y = act(sum_z part[z] + bias), fixed summation order
 __global__ void k_tc16_splitk_reduce(const float *__restrict__ part, int splits, size_t mn, int Nout,
                                      const float *__restrict__ bias, int relu, float *__restrict__ y,
-                                     __half *__restrict__ y_hi, __half *__restrict__ y_lo) {
+                                     __half *__restrict__ y_hi, __half *__restrict__ y_lo, const float *__restrict__ out_scale) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < mn; i += (size_t)gridDim.x * blockDim.x) {
     float s = 0.f;
     for (int z = 0; z < splits; ++z) s += part[(size_t)z * mn + i];
+    if (out_scale != nullptr) s *= __ldg(out_scale);
     if (bias != nullptr) s += __ldg(bias + (int)(i % Nout));
     if (relu) s = fmaxf(s, 0.f);
     y[i] = s;
@@ -529,7 +532,8 @@ __global__ void k_tc16_splitk_reduce(const float *__restrict__ part, int splits,
 // Partition arithmetic mirrors k_tc16 (lo_c = c*W/G).
 __global__ void k_tc16_streamk_reduce(const float *__restrict__ part, int W, int C, int G, int maxseg, int col_tiles,
                                       int ncol, int M, int Nout, const float *__restrict__ bias, int relu,
-                                      float *__restrict__ y, __half *__restrict__ y_hi, __half *__restrict__ y_lo) {
+                                      float *__restrict__ y, __half *__restrict__ y_hi, __half *__restrict__ y_lo,
+                                      const float *__restrict__ out_scale) {
   const int t = blockIdx.x;
   const long long a = (long long)t * C, b = a + C;
   const int c_first = (int)(((a + 1) * G + W - 1) / W) - 1;
@@ -546,8 +550,10 @@ __global__ void k_tc16_streamk_reduce(const float *__restrict__ part, int W, int
     acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
   }
   float o[4] = {acc.x, acc.y, acc.z, acc.w};
+  const float osc = out_scale != nullptr ? __ldg(out_scale) : 1.0f;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
+    o[k] *= osc;
     if (bias != nullptr && j + k < Nout) o[k] += __ldg(bias + j + k);
     if (relu) o[k] = fmaxf(o[k], 0.f);
   }
@@ -680,9 +686,6 @@ static LinPlan plan_linear(int M, int Nout, int K, bool allow_split) {
   return best;
 }
 
-int linear_planes(const float *x, const float *w_split, const float *b, float *y, __half *y_hi, __half *y_lo, int M,
-                  int Nout, int K, int relu, float *ws, cudaStream_t st);
-
 size_t linear_workspace_floats(int M, int Nout, int K) {
   if (M <= 0 || Nout <= 0) return 0;
   const LinPlan pl = plan_linear(M, Nout, K, true);
@@ -694,11 +697,15 @@ int linear(const float *x, const float *w_split, const float *b, float *y, int M
            cudaStream_t st) {
   return linear_planes(x, w_split, b, y, nullptr, nullptr, M, Nout, K, relu, ws, st);
 }
+int linear_scaled(const float *x, const float *w_split, float *y, int M, int Nout, int K, const float *out_scale, float *ws,
+                  cudaStream_t st) {
+  return linear_planes(x, w_split, nullptr, y, nullptr, nullptr, M, Nout, K, 0, ws, st, out_scale);
+}
 
 // same, and the epilogue (or the split-K / stream-K reducer) also writes the fp16 [hi | lo * 2^11] planes of y
 // (Nout % 4 == 0 required when planes are requested)
 int linear_planes(const float *x, const float *w_split, const float *b, float *y, __half *y_hi, __half *y_lo, int M,
-                  int Nout, int K, int relu, float *ws, cudaStream_t st) {
+                  int Nout, int K, int relu, float *ws, cudaStream_t st, const float *out_scale) {
   if (M <= 0 || Nout <= 0) return 0;
   if (y_hi != nullptr && (Nout & 3)) return sgg_set_err(SGG_E_BADARG, "tc16 linear: planes need Nout %% 4 == 0");
   if ((K & 7) || !ok16(x) || !ok16(w_split)) return sgg_set_err(SGG_E_BADARG, "tc16 linear: K %% 8 / alignment");
@@ -707,7 +714,7 @@ int linear_planes(const float *x, const float *w_split, const float *b, float *y
   const __half *wh = reinterpret_cast<const __half *>(w_split);
   Seg sg[2] = {{x, wh, wh + (size_t)Nout * K, Nout}, {}};
   Params p{}; p.M = M; p.K = K; p.Nout = Nout; p.relu = relu; p.bias = b; p.dbg = dbg_ptr();
-  p.out_hi = y_hi; p.out_lo = y_lo;
+  p.out_hi = y_hi; p.out_lo = y_lo; p.out_scale = out_scale;
   static const int pf_env = getenv("SGG_TC16_PF") ? atoi(getenv("SGG_TC16_PF")) : 8;
   p.pf = kblocks >= 32 ? pf_env : 0;
   int rc;
@@ -721,7 +728,7 @@ int linear_planes(const float *x, const float *w_split, const float *b, float *y
     if (rc) return rc;
     const int rows_per_cta = 256 / (pl.ncol / 4);
     k_tc16_streamk_reduce<<<dim3(col_tiles * rows, BM / rows_per_cta), 256, 0, st>>>(
-        ws, p.sk_W, p.sk_C, pl.sk_ctas, pl.sk_maxseg, col_tiles, pl.ncol, M, Nout, b, relu, y, y_hi, y_lo);
+        ws, p.sk_W, p.sk_C, pl.sk_ctas, pl.sk_maxseg, col_tiles, pl.ncol, M, Nout, b, relu, y, y_hi, y_lo, out_scale);
     SGG_RETURN_IF_LAUNCH_FAILED("k_tc16_streamk_reduce");
     return 0;
   }
@@ -741,7 +748,7 @@ int linear_planes(const float *x, const float *w_split, const float *b, float *y
   if (splits > 1) {
     const size_t mn = (size_t)M * Nout;
     int blocks = (int)((mn + 255) / 256 < 2048 ? (mn + 255) / 256 : 2048);
-    k_tc16_splitk_reduce<<<blocks, 256, 0, st>>>(ws, splits, mn, Nout, b, relu, y, y_hi, y_lo);
+    k_tc16_splitk_reduce<<<blocks, 256, 0, st>>>(ws, splits, mn, Nout, b, relu, y, y_hi, y_lo, out_scale);
     SGG_RETURN_IF_LAUNCH_FAILED("k_tc16_splitk_reduce");
   }
   return 0;

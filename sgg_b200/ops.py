@@ -623,7 +623,10 @@ def grad_sink(weight):
     return hit
 
 
-_TC_BWD = {'min_rows': 256, 'min_red': 1024, 'enabled': True}      # below these the SIMT tiles (split-K) are faster
+# below min_rows / min_red the SIMT tiles (split-K) are faster.  engine: 'tc16' = 3xFP16 with an exact power-of-two scale
+# of the gradient operand (twice the MMA rate), 'tc32' = 3xTF32 (fp32 exponent range, no scale needed)
+import os as _os
+_TC_BWD = {'min_rows': 256, 'min_red': 1024, 'enabled': True, 'engine': _os.environ.get('SGG_BWD_ENGINE', 'tc16')}
 
 
 def _pad32(n):
@@ -646,6 +649,39 @@ def _tc32_linear(x, w_split, M, Nout, K, out=None):
     ws = torch.empty(nb, dtype=torch.uint8, device=x.device) if nb else None
     check(lib.sgg_tc32_linear_forward(_ptr(x), _ptr(w_split), None, _ptr(y), M, Nout, K, 0, _ptr(ws), nb, _stream()),
           'sgg_tc32_linear_forward')
+    return y
+
+
+def _pow2_scale(x):
+    """device floats [s, 1/s], s = 2^k with max|x| * s in [1024, 2048) — no synchronisation"""
+    lib = _lib.load()
+    sc = torch.empty(2, dtype=torch.float32, device=x.device)
+    nb = lib.sgg_pow2_scale_workspace_bytes()
+    ws = torch.empty(nb, dtype=torch.uint8, device=x.device)
+    check(lib.sgg_pow2_scale(_ptr(x), x.numel(), _ptr(sc), _ptr(ws), nb, _stream()), 'sgg_pow2_scale')
+    return sc
+
+
+def _transpose16(inp, R, C, ldin, Rpad, planes, sc=None):
+    """inp [R, C] (row stride ldin) -> [C, Rpad]: planes=False: fp32 scaled by sc[0]; planes=True: fp16 [hi | lo] [2, C, Rpad]"""
+    lib = _lib.load()
+    if planes:
+        out = torch.empty((2, C, Rpad), dtype=torch.float16, device=inp.device)
+    else:
+        out = torch.empty((C, Rpad), dtype=torch.float32, device=inp.device)
+    check(lib.sgg_bwd_transpose16(_ptr(inp), ldin, R, C, _ptr(out), Rpad, 1 if planes else 0, _ptr(sc), _stream()),
+          'sgg_bwd_transpose16')
+    return out
+
+
+def _tc16_linear_scaled(x, w_planes, M, Nout, K, inv_scale, out=None):
+    """y [M, Nout] = inv_scale[0] * (x [M, K] @ w^T) on the 3xFP16 engine; w_planes fp16 [2, Nout, K]"""
+    lib = _lib.load()
+    y = out if out is not None else torch.empty((M, Nout), dtype=torch.float32, device=x.device)
+    nb = lib.sgg_tc16_linear_workspace_bytes(M, Nout, K)
+    ws = torch.empty(nb, dtype=torch.uint8, device=x.device) if nb else None
+    check(lib.sgg_tc16_linear_scaled(_ptr(x), _ptr(w_planes), _ptr(y), M, Nout, K, _ptr(inv_scale), _ptr(ws), nb, _stream()),
+          'sgg_tc16_linear_scaled')
     return y
 
 
@@ -683,24 +719,40 @@ def linear_backward(x, weight, dy, need_dx=True, need_dw=True, need_db=True):
     dx = dw = db = None
     sink = grad_sink(w_obj) if need_dw else None
     # ---- dX [M,K] = dY [M,Nout] W [Nout,K]
-    tc_dx = need_dx and use_tc and M >= _TC_BWD['min_rows'] and Nout % 4 == 0 and Nout >= 64 and K >= 64
-    if tc_dx:
+    tc_dx = need_dx and use_tc and M >= _TC_BWD['min_rows'] and Nout % 8 == 0 and Nout >= 64 and K >= 64
+    tc_dw = need_dw and use_tc and M >= _TC_BWD['min_red'] and Nout >= 64 and K >= 64
+    tc16 = _TC_BWD['engine'] == 'tc16' and M % 4 == 0
+    sc = _pow2_scale(dy) if tc16 and (tc_dx or tc_dw) else None
+    if tc_dx and tc16:
+        wT = _transpose16(weight, Nout, K, K, Nout, planes=True)          # fp16 planes [2, K, Nout]
+        dys = torch.empty_like(dy)
+        check(lib.sgg_scale_by(_ptr(dy), dy.numel(), _ptr(sc), _ptr(dys), _stream()), 'sgg_scale_by')
+        dx = _tc16_linear_scaled(dys, wT, M, K, Nout, sc[1:])
+        del wT, dys
+    elif tc_dx:
         wT = _transpose(weight, Nout, K, K, Nout, split=True)             # [2, K, Nout]
         dx = _tc32_linear(dy, wT, M, K, Nout)
         del wT
     # ---- dW [Nout,K] = dY^T X (reduction over the M rows)
-    tc_dw = need_dw and use_tc and M >= _TC_BWD['min_red'] and Nout >= 64 and K >= 64
     if need_dw:
         dw = sink[1] if sink is not None else torch.empty((Nout, K), dtype=torch.float32, device=dev)
     if tc_dw:
         Mp = _pad32(M)
-        xT = _transpose(x, M, K, K, Mp, split=True)                       # [2, K, Mp], shared by every row chunk
         chunks = sink[2] if (sink is not None and sink[2]) else [(0, Nout)]
-        for r0, r1 in chunks:
-            dyT = _transpose(dy[:, r0:], M, r1 - r0, Nout, Mp, split=False)    # [r1-r0, Mp]
-            _tc32_linear(dyT, xT, r1 - r0, K, Mp, out=dw[r0:r1])
-            if sink is not None:
-                sink[3](sink[0](), r0, r1)
+        if tc16 and sc is not None:
+            xT = _transpose16(x, M, K, K, Mp, planes=True)                # fp16 planes [2, K, Mp], shared by every row chunk
+            for r0, r1 in chunks:
+                dyT = _transpose16(dy[:, r0:], M, r1 - r0, Nout, Mp, planes=False, sc=sc)    # (s dY)^T [r1-r0, Mp]
+                _tc16_linear_scaled(dyT, xT, r1 - r0, K, Mp, sc[1:], out=dw[r0:r1])
+                if sink is not None:
+                    sink[3](sink[0](), r0, r1)
+        else:
+            xT = _transpose(x, M, K, K, Mp, split=True)                   # [2, K, Mp], shared by every row chunk
+            for r0, r1 in chunks:
+                dyT = _transpose(dy[:, r0:], M, r1 - r0, Nout, Mp, split=False)    # [r1-r0, Mp]
+                _tc32_linear(dyT, xT, r1 - r0, K, Mp, out=dw[r0:r1])
+                if sink is not None:
+                    sink[3](sink[0](), r0, r1)
         del xT
     # ---- remaining pieces on the SIMT tiles (one call; accumulate = 0: plain stores, no zero-fill)
     rest_dx, rest_dw = need_dx and not tc_dx, need_dw and not tc_dw

@@ -64,7 +64,6 @@ def test_conv_stack_large_activations_raise_the_range_flag():
     x = torch.rand(1, 3, 32, 32, device='cuda') * 3e6          # relu(conv1_1) overflows fp16
     ops._lib.load().sgg_conv_overflow(1)
     ops.vgg_features(x, layers[:2])
-    # the first layer writes its planes without a check, the second layer's emission sees inf / nan
     assert ops._lib.load().sgg_conv_overflow(1) != 0
 
 
