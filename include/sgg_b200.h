@@ -24,6 +24,9 @@
 #include <stddef.h>
 #include <stdint.h>
 
+/* Process model: ONE process per GPU (as torchrun launches them).  The library keeps a few process-global caches that are
+ * not keyed by device (side streams / events of the fork-join helper, the SM count, per-kernel shared-memory opt-ins):
+ * driving two devices from one process, or calling in from several host threads at once, is not supported. */
 #ifdef __cplusplus
 extern "C" {
 #endif

@@ -736,6 +736,12 @@ size_t workspace_bytes(int N, int E, int H) {
 
 bool supported(const sgg_mp_weights *w, int N, int E, int H) {
   static int enabled = env_int("SGG_MP_FUSED", 1);
+  // Many-wave graphs (cfg5: 903 GRU tiles = 6.1 waves) run 7 % faster on the multi-stream schedule of mp.cu, whose edge
+  // kernel, ctx gather, P GEMM and node GRU overlap across waves; up to ~4 waves (cfg3 / cfg4 shards) the fused one wins.
+  if (enabled == 1) {
+    const long tiles = (long)((E + BM - 1) / BM + (N + BM - 1) / BM) * ((H + NBR - 1) / NBR);
+    if (tiles > 5L * sgg_num_sms()) return false;
+  }
   return enabled && sgg_tc_get_mode() == 1 && N > 0 && E > 0 && H % 128 == 0 && H <= 512 && w->edge_w_ih_split && w->edge_w_hh_split &&
          w->node_w_ih_split && w->node_w_hh_split;
 }

@@ -9,6 +9,12 @@
 
 namespace sgg {
 
+// Indices come from the caller (rel_inds / im_inds): clamp them so a bad value can never become an out-of-bounds read
+// (graph.cu flags the same situation for the message-passing graph; here the result for such a row is simply that of
+// the clamped index).
+__device__ __forceinline__ int clamp_idx(long long v, int n) { return v < 0 ? 0 : (v >= n ? n - 1 : (int)v); }
+
+
 __device__ __forceinline__ float bilinear(const float *__restrict__ f, int Hf, int Wf, float y, float x) {
   if (y < -1.0f || y > (float)Hf || x < -1.0f || x > (float)Wf) return 0.f;
   if (y <= 0.f) y = 0.f;
@@ -23,7 +29,7 @@ __device__ __forceinline__ float bilinear(const float *__restrict__ f, int Hf, i
 
 // One thread per output element (r, c, ph, pw); r < N are objects, r >= N union boxes.
 __global__ void __launch_bounds__(256)
-k_roi_align(const float *__restrict__ fmap, int C, int Hf, int Wf, const float *__restrict__ rois, int N,
+k_roi_align(const float *__restrict__ fmap, int B, int C, int Hf, int Wf, const float *__restrict__ rois, int N,
             const int64_t *__restrict__ ui, int64_t stride, int cs, int co, int E, float scale, int pool, int sr,
             float *__restrict__ node_out, float *__restrict__ edge_out, int do_node, int do_edge,
             const float *__restrict__ edge_add) {
@@ -39,12 +45,12 @@ k_roi_align(const float *__restrict__ fmap, int C, int Hf, int Wf, const float *
     float *dst;
     if (r < (size_t)N) {
       const float *q = rois + r * 5;
-      b = (int)q[0]; x1 = q[1]; y1 = q[2]; x2 = q[3]; y2 = q[4];
+      b = clamp_idx((long long)q[0], B); x1 = q[1]; y1 = q[2]; x2 = q[3]; y2 = q[4];
       dst = node_out + r * per + rem;
     } else {
       const size_t e = r - N;
-      const float *qs = rois + (size_t)ui[e * stride + cs] * 5, *qo = rois + (size_t)ui[e * stride + co] * 5;
-      b = (int)qs[0];
+      const float *qs = rois + (size_t)clamp_idx(ui[e * stride + cs], N) * 5, *qo = rois + (size_t)clamp_idx(ui[e * stride + co], N) * 5;
+      b = clamp_idx((long long)qs[0], B);
       x1 = fminf(qs[1], qo[1]); y1 = fminf(qs[2], qo[2]); x2 = fmaxf(qs[3], qo[3]); y2 = fmaxf(qs[4], qo[4]);
       dst = edge_out + e * per + rem;
     }
@@ -90,7 +96,7 @@ __global__ void k_nchw_to_nhwc(const float *__restrict__ in, int C, int HW, floa
 constexpr int RA_MAXS = 32;   // max samples per axis (pool * sampling_ratio)
 
 __global__ void __launch_bounds__(256)
-k_roi_align_nhwc(const float *__restrict__ fmap /*[B,Hf,Wf,C]*/, int C, int Hf, int Wf, const float *__restrict__ rois,
+k_roi_align_nhwc(const float *__restrict__ fmap /*[B,Hf,Wf,C]*/, int B, int C, int Hf, int Wf, const float *__restrict__ rois,
                  int N, const int64_t *__restrict__ ui, int64_t stride, int cs, int co, int E, float scale, int pool,
                  int sr, float *__restrict__ node_out, float *__restrict__ edge_out, int r_begin,
                  const float *__restrict__ edge_add) {
@@ -103,12 +109,12 @@ k_roi_align_nhwc(const float *__restrict__ fmap /*[B,Hf,Wf,C]*/, int C, int Hf, 
   float *dst;
   if (r < N) {
     const float *q = rois + (size_t)r * 5;
-    b = (int)q[0]; x1 = q[1]; y1 = q[2]; x2 = q[3]; y2 = q[4];
+    b = clamp_idx((long long)q[0], B); x1 = q[1]; y1 = q[2]; x2 = q[3]; y2 = q[4];
     dst = node_out + (size_t)r * C * pp;
   } else {
     const size_t e = (size_t)(r - N);
-    const float *qs = rois + (size_t)ui[e * stride + cs] * 5, *qo = rois + (size_t)ui[e * stride + co] * 5;
-    b = (int)qs[0];
+    const float *qs = rois + (size_t)clamp_idx(ui[e * stride + cs], N) * 5, *qo = rois + (size_t)clamp_idx(ui[e * stride + co], N) * 5;
+    b = clamp_idx((long long)qs[0], B);
     x1 = fminf(qs[1], qo[1]); y1 = fminf(qs[2], qo[2]); x2 = fmaxf(qs[3], qo[3]); y2 = fmaxf(qs[4], qo[4]);
     dst = edge_out + e * C * pp;
   }
@@ -172,7 +178,7 @@ k_roi_align_nhwc(const float *__restrict__ fmap /*[B,Hf,Wf,C]*/, int C, int Hf, 
 // the per-channel arithmetic (and its order) is unchanged.  Needs C % 4 == 0 and C / 4 <= blockDim.x.
 template <int SR>
 __global__ void __launch_bounds__(256)
-k_roi_align_nhwc4(const float *__restrict__ fmap /*[B,Hf,Wf,C]*/, int C, int Hf, int Wf, const float *__restrict__ rois,
+k_roi_align_nhwc4(const float *__restrict__ fmap /*[B,Hf,Wf,C]*/, int B, int C, int Hf, int Wf, const float *__restrict__ rois,
                   int N, const int64_t *__restrict__ ui, int64_t stride, int cs, int co, int E, float scale, int pool,
                   float *__restrict__ node_out, float *__restrict__ edge_out, int r_begin,
                   const float *__restrict__ edge_add) {
@@ -185,12 +191,12 @@ k_roi_align_nhwc4(const float *__restrict__ fmap /*[B,Hf,Wf,C]*/, int C, int Hf,
   float *dst;
   if (r < N) {
     const float *q = rois + (size_t)r * 5;
-    b = (int)q[0]; x1 = q[1]; y1 = q[2]; x2 = q[3]; y2 = q[4];
+    b = clamp_idx((long long)q[0], B); x1 = q[1]; y1 = q[2]; x2 = q[3]; y2 = q[4];
     dst = node_out + (size_t)r * C * pp;
   } else {
     const size_t e = (size_t)(r - N);
-    const float *qs = rois + (size_t)ui[e * stride + cs] * 5, *qo = rois + (size_t)ui[e * stride + co] * 5;
-    b = (int)qs[0];
+    const float *qs = rois + (size_t)clamp_idx(ui[e * stride + cs], N) * 5, *qo = rois + (size_t)clamp_idx(ui[e * stride + co], N) * 5;
+    b = clamp_idx((long long)qs[0], B);
     x1 = fminf(qs[1], qo[1]); y1 = fminf(qs[2], qo[2]); x2 = fmaxf(qs[3], qo[3]); y2 = fmaxf(qs[4], qo[4]);
     dst = edge_out + e * C * pp;
   }
@@ -306,12 +312,12 @@ extern "C" int sgg_node_edge_features_add(const float *fmap, int B, int C, int H
         SGG_CUDA_TRY(cudaFuncSetAttribute(sgg::k_roi_align_nhwc4<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr4 = true;
       }
-      sgg::k_roi_align_nhwc4<2><<<r1 - r0, 256, smem_need, st>>>(nhwc, C, Hf, Wf, rois, N, union_inds, row_stride, col_subj,
+      sgg::k_roi_align_nhwc4<2><<<r1 - r0, 256, smem_need, st>>>(nhwc, B, C, Hf, Wf, rois, N, union_inds, row_stride, col_subj,
                                                               col_obj, E, spatial_scale, pool, node_feat, edge_feat, r0, edge_add);
       SGG_RETURN_IF_LAUNCH_FAILED("k_roi_align_nhwc4");
       return 0;
     }
-    sgg::k_roi_align_nhwc<<<r1 - r0, 256, smem_need, st>>>(nhwc, C, Hf, Wf, rois, N, union_inds, row_stride, col_subj,
+    sgg::k_roi_align_nhwc<<<r1 - r0, 256, smem_need, st>>>(nhwc, B, C, Hf, Wf, rois, N, union_inds, row_stride, col_subj,
                                                           col_obj, E, spatial_scale, pool, sampling_ratio, node_feat,
                                                           edge_feat, r0, edge_add);
     SGG_RETURN_IF_LAUNCH_FAILED("k_roi_align_nhwc");
@@ -319,7 +325,7 @@ extern "C" int sgg_node_edge_features_add(const float *fmap, int B, int C, int H
   }
   const size_t total = ((size_t)(do_node ? N : 0) + (do_edge ? E : 0)) * C * pool * pool;
   int blocks = (int)((total + 255) / 256 < (size_t)sgg_num_sms() * 32 ? (total + 255) / 256 : (size_t)sgg_num_sms() * 32);
-  sgg::k_roi_align<<<blocks, 256, 0, (cudaStream_t)stream>>>(fmap, C, Hf, Wf, rois, N, union_inds, row_stride,
+  sgg::k_roi_align<<<blocks, 256, 0, (cudaStream_t)stream>>>(fmap, B, C, Hf, Wf, rois, N, union_inds, row_stride,
                                                              col_subj, col_obj, E, spatial_scale, pool,
                                                              sampling_ratio, node_feat, edge_feat, do_node, do_edge, edge_add);
   SGG_RETURN_IF_LAUNCH_FAILED("k_roi_align");

@@ -46,6 +46,7 @@ struct Params {
   int sk_W, sk_C, sk_ct, sk_maxseg;
   float *sk_part;
   int pf;                     // LINEAR: k-blocks of L2 prefetch distance for the streamed A operand (0 = off)
+  const float *a_direct;      // LINEAR, DIRECT: the fp32 A operand [M,K] (read by the converter warps, not by TMA)
   const float *bias;          // LINEAR
   float *out;                 // LINEAR: [M,Nout] (or partials [splits,M,Nout]); GRU: [M,H]
   const float *b_ih, *b_hh;   // GRU
@@ -79,7 +80,11 @@ struct Cfg {
 };
 
 // NBLK gate blocks of NBR weight rows each (LINEAR: NBLK = 1, NBR = tile width); NSEG K-segments (NODE: 2)
-template <int NBLK, int NBR, int NSEG, int EPI>
+// DIRECT (LINEAR only): the converter warps load the fp32 A tile straight from global memory into registers (two k-blocks
+// ahead), split it and write the fp16 [hi | lo] tiles — A never exists as fp32 in shared memory.  The main loop is bound by
+// shared-memory bandwidth; this removes the 32 KB TMA write and the 32 KB read-back of the raw tile
+// from every k-block (224 -> 160 KB at 128 columns).
+template <int NBLK, int NBR, int NSEG, int EPI, int DIRECT = 0>
 __global__ void __launch_bounds__(NTHR, 1)
 k_tc16(Params p, const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
        const __grid_constant__ CUtensorMap tmBh0, const __grid_constant__ CUtensorMap tmBl0,
@@ -157,15 +162,17 @@ k_tc16(Params p, const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           k0 = (gk - t * kbt) * BK; am0 = (t / p.sk_ct) * BM; bj0 = (t % p.sk_ct) * NCOL;
         }
         uint8_t *st = stage_ptr(s);
-        mbar_arrive_expect_tx(full + s, A_BYTES + 2 * B_BYTES);
+        mbar_arrive_expect_tx(full + s, (DIRECT ? 0 : A_BYTES) + 2 * B_BYTES);
         const CUtensorMap *ta = (NSEG > 1 && seg == 1) ? &tmA1 : &tmA0;
         const CUtensorMap *tbh = (NSEG > 1 && seg == 1) ? &tmBh1 : &tmBh0;
         const CUtensorMap *tbl = (NSEG > 1 && seg == 1) ? &tmBl1 : &tmBl0;
-        tma_load_2d(st, ta, full + s, k0, am0);                      // fp32 k0 .. k0+31
-        tma_load_2d(st + A_HALF, ta, full + s, k0 + 32, am0);        // fp32 k0+32 .. k0+63
-        if (CHUNKED && !SK && p.pf > 0 && it + p.pf < total) {       // A comes from HBM (16 KB / row): pull it into L2 early
-          tma_prefetch_2d(ta, k0 + p.pf * BK, am0);
-          tma_prefetch_2d(ta, k0 + p.pf * BK + 32, am0);
+        if (!DIRECT) {
+          tma_load_2d(st, ta, full + s, k0, am0);                      // fp32 k0 .. k0+31
+          tma_load_2d(st + A_HALF, ta, full + s, k0 + 32, am0);        // fp32 k0+32 .. k0+63
+          if (CHUNKED && !SK && p.pf > 0 && it + p.pf < total) {       // A comes from HBM (16 KB / row): pull it into L2 early
+            tma_prefetch_2d(ta, k0 + p.pf * BK, am0);
+            tma_prefetch_2d(ta, k0 + p.pf * BK + 32, am0);
+          }
         }
 #pragma unroll
         for (int b = 0; b < NBLK; ++b) {
@@ -258,6 +265,52 @@ k_tc16(Params p, const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       fence_proxy_async_smem();
       mbar_arrive(ready + s);
     };
+    // ---- DIRECT: global -> registers -> fp16 tiles.  Lane <-> (row r of an 8-row swizzle atom, 16-byte output chunk c);
+    // a warp's load instruction covers 4 rows x 256 contiguous bytes.  PRE[j] holds the 8 floats of item j.
+    auto a_coords = [&](int it, int &k0, int &am0) {
+      k0 = (kb_lo + it) * BK; am0 = m0;
+      if (SK) {
+        const int gk = gc_lo * KCB + it, kbt = p.sk_C * KCB;
+        const int t = gk / kbt;
+        k0 = (gk - t * kbt) * BK; am0 = (t / p.sk_ct) * BM;
+      }
+    };
+    auto load_direct = [&](int it, float4 (&pre)[4 * APW]) {
+      int k0, am0;
+      a_coords(it, k0, am0);
+      const int k = k0 + 8 * c;
+      const bool kin = k + 8 <= p.K;                       // K % 8 == 0: a chunk is entirely inside or outside
+#pragma unroll
+      for (int i = 0; i < 2 * APW; ++i) {
+        const int g = APW * wc + (i >> 1), r = (lane >> 3) + 4 * (i & 1);
+        const int m = am0 + 8 * g + r;
+        if (kin && m < p.M) {
+          const float4 *src = reinterpret_cast<const float4 *>(p.a_direct + (size_t)m * p.K + k);
+          pre[2 * i] = __ldg(src); pre[2 * i + 1] = __ldg(src + 1);
+        } else {
+          pre[2 * i] = make_float4(0.f, 0.f, 0.f, 0.f); pre[2 * i + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+    };
+    auto store_direct = [&](int it, const float4 (&pre)[4 * APW]) {
+      const int s = it % STAGES, ph = (it / STAGES) & 1;
+      mbar_wait(empty + s, ph ^ 1);                        // the MMAs that read this stage's previous tile have retired
+      const uint32_t a_addr = smem_u32(stage_ptr(s));
+#pragma unroll
+      for (int i = 0; i < 2 * APW; ++i) {
+        const int g = APW * wc + (i >> 1), r = (lane >> 3) + 4 * (i & 1);
+        const float4 f0 = pre[2 * i], f1 = pre[2 * i + 1];
+        uint4 hi, lo;
+        split2(f0.x, f0.y, hi.x, lo.x); split2(f0.z, f0.w, hi.y, lo.y);
+        split2(f1.x, f1.y, hi.z, lo.z); split2(f1.z, f1.w, hi.w, lo.w);
+        ovf |= f16x2_nonfinite(hi.x) | f16x2_nonfinite(hi.y) | f16x2_nonfinite(hi.z) | f16x2_nonfinite(hi.w);
+        const uint32_t dst = a_addr + (uint32_t)(g * 1024 + r * 128 + (((c ^ r) & 7) << 4));
+        sts128u(dst, hi);
+        sts128u(dst + A_HALF, lo);
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(ready + s);
+    };
    if (CHUNKED) {
     // ===================== LINEAR: thread <-> (output row, half of the tile's columns) =====================
     // Chunk ch (256 of K) is drained from TMEM into fp32 registers one k-block AFTER its last k-block was converted,
@@ -307,9 +360,25 @@ k_tc16(Params p, const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     // the converters run up to STAGES k-blocks ahead of the MMA issuer, so an early drain made them wait for the tensor
     // pipe and then starved it — the ring emptied once per chunk).  The MMA issuer needs the buffer back one k-block later.
     int next_drain = 0;
-    for (int it = 0; it < total; ++it) {
-      convert(it);
-      if ((it % KCB) == KCB - 1 && it / KCB >= 1) { drain(next_drain); sk_flush(next_drain); ++next_drain; }
+    if (DIRECT) {
+      float4 pre0[4 * APW], pre1[4 * APW];               // two k-blocks of A in flight per thread
+      if (total > 0) load_direct(0, pre0);
+      if (total > 1) load_direct(1, pre1);
+      for (int it = 0; it < total; it += 2) {
+        store_direct(it, pre0);
+        if (it + 2 < total) load_direct(it + 2, pre0);
+        if ((it % KCB) == KCB - 1 && it / KCB >= 1) { drain(next_drain); sk_flush(next_drain); ++next_drain; }
+        if (it + 1 < total) {
+          store_direct(it + 1, pre1);
+          if (it + 3 < total) load_direct(it + 3, pre1);
+          if (((it + 1) % KCB) == KCB - 1 && (it + 1) / KCB >= 1) { drain(next_drain); sk_flush(next_drain); ++next_drain; }
+        }
+      }
+    } else {
+      for (int it = 0; it < total; ++it) {
+        convert(it);
+        if ((it % KCB) == KCB - 1 && it / KCB >= 1) { drain(next_drain); sk_flush(next_drain); ++next_drain; }
+      }
     }
     for (; next_drain < nchunks; ++next_drain) { drain(next_drain); sk_flush(next_drain); }
     if (!SK && m < p.M) {
@@ -576,12 +645,12 @@ __global__ void k_tc16_streamk_reduce(const float *__restrict__ part, int W, int
 // ------------------------------- host side -------------------------------------------------------
 struct Seg { const float *A; const __half *Bhi; const __half *Blo; int brows; };
 
-template <int NBLK, int NBR, int NSEG, int EPI>
+template <int NBLK, int NBR, int NSEG, int EPI, int DIRECT = 0>
 static int launch(const Params &p, const Seg *segs, int col_tiles, int splits, cudaStream_t st) {
   using C = Cfg<NBLK * NBR>;
   static bool attr = false;
   if (!attr) {
-    SGG_CUDA_TRY(cudaFuncSetAttribute(k_tc16<NBLK, NBR, NSEG, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    SGG_CUDA_TRY(cudaFuncSetAttribute(k_tc16<NBLK, NBR, NSEG, EPI, DIRECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
     attr = true;
   }
   CUtensorMap tm[6];
@@ -594,7 +663,7 @@ static int launch(const Params &p, const Seg *segs, int col_tiles, int splits, c
   }
   dim3 grid(col_tiles, (p.M + BM - 1) / BM, splits);
   if (p.sk_W > 0) grid = dim3(splits, 1, 1);        // stream-K: `splits` carries the CTA count
-  k_tc16<NBLK, NBR, NSEG, EPI><<<grid, NTHR, C::SMEM, st>>>(p, tm[0], tm[3], tm[1], tm[2], tm[4], tm[5]);
+  k_tc16<NBLK, NBR, NSEG, EPI, DIRECT><<<grid, NTHR, C::SMEM, st>>>(p, tm[0], tm[3], tm[1], tm[2], tm[4], tm[5]);
   SGG_RETURN_IF_LAUNCH_FAILED("k_tc16");
   return 0;
 }
@@ -715,15 +784,24 @@ int linear_planes(const float *x, const float *w_split, const float *b, float *y
   Seg sg[2] = {{x, wh, wh + (size_t)Nout * K, Nout}, {}};
   Params p{}; p.M = M; p.K = K; p.Nout = Nout; p.relu = relu; p.bias = b; p.dbg = dbg_ptr();
   p.out_hi = y_hi; p.out_lo = y_lo; p.out_scale = out_scale;
-  static const int pf_env = getenv("SGG_TC16_PF") ? atoi(getenv("SGG_TC16_PF")) : 8;
+  static const int pf_env = getenv("SGG_TC16_PF") ? atoi(getenv("SGG_TC16_PF")) : 0;
   p.pf = kblocks >= 32 ? pf_env : 0;
+  // tried and NOT adopted (opt-in, SGG_TC16_DIRECT=1): 62 -> 65 us on the cfg2 edge-unary GEMM, 166 -> 180 us at M = 9600.
+  // Global loads return through the same L1 / shared-memory data path the TMA write + LDS read-back used, so no bytes are
+  // saved there, and the converters' stage-free wait shortens the effective prefetch distance.
+  static const int direct_env = getenv("SGG_TC16_DIRECT") ? atoi(getenv("SGG_TC16_DIRECT")) : 0;
+  const bool direct = direct_env != 0;
+  p.a_direct = x;
   int rc;
   if (pl.sk_ctas > 0) {
     const int col_tiles = (Nout + pl.ncol - 1) / pl.ncol, rows = (M + BM - 1) / BM;
     p.kb_per_split = kblocks;
     p.sk_C = K / 256; p.sk_ct = col_tiles; p.sk_W = col_tiles * rows * p.sk_C; p.sk_maxseg = pl.sk_maxseg; p.sk_part = ws;
     p.out = y;
-    if (pl.ncol == 64) rc = launch<1, 64, 1, EPI_LINEAR>(p, sg, col_tiles, pl.sk_ctas, st);
+    if (direct) {
+      if (pl.ncol == 64) rc = launch<1, 64, 1, EPI_LINEAR, 1>(p, sg, col_tiles, pl.sk_ctas, st);
+      else rc = launch<1, 128, 1, EPI_LINEAR, 1>(p, sg, col_tiles, pl.sk_ctas, st);
+    } else if (pl.ncol == 64) rc = launch<1, 64, 1, EPI_LINEAR>(p, sg, col_tiles, pl.sk_ctas, st);
     else rc = launch<1, 128, 1, EPI_LINEAR>(p, sg, col_tiles, pl.sk_ctas, st);
     if (rc) return rc;
     const int rows_per_cta = 256 / (pl.ncol / 4);
@@ -741,7 +819,11 @@ int linear_planes(const float *x, const float *w_split, const float *b, float *y
   }
   p.kb_per_split = kb_per;
   p.out = splits > 1 ? ws : y;
-  if (pl.ncol == 64) rc = launch<1, 64, 1, EPI_LINEAR>(p, sg, (Nout + 63) / 64, splits, st);
+  if (direct) {
+    if (pl.ncol == 64) rc = launch<1, 64, 1, EPI_LINEAR, 1>(p, sg, (Nout + 63) / 64, splits, st);
+    else if (pl.ncol == 96) rc = launch<1, 96, 1, EPI_LINEAR, 1>(p, sg, (Nout + 95) / 96, splits, st);
+    else rc = launch<1, 128, 1, EPI_LINEAR, 1>(p, sg, (Nout + 127) / 128, splits, st);
+  } else if (pl.ncol == 64) rc = launch<1, 64, 1, EPI_LINEAR>(p, sg, (Nout + 63) / 64, splits, st);
   else if (pl.ncol == 96) rc = launch<1, 96, 1, EPI_LINEAR>(p, sg, (Nout + 95) / 96, splits, st);
   else rc = launch<1, 128, 1, EPI_LINEAR>(p, sg, (Nout + 127) / 128, splits, st);
   if (rc) return rc;

@@ -124,6 +124,18 @@ def split_weight(w):
     return out
 
 
+def invalidate_split_cache(params=None):
+    """Drop cached tensor-core operand splits (and conv weight planes).  The caches are keyed by the tensor object and
+    ``_version``; writes that do NOT bump the version — ``p.data.copy_()/mul_()``, ``dist.broadcast(p.data)``, EMA /
+    weight surgery through ``.data`` — leave a stale split behind, so call this after any such write (or pass the
+    tensors that changed).  ``load_state_dict`` / ``optimizer.step`` bump versions and need nothing."""
+    if params is None:
+        _SPLIT_CACHE.clear(); _CONV_W_CACHE.clear()
+        return
+    for p in (params.values() if isinstance(params, dict) else params):
+        _SPLIT_CACHE.pop(id(p), None); _CONV_W_CACHE.pop(id(p), None)
+
+
 def split_cache_peek(w):
     """The cached operand-split buffer of the live tensor object ``w`` (whatever version it was made for), or None.
     Used by the fused optimizer (sgg_b200.optim), which rewrites the split in the same sweep that updates ``w``."""
@@ -378,6 +390,13 @@ class L1Plan(object):
         self.ws = torch.empty(self.nbytes, dtype=torch.uint8, device=device)
         self._fn = lib.sgg_l1_forward
         self.graph_ws, self.graph_bytes = None, 0
+
+    def refresh(self, params):
+        """Re-read the weights (and re-split them if they changed): call after the parameters were updated by anything
+        other than ``FusedSGD`` in 3xFP16 mode (which rewrites the cached splits in place), or after
+        ``invalidate_split_cache()``."""
+        self.hw, self._k1 = head_weights(params)
+        self.w, self._k2, self.H = mp_weights(params)
 
     def run(self, obj_feat, edge_feat, graph):
         """graph: a prebuilt ``Graph``, or the int64 rel_inds [E, 2] themselves (global subject / object ids) — then the

@@ -41,6 +41,11 @@ class ImpL1Runner(object):
         n_cls = self.params['obj_fc.weight'].shape[0]; n_rel = self.params['rel_fc.weight'].shape[0]
         self.slots = [_Slot(N, E, self.D, n_cls, n_rel, self.device) for _ in range(slots)]
         self.plans = [ops.L1Plan(self.params, N, E, self.D, mp_iter, self.device) for _ in range(slots)]
+        # the parameter upload and weight splits above ran on the current stream; the slot streams are non-blocking and
+        # must not start before them
+        cur = torch.cuda.current_stream(self.device)
+        for sl in self.slots:
+            sl.stream.wait_stream(cur)
         self._next = 0
         self.h2d_bytes = (N + E) * self.D * 4 + E * 2 * 8
         self.d2h_bytes = (N * n_cls + E * n_rel) * 4
@@ -67,6 +72,8 @@ class ImpL1Runner(object):
         return i
 
     def wait(self, handle):
+        """Returns the slot's pinned result buffers (views, valid until the slot is reused by a later ``submit``: copy them
+        if they must outlive ``len(slots)`` further submissions; ``__call__`` returns copies)."""
         s = self.slots[handle]
         s.done.synchronize()
         s.busy = False
