@@ -89,6 +89,7 @@ class RelModelBase(nn.Module):
         self.rel_classes = train_data.ind_to_predicates
         self.mode, self.backbone, self.RELS_PER_IMG = mode, backbone, RELS_PER_IMG
         self.pool_sz, self.stride = 7, 16
+        self.dropout_p = 0.5            # torchvision's VGG classifier dropout (roi_fmap / roi_fmap_obj); tests set it to 0
         self.use_bias, self.test_bias = use_bias, test_bias
         self.require_overlap = require_overlap_det and self.mode == 'sgdet'
         if backbone != 'vgg16':
@@ -282,14 +283,14 @@ class RelModelStanford(RelModelBase):
         fo, fe = self.roi_fmap_obj, self.roi_fmap[1]
         drop = self.training
         n = K.linear(node_feat.reshape(node_feat.shape[0], -1), fo[0].weight, fo[0].bias, relu=True)
-        n = F.dropout(n, 0.5, drop)
+        n = F.dropout(n, self.dropout_p, drop)
         n = K.linear(n, fo[3].weight, fo[3].bias, relu=True)
-        n = F.dropout(n, 0.5, drop)
+        n = F.dropout(n, self.dropout_p, drop)
         if geom is not None:
             e = K.fc_broadcast(edge_feat, geom, fe[0].weight, fe[0].bias)
         else:
             e = K.linear(edge_feat.reshape(E, -1), fe[0].weight, fe[0].bias, relu=True)
-        e = F.dropout(e, 0.5, drop)
+        e = F.dropout(e, self.dropout_p, drop)
         e = K.linear(e, fe[3].weight, fe[3].bias, relu=False)
         n = K.linear(n, self.obj_unary.weight, self.obj_unary.bias)
         e = K.linear(e, self.edge_unary.weight, self.edge_unary.bias, relu=True)

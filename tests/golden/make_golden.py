@@ -320,6 +320,49 @@ def main():
              obj_dists=od.numpy(), rel_dists=rd.numpy())
 
 
+    # ---------------- L2 in TRAINING mode: predict() forward + autograd through every trainable tensor --------------
+    # (batch-statistics BN in the geometry branch, fc6 on pools + broadcast geometry, fc7, unary, T x message passing,
+    # heads; dropout probability set to 0 on the live modules so the run is deterministic)
+    if want('l2_train_grad'):
+        seed = 6236
+        g = synth.synth_graph(3, 6, 14, seed)
+        N, E = g['boxes'].shape[0], g['rel_inds'].shape[0]
+        nfe, efe = synth.synth_pooled(N, E, seed)
+        p = synth.synth_params(seed, level='l2', scale=1.0)
+        load_params(model, p)
+        model.mp_iter = 3
+        model.train()
+        drops = [m for m in model.modules() if isinstance(m, torch.nn.Dropout)]
+        old_p = [m.p for m in drops]
+        for m in drops:
+            m.p = 0.0
+        for q in model.parameters():
+            q.grad = None
+        rng = np.random.default_rng(seed + 5)
+        r1 = rng.standard_normal((N, 151), dtype=np.float32); r2 = rng.standard_normal((E, 51), dtype=np.float32)
+        od, rd = model.predict(tt(nfe), tt(efe), tt(g['rel_inds']), tt(g['rois']), None)
+        loss = (od * tt(r1)).sum() + (rd * tt(r2)).sum()
+        loss.backward()
+        out = dict(seed=seed, N=N, E=E, digest=synth.digest(nfe, efe, p['roi_fmap.1.0.weight'][:64]), loss=float(loss.detach()),
+                   obj_dists=od.detach().numpy(), rel_dists=rd.detach().numpy(),
+                   rm1=model.union_boxes.conv[2].running_mean.numpy().copy(), rv2=model.union_boxes.conv[6].running_var.numpy().copy())
+        names = []
+        for k, q in model.named_parameters():
+            if k.startswith('detector.') or q.grad is None:
+                continue
+            flat = q.grad.numpy().reshape(-1)
+            idx = np.sort(np.random.default_rng(seed + 11).choice(flat.shape[0], min(512, flat.shape[0]), replace=False))
+            kk = k.replace('.', '__')
+            out['idx__' + kk] = idx; out['val__' + kk] = flat[idx]
+            out['asum__' + kk] = np.float64(np.abs(flat).astype(np.float64).sum())
+            names.append(k)
+        out['names'] = np.array(names)
+        for m, pp in zip(drops, old_p):
+            m.p = pp
+        model.eval()
+        save('l2_train_grad', **out)
+
+
 def l3_case(seed=8235):
     """Shared by make_golden and the tests: 2 images (one non-square), GT boxes inside the image."""
     sizes = [(592, 592), (400, 592)]

@@ -43,6 +43,59 @@ def test_l2_predict_vs_golden(model):
     assert np.abs(rd.cpu().numpy() - fx['rel_dists']).max() <= 1e-4
 
 
+def test_l2_train_mode_predict_and_all_gradients_vs_reference_autograd(model):
+    """predict() in TRAINING mode (batch-statistics BN in the geometry branch, fc6 on pools + broadcast geometry through the
+    7x7-summed-weight backward, fc7, unary, 3 x fused message passing with the tape, heads) and the gradients of all 40
+    trainable tensors against the reference's own forward + torch.autograd (tests/golden/l2_train_grad.npz; dropout
+    probability 0 on both sides)."""
+    fx = cases.load('l2_train_grad')
+    seed = int(fx['seed'])
+    g = synth.synth_graph(3, 6, 14, seed)
+    N, E = g['boxes'].shape[0], g['rel_inds'].shape[0]
+    nfe, efe = synth.synth_pooled(N, E, seed)
+    p = synth.synth_params(seed, level='l2', scale=1.0)
+    assert synth.digest(nfe, efe, p['roi_fmap.1.0.weight'][:64]) == str(fx['digest']), 'generator drift'
+    load(model, p)
+    for bn in (model.union_boxes.conv[2], model.union_boxes.conv[6]):
+        bn.num_batches_tracked.zero_()
+    model.train()
+    old_p, model.dropout_p = model.dropout_p, 0.0
+    try:
+        for q in model.parameters():
+            q.grad = None
+        rng = np.random.default_rng(seed + 5)
+        r1 = torch.from_numpy(rng.standard_normal((N, 151), dtype=np.float32)).cuda()
+        r2 = torch.from_numpy(rng.standard_normal((E, 51), dtype=np.float32)).cuda()
+        od, rd = model.predict(torch.from_numpy(nfe).cuda(), torch.from_numpy(efe).cuda(), torch.from_numpy(g['rel_inds']).cuda(),
+                               torch.from_numpy(g['rois']).cuda(), None)
+        loss = (od * r1).sum() + (rd * r2).sum()
+        loss.backward()
+    finally:
+        model.dropout_p = old_p
+        model.eval()
+    assert np.abs(od.detach().cpu().numpy() - fx['obj_dists']).max() <= 1e-4
+    assert np.abs(rd.detach().cpu().numpy() - fx['rel_dists']).max() <= 1e-4
+    assert abs(float(loss) - float(fx['loss'])) <= 2e-3
+    assert np.abs(model.union_boxes.conv[2].running_mean.cpu().numpy() - fx['rm1']).max() <= 1e-6
+    assert np.abs(model.union_boxes.conv[6].running_var.cpu().numpy() - fx['rv2']).max() <= 1e-6
+    params = dict(model.named_parameters())
+    names = [str(n) for n in fx['names']]
+    assert len(names) == 40
+    for k in names:
+        gq = params[k].grad
+        assert gq is not None, 'no gradient for ' + k
+        kk = k.replace('.', '__')
+        flat = gq.detach().cpu().numpy().reshape(-1)
+        ref = fx['val__' + kk]; got = flat[fx['idx__' + kk]]
+        asum_ref = float(fx['asum__' + kk])
+        # scale: the tensor's mean |gradient| (the sampled entries of the huge fc6 matrices can all be tiny)
+        scale = max(float(np.abs(ref).max()), asum_ref / flat.shape[0], 1e-12)
+        err = float(np.abs(got - ref).max()) / scale
+        assert err <= 5e-4, '%s: max|d|/scale = %.3e' % (k, err)
+        asum = float(np.abs(flat).astype(np.float64).sum())
+        assert abs(asum - asum_ref) <= 5e-4 * max(asum_ref, 1e-12), k
+
+
 @pytest.mark.parametrize('mode', ['predcls', 'sgcls'])
 def test_l3_forward_eval_vs_golden(model, mode):
     fx = cases.load('l3_forward')
