@@ -35,8 +35,9 @@ class Blob(object):
         self.batch_size_per_gpu, self.primary_gpu = batch_size_per_gpu, primary_gpu
         self.torch_detector, self.is_cuda = torch_detector, is_cuda
         self.fns, self.imgs, self.im_sizes = [], [], []
-        self.gt_boxes, self.gt_classes, self.gt_rels, self.proposals = [], [], [], []
+        self.gt_boxes = self.gt_classes = self.gt_rels = self.proposals = None
         self.gt_box_chunks = self.gt_rel_chunks = self.proposal_chunks = None
+        self._entries = []                # per-image raw arrays; the (image, ...) index columns are built in reduce()
 
     @property
     def is_rel(self):
@@ -47,51 +48,56 @@ class Blob(object):
         return not self.is_train
 
     def append(self, d):
-        """Add one dataset entry (dataloaders/blob.py:77-124)."""
+        """Add one dataset entry (visual_genome.py:439-449 dict; wire format of dataloaders/blob.py:77-124)."""
         self.fns.append(os.path.basename(d['fn']))
-        i = len(self.imgs)
         self.imgs.append(d['img'])
-        h, w, scale = d['img_size']
-        self.im_sizes.append((h, w, scale))
-        self.gt_boxes.append(d['gt_boxes'].astype(np.float32) * d['scale'])
-        self.gt_classes.append(np.column_stack((i * np.ones(d['gt_classes'].shape[0], dtype=np.int64), d['gt_classes'])))
-        if self.is_rel:
-            self.gt_rels.append(np.column_stack((i * np.ones(d['gt_relations'].shape[0], dtype=np.int64),
-                                                 d['gt_relations'])))
-        if 'proposals' in d:
-            self.proposals.append(np.column_stack((i * np.ones(d['proposals'].shape[0], dtype=np.float32),
-                                                   d['scale'] * d['proposals'].astype(np.float32))))
+        self.im_sizes.append(tuple(d['img_size']))            # (h, w, scale)
+        sc = d['scale']
+        self._entries.append({
+            'boxes': np.asarray(d['gt_boxes'], np.float32) * sc,
+            'classes': np.asarray(d['gt_classes'], np.int64).reshape(-1),
+            'rels': np.asarray(d['gt_relations'], np.int64).reshape(-1, 3) if self.is_rel else None,
+            'props': sc * np.asarray(d['proposals'], np.float32) if 'proposals' in d else None,
+        })
 
     def _pin(self, t):
         if self.is_cuda and torch.cuda.is_available():
             return t.pin_memory()
         return t
 
-    def _chunkize(self, datom, dtype=torch.int64):
-        """Flat tensor + rows per GPU (dataloaders/blob.py:128-142).  An empty list of rows gives 0, as there."""
-        chunk_sizes = [0] * self.num_gpus
-        for i in range(self.num_gpus):
-            for j in range(self.batch_size_per_gpu):
-                chunk_sizes[i] += datom[i * self.batch_size_per_gpu + j].shape[0]
-        t = np.concatenate(datom, 0)
-        if len(t) == 0:
-            return 0, chunk_sizes
-        return self._pin(torch.from_numpy(np.ascontiguousarray(t)).to(dtype)), chunk_sizes
+    def _flatten(self, key, index_dtype, out_dtype):
+        """Rows of every image stacked, optionally prefixed by the image-index column; plus rows per GPU.
+        Returns (tensor or 0 when there are no rows at all — as the reference does —, per-GPU row counts)."""
+        rows = [e[key] for e in self._entries]
+        counts = np.array([r.shape[0] for r in rows], dtype=np.int64)
+        per_gpu = counts.reshape(self.num_gpus, self.batch_size_per_gpu).sum(1).tolist()
+        if counts.sum() == 0:
+            return 0, per_gpu
+        flat = np.concatenate([r.reshape(r.shape[0], -1) for r in rows], 0)
+        if index_dtype is not None:
+            img = np.repeat(np.arange(len(rows)), counts).astype(index_dtype)
+            flat = np.concatenate((img[:, None], flat.astype(index_dtype)), 1)
+        return self._pin(torch.from_numpy(np.ascontiguousarray(flat)).to(out_dtype)), per_gpu
 
     def reduce(self):
-        """Merge the per-image lists into flat tensors + per-GPU row counts (dataloaders/blob.py:145-169)."""
-        if len(self.imgs) != self.batch_size_per_gpu * self.num_gpus:
+        """Per-image lists -> flat pinned tensors + per-GPU row counts (dataloaders/blob.py:145-169)."""
+        want = self.batch_size_per_gpu * self.num_gpus
+        if len(self.imgs) != want:
             raise ValueError('Wrong batch size? imgs len {} bsize/gpu {} numgpus {}'.format(
                 len(self.imgs), self.batch_size_per_gpu, self.num_gpus))
         if not self.torch_detector:
             self.imgs = self._pin(torch.stack(self.imgs, 0))
-        self.im_sizes = np.stack(self.im_sizes).reshape((self.num_gpus, self.batch_size_per_gpu, 3))
+        self.im_sizes = np.asarray(self.im_sizes).reshape(self.num_gpus, self.batch_size_per_gpu, 3)
+        self.gt_boxes, self.gt_box_chunks = self._flatten('boxes', None, torch.float32)
+        self.gt_classes, _ = self._flatten('classes', np.int64, torch.int64)
         if self.is_rel:
-            self.gt_rels, self.gt_rel_chunks = self._chunkize(self.gt_rels)
-        self.gt_boxes, self.gt_box_chunks = self._chunkize(self.gt_boxes, dtype=torch.float32)
-        self.gt_classes, _ = self._chunkize(self.gt_classes)
-        if len(self.proposals) != 0:
-            self.proposals, self.proposal_chunks = self._chunkize(self.proposals, dtype=torch.float32)
+            self.gt_rels, self.gt_rel_chunks = self._flatten('rels', np.int64, torch.int64)
+        else:
+            self.gt_rels = []
+        if any(e['props'] is not None for e in self._entries):
+            self.proposals, self.proposal_chunks = self._flatten('props', np.float32, torch.float32)
+        else:
+            self.proposals = []
 
     def _to_device(self, x, device=None):
         if not self.is_cuda or not isinstance(x, torch.Tensor):

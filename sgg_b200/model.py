@@ -31,7 +31,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import host, ops
+from . import heads, host, ops
 from . import autograd as K
 from .host import Result, IM_SCALE, BATCHNORM_MOMENTUM
 
@@ -237,26 +237,10 @@ class RelModelStanford(RelModelBase):
     def __init__(self, train_data, hidden_dim=512, mp_iter=3, **kwargs):
         super().__init__(train_data, **kwargs)
         self.hidden_dim, self.mp_iter = hidden_dim, mp_iter
-        self.rel_fc = nn.Linear(hidden_dim, self.num_rels)
-        self.obj_fc = nn.Linear(hidden_dim, self.num_classes)
-        self.obj_unary = nn.Linear(self.obj_dim, hidden_dim)
-        self.edge_unary = nn.Linear(self.obj_dim, hidden_dim)
-        self.edge_gru = nn.GRUCell(input_size=hidden_dim, hidden_size=hidden_dim)
-        self.node_gru = nn.GRUCell(input_size=hidden_dim, hidden_size=hidden_dim)
-        gate = lambda: nn.Sequential(nn.Linear(hidden_dim * 2, 1), nn.Sigmoid())
-        self.sub_vert_w_fc, self.obj_vert_w_fc = gate(), gate()
-        self.out_edge_w_fc, self.in_edge_w_fc = gate(), gate()
+        heads.add_imp_heads(self, hidden_dim, self.obj_dim, self.num_classes, self.num_rels)     # :27-45, reference order
 
     def _mp_params(self):
-        p = OrderedDict()
-        for g in ('edge_gru', 'node_gru'):
-            m = getattr(self, g)
-            for k in ('weight_ih', 'weight_hh', 'bias_ih', 'bias_hh'):
-                p[g + '.' + k] = getattr(m, k)
-        for g in ('sub_vert_w_fc', 'obj_vert_w_fc', 'out_edge_w_fc', 'in_edge_w_fc'):
-            p[g + '.0.weight'] = getattr(self, g)[0].weight
-            p[g + '.0.bias'] = getattr(self, g)[0].bias
-        return p
+        return heads.mp_params(self)
 
     def message_pass(self, rel_rep, obj_rep, rel_inds):
         """rel_rep [E,H], obj_rep [N,H], rel_inds [E,2] global (subject, object) ids -> (V_T, E_T)."""
