@@ -39,6 +39,61 @@ __device__ __forceinline__ void tma_load_4d(void *smem_dst, const CUtensorMap *m
       : "memory");
 }
 
+// ---- cta_group::2 (one 256-row UMMA tile per CTA pair; each CTA stages its own 128 pixel rows and HALF of the weight slab) ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `local` (a shared::cta address) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// pair loads: the destination is this CTA's shared memory, the transaction bytes are counted on the LEADER's barrier
+__device__ __forceinline__ void tma_load_4d_pair(void *smem_dst, const CUtensorMap *m, uint32_t leader_bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+          tc::smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(void *smem_dst, const CUtensorMap *m, uint32_t leader_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          tc::smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void mma_f16_ss_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// all MMAs issued so far by this thread complete -> one arrival on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void mma_commit_pair(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   tc::smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t *dst_smem, uint32_t ncols) {   // one full warp in EACH CTA of the pair
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t addr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
+}
+
 __device__ __forceinline__ void mbar_wait_b(uint64_t *bar, uint32_t parity) {
   uint32_t done = 0;
   for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
@@ -52,25 +107,29 @@ __device__ __forceinline__ void mbar_wait_b(uint64_t *bar, uint32_t parity) {
   __trap();
 }
 
-template <int NC>
+template <int NC, int CG>
 struct CCfg {
   static constexpr int A_PLANE = BM * BK * 2;              // 16 KB
-  static constexpr int B_PLANE = NC * BK * 2;
-  static constexpr int STAGE = 2 * A_PLANE + 2 * B_PLANE;  // NC = 128: 64 KB; NC = 64: 48 KB
-  static constexpr int STAGES = NC == 128 ? 3 : 4;
+  static constexpr int B_PLANE = (NC / CG) * BK * 2;       // CG = 2: this CTA's half of the weight slab
+  static constexpr int STAGE = 2 * A_PLANE + 2 * B_PLANE;  // NC = 128: 64 KB (pair: 48 KB); NC = 64: 48 KB (pair: 40 KB)
+  static constexpr int STAGES = STAGE > 48 * 1024 ? 3 : 4;
   static constexpr int RING = STAGES * STAGE;
   static constexpr int SMEM = RING + 1024 + 256;
   static constexpr int TS = NC + 4;                        // fp32 staging tile row stride (pool / NCHW epilogues)
   static_assert(BM * TS * 4 <= RING, "staging tile must fit in the ring");
 };
 
-template <int NC>
+// CG = 1: one CTA per 128-pixel tile.  CG = 2: launched as clusters of two CTAs (adjacent tiles of the same channel
+// block); the even CTA issues cta_group::2 MMAs (M = 256) that read both CTAs' pixel rows and the two halves of the
+// weight slab, so each SM stages and re-reads only NC / 2 weight rows per k-block.
+template <int NC, int CG>
 __global__ void __launch_bounds__(NTHR, 1)
 k_conv3x3(const ConvParams p, const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
           const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl) {
   using namespace tc;
-  using C = CCfg<NC>;
+  using C = CCfg<NC, CG>;
   constexpr int STAGES = C::STAGES, STAGE = C::STAGE, KCB = 256 / BK;
+  const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
   constexpr uint32_t TMEM_COLS = 4 * NC <= 256 ? 256 : 512;
 
   extern __shared__ uint8_t smem_raw[];
@@ -92,14 +151,17 @@ k_conv3x3(const ConvParams p, const __grid_constant__ CUtensorMap tmAh, const __
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmAh); prefetch_tmap(&tmAl); prefetch_tmap(&tmBh); prefetch_tmap(&tmBl);
-    for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+    // pair: `full` and `tmem_empty` are used on the leader only (one arrival per producer / per draining thread of both CTAs)
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, CG); mbar_init(empty + s, 1); }
     mbar_init(tmem_full, 1); mbar_init(tmem_full + 1, 1);
-    mbar_init(tmem_empty, 256); mbar_init(tmem_empty + 1, 256);
+    mbar_init(tmem_empty, CG == 2 ? 16 : 256); mbar_init(tmem_empty + 1, CG == 2 ? 16 : 256);   // pair: one arrival per warp
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  if (warp == 1) {
+    if constexpr (CG == 2) tmem_alloc_pair(tmem_slot, TMEM_COLS); else tmem_alloc(tmem_slot, TMEM_COLS);
+  }
   fence_before_sync();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -112,17 +174,27 @@ k_conv3x3(const ConvParams p, const __grid_constant__ CUtensorMap tmAh, const __
         const int cb = it / 9, tap = it - cb * 9;
         const int dy = tap / 3, dx = tap - dy * 3;
         uint8_t *st = smem + (size_t)s * STAGE;
-        mbar_arrive_expect_tx(full + s, STAGE);
-        tma_load_4d(st, &tmAh, full + s, cb * BK, w0 + dx - 1, h0 + dy - 1, n);
-        tma_load_4d(st + C::A_PLANE, &tmAl, full + s, cb * BK, w0 + dx - 1, h0 + dy - 1, n);
-        tma_load_2d(st + 2 * C::A_PLANE, &tmBh, full + s, tap * p.Cin + cb * BK, cout0);
-        tma_load_2d(st + 2 * C::A_PLANE + C::B_PLANE, &tmBl, full + s, tap * p.Cin + cb * BK, cout0);
+        if constexpr (CG == 2) {
+          const uint32_t lbar = mapa_u32(smem_u32(full + s), 0);
+          if (rank == 0) mbar_arrive_expect_tx(full + s, 2 * STAGE); else mbar_arrive_cluster(lbar);
+          const int brow = cout0 + (int)rank * (NC / 2);
+          tma_load_4d_pair(st, &tmAh, lbar, cb * BK, w0 + dx - 1, h0 + dy - 1, n);
+          tma_load_4d_pair(st + C::A_PLANE, &tmAl, lbar, cb * BK, w0 + dx - 1, h0 + dy - 1, n);
+          tma_load_2d_pair(st + 2 * C::A_PLANE, &tmBh, lbar, tap * p.Cin + cb * BK, brow);
+          tma_load_2d_pair(st + 2 * C::A_PLANE + C::B_PLANE, &tmBl, lbar, tap * p.Cin + cb * BK, brow);
+        } else {
+          mbar_arrive_expect_tx(full + s, STAGE);
+          tma_load_4d(st, &tmAh, full + s, cb * BK, w0 + dx - 1, h0 + dy - 1, n);
+          tma_load_4d(st + C::A_PLANE, &tmAl, full + s, cb * BK, w0 + dx - 1, h0 + dy - 1, n);
+          tma_load_2d(st + 2 * C::A_PLANE, &tmBh, full + s, tap * p.Cin + cb * BK, cout0);
+          tma_load_2d(st + 2 * C::A_PLANE + C::B_PLANE, &tmBl, full + s, tap * p.Cin + cb * BK, cout0);
+        }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_f16(BM, NC);
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(BM * CG, NC);
       for (int it = 0; it < kblocks; ++it) {
         const int s = it % STAGES, ph = (it / STAGES) & 1;
         mbar_wait_b(full + s, ph);
@@ -140,12 +212,23 @@ k_conv3x3(const ConvParams p, const __grid_constant__ CUtensorMap tmAh, const __
         for (int kk = 0; kk < BK / 16; ++kk) {
           const uint64_t o = (uint64_t)(kk * 2);
           const uint32_t acc = (kc == 0 && kk == 0) ? 0u : 1u;
-          mma_f16_ss(dc, al + o, bh + o, idesc, acc);
-          mma_f16_ss(dc, ah + o, bl + o, idesc, 1u);
-          mma_f16_ss(dm, ah + o, bh + o, idesc, acc);
+          if constexpr (CG == 2) {
+            mma_f16_ss_pair(dc, al + o, bh + o, idesc, acc);
+            mma_f16_ss_pair(dc, ah + o, bl + o, idesc, 1u);
+            mma_f16_ss_pair(dm, ah + o, bh + o, idesc, acc);
+          } else {
+            mma_f16_ss(dc, al + o, bh + o, idesc, acc);
+            mma_f16_ss(dc, ah + o, bl + o, idesc, 1u);
+            mma_f16_ss(dm, ah + o, bh + o, idesc, acc);
+          }
         }
-        mma_commit(empty + s);
-        if (kc == KCB - 1 || it == kblocks - 1) mma_commit(tmem_full + (chunk & 1));
+        if constexpr (CG == 2) {
+          mma_commit_pair(empty + s);
+          if (kc == KCB - 1 || it == kblocks - 1) mma_commit_pair(tmem_full + (chunk & 1));
+        } else {
+          mma_commit(empty + s);
+          if (kc == KCB - 1 || it == kblocks - 1) mma_commit(tmem_full + (chunk & 1));
+        }
       }
     }
   } else {
@@ -172,7 +255,12 @@ k_conv3x3(const ConvParams p, const __grid_constant__ CUtensorMap tmAh, const __
         for (int cc = 0; cc < 16; ++cc) acc[c0 + cc] += fmaf(w[cc], LO_INV, v[cc]);
       }
       fence_before_sync();
-      mbar_arrive(tmem_empty + b);
+      if constexpr (CG == 2) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(tmem_empty + b), 0));
+      } else {
+        mbar_arrive(tmem_empty + b);
+      }
     }
     // bias + ReLU
     const int cbase = cout0 + half * HC;
@@ -189,7 +277,7 @@ k_conv3x3(const ConvParams p, const __grid_constant__ CUtensorMap tmAh, const __
     const int y = h0 + ty, x = w0 + tx;
     if (!p.pool && p.out_f32 == nullptr) {
       // planes, NHWC: this thread's pixel, HC consecutive channels (HC * 2 bytes contiguous per plane)
-      if (y < p.H && x < p.W) {
+      if (n < p.B && y < p.H && x < p.W) {
         const size_t off = (((size_t)n * p.H + y) * p.W + x) * p.Cout + cbase;
         uint32_t ovf = 0;
 #pragma unroll
@@ -229,7 +317,7 @@ k_conv3x3(const ConvParams p, const __grid_constant__ CUtensorMap tmAh, const __
             v = tile[(size_t)pp * TS + c];
           }
           const int gy = (p.pool ? h0 / 2 : h0) + oy, gx = (p.pool ? w0 / 2 : w0) + ox;
-          if (gy < Ho && gx < Wo) p.out_f32[(((size_t)n * p.Cout + cout0 + c) * Ho + gy) * Wo + gx] = v;
+          if (n < p.B && gy < Ho && gx < Wo) p.out_f32[(((size_t)n * p.Cout + cout0 + c) * Ho + gy) * Wo + gx] = v;
         }
       } else {
         // pooled planes, NHWC: thread <-> (output pixel, 8 consecutive channels)
@@ -250,7 +338,7 @@ k_conv3x3(const ConvParams p, const __grid_constant__ CUtensorMap tmAh, const __
             v[k + 2] = fmaxf(fmaxf(a.z, b.z), fmaxf(d.z, e.z)); v[k + 3] = fmaxf(fmaxf(a.w, b.w), fmaxf(d.w, e.w));
           }
           const int gy = h0 / 2 + oy, gx = w0 / 2 + ox;
-          if (gy < Ho && gx < Wo) {
+          if (n < p.B && gy < Ho && gx < Wo) {
             uint4 hi, lo;
             split2(v[0], v[1], hi.x, lo.x); split2(v[2], v[3], hi.y, lo.y);
             split2(v[4], v[5], hi.z, lo.z); split2(v[6], v[7], hi.w, lo.w);
@@ -265,8 +353,287 @@ k_conv3x3(const ConvParams p, const __grid_constant__ CUtensorMap tmAh, const __
     }
   }
   tc::fence_before_sync();
-  __syncthreads();
-  if (warp == 1) tc::tmem_dealloc(tmem_base, TMEM_COLS);
+  if constexpr (CG == 2) {
+    cluster_sync_all();                      // no remote arrival may still be in flight towards a CTA that has exited
+    if (warp == 1) tmem_dealloc_pair(tmem_base, TMEM_COLS);
+  } else {
+    __syncthreads();
+    if (warp == 1) tc::tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// v2: halo tiles + persistent CTAs.
+// The v1 kernel above fetches the A operand of every tap separately (nine shifted 128-pixel boxes per 64-channel block) and
+// runs one tile per CTA; ncu (profiles/r02_ncu_conv.md) shows the deep layers AT the L2 -> SM throughput cap (11.9 TB/s,
+// 6300 B/clk) with the tensor pipe 52 % busy, and the Cin = 64 layers bound by per-tile prologue / epilogue (18 %).
+// Here the output tile is 16 rows x 8 columns and ONE 18 x 10 pixel halo box per channel block serves all nine taps: the
+// UMMA shared-memory descriptor of tap (dy, dx) simply starts (dy * 10 + dx) pixel rows into the halo, with a stride of
+// 10 pixel rows (1280 B) between the 8-row groups.  The 128-byte swizzle is a function of the shared-memory ADDRESS, so a
+// descriptor may start at any 128-byte row of a TMA-written box and use any group stride (tools/ubench/umma_shift.cu,
+// measured on B200).  A bytes per tile and channel block drop from 288 KB to 46 KB.  CTAs are persistent: each loops over
+// (channel tile, spatial tile) work items, the TMEM ping-pong and both shared-memory rings run across item boundaries, and
+// the drain warps' epilogue (bias, ReLU, 2x2 max-pool by warp shuffles, stores) overlaps the next item's main loop.
+constexpr int VH = 16, VW = 8;               // output tile (rows x columns) = 128 pixels; GEMM row m = ty * 8 + tx
+constexpr int HP = VW + 2;                   // halo pitch (pixel rows per halo line)
+constexpr int HALO_ROWS = (VH + 2) * HP;     // 180 pixel rows of 128 B
+constexpr int HALO_PLANE = ((HALO_ROWS * 128 + 1023) / 1024) * 1024;   // 23552 B (1024-aligned plane base for the swizzle)
+
+template <int NC, int CG>
+struct VCfg {
+  static constexpr int A_STAGE = 2 * HALO_PLANE;            // hi + lo halo of one 64-channel block
+  static constexpr int A_STAGES = 2;
+  static constexpr int B_PLANE = (NC / CG) * BK * 2;        // one tap, one plane (this CTA's share of the channel tile)
+  static constexpr int B_STAGE = 2 * B_PLANE;
+  static constexpr int B_STAGES = (225 * 1024 - A_STAGES * A_STAGE) / B_STAGE > 8 ? 8 : (225 * 1024 - A_STAGES * A_STAGE) / B_STAGE;
+  static constexpr int RING = A_STAGES * A_STAGE + B_STAGES * B_STAGE;
+  static constexpr int SMEM = RING + 1024 + 512;
+};
+
+__device__ __forceinline__ uint64_t make_sdesc128_sbo(uint32_t smem_addr, uint32_t sbo_bytes) {
+  return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+template <int NC, int CG>
+__global__ void __launch_bounds__(NTHR, 1)
+k_conv3x3_v2(const ConvParams p, const int n_items, const int n_sp, const __grid_constant__ CUtensorMap tmAh,
+             const __grid_constant__ CUtensorMap tmAl, const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl) {
+  using namespace tc;
+  using C = VCfg<NC, CG>;
+  constexpr int AS = C::A_STAGES, BS = C::B_STAGES, KCB = 256 / BK;
+  constexpr uint32_t TMEM_COLS = 4 * NC <= 256 ? 256 : 512;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t *ring_a = smem, *ring_b = smem + AS * C::A_STAGE;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + C::RING);
+  uint64_t *a_full = bars, *a_empty = bars + AS, *b_full = bars + 2 * AS, *b_empty = bars + 2 * AS + BS;
+  uint64_t *tmem_full = bars + 2 * AS + 2 * BS, *tmem_empty = tmem_full + 2;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
+  const int unit = (int)blockIdx.x / CG, n_units = (int)gridDim.x / CG;   // a unit = one CTA or one CTA pair
+  const int cblocks = p.Cin / BK;
+  const int kblocks = 9 * cblocks;
+  const int nchunks = (kblocks + KCB - 1) / KCB;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmAh); prefetch_tmap(&tmAl); prefetch_tmap(&tmBh); prefetch_tmap(&tmBl);
+    // pair: the `full` and `tmem_empty` barriers live on the leader (one arrival per producer / per draining warp of both CTAs)
+    for (int s = 0; s < AS; ++s) { mbar_init(a_full + s, CG); mbar_init(a_empty + s, 1); }
+    for (int s = 0; s < BS; ++s) { mbar_init(b_full + s, CG); mbar_init(b_empty + s, 1); }
+    mbar_init(tmem_full, 1); mbar_init(tmem_full + 1, 1);
+    mbar_init(tmem_empty, 8 * CG); mbar_init(tmem_empty + 1, 8 * CG);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    if constexpr (CG == 2) tmem_alloc_pair(tmem_slot, TMEM_COLS); else tmem_alloc(tmem_slot, TMEM_COLS);
+  }
+  fence_before_sync();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // work item -> (channel tile, image, tile row, tile column) of THIS CTA; spatial index n_sp.. is padding (n = B: loads are
+  // zero-filled by TMA, stores are masked)
+  auto decode = [&](int item, int &cout0, int &n, int &h0, int &w0) {
+    const int ct = item / n_sp;
+    int t = (item - ct * n_sp) * CG + (int)rank;
+    cout0 = ct * NC;
+    const int tw = t % p.tiles_w; t /= p.tiles_w;
+    const int th = t % p.tiles_h;
+    n = t / p.tiles_h; h0 = th * VH; w0 = tw * VW;
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer: per channel block one halo (hi, lo), then nine weight taps =====================
+    if (lane == 0) {
+      uint32_t ga = 0, gb = 0;                 // halos / taps issued so far (ring position and phase)
+      for (int item = unit; item < n_items; item += n_units) {
+        int cout0, n, h0, w0;
+        decode(item, cout0, n, h0, w0);
+        const int brow = cout0 + (int)rank * (NC / CG);
+        for (int cb = 0; cb < cblocks; ++cb) {
+          {
+            const uint32_t s = ga % AS, ph = (ga / AS) & 1; ++ga;
+            mbar_wait_b(a_empty + s, ph ^ 1);
+            uint8_t *st = ring_a + (size_t)s * C::A_STAGE;
+            constexpr uint32_t HALO_TX = HALO_ROWS * 128;      // bytes one halo box delivers
+            if constexpr (CG == 2) {
+              const uint32_t lbar = mapa_u32(smem_u32(a_full + s), 0);
+              if (rank == 0) mbar_arrive_expect_tx(a_full + s, 4 * HALO_TX); else mbar_arrive_cluster(lbar);
+              tma_load_4d_pair(st, &tmAh, lbar, cb * BK, w0 - 1, h0 - 1, n);
+              tma_load_4d_pair(st + HALO_PLANE, &tmAl, lbar, cb * BK, w0 - 1, h0 - 1, n);
+            } else {
+              mbar_arrive_expect_tx(a_full + s, 2 * HALO_TX);
+              tma_load_4d(st, &tmAh, a_full + s, cb * BK, w0 - 1, h0 - 1, n);
+              tma_load_4d(st + HALO_PLANE, &tmAl, a_full + s, cb * BK, w0 - 1, h0 - 1, n);
+            }
+          }
+          for (int tap = 0; tap < 9; ++tap) {
+            const uint32_t s = gb % BS, ph = (gb / BS) & 1; ++gb;
+            mbar_wait_b(b_empty + s, ph ^ 1);
+            uint8_t *st = ring_b + (size_t)s * C::B_STAGE;
+            if constexpr (CG == 2) {
+              const uint32_t lbar = mapa_u32(smem_u32(b_full + s), 0);
+              if (rank == 0) mbar_arrive_expect_tx(b_full + s, 2 * C::B_STAGE); else mbar_arrive_cluster(lbar);
+              tma_load_2d_pair(st, &tmBh, lbar, tap * p.Cin + cb * BK, brow);
+              tma_load_2d_pair(st + C::B_PLANE, &tmBl, lbar, tap * p.Cin + cb * BK, brow);
+            } else {
+              mbar_arrive_expect_tx(b_full + s, C::B_STAGE);
+              tma_load_2d(st, &tmBh, b_full + s, tap * p.Cin + cb * BK, brow);
+              tma_load_2d(st + C::B_PLANE, &tmBl, b_full + s, tap * p.Cin + cb * BK, brow);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (pair: the leader only) =====================
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(BM * CG, NC);
+      uint32_t ga = 0, gb = 0, gch = 0;
+      for (int item = unit; item < n_items; item += n_units) {
+        for (int cb = 0; cb < cblocks; ++cb) {
+          const uint32_t as = ga % AS, aph = (ga / AS) & 1; ++ga;
+          mbar_wait_b(a_full + as, aph);
+          const uint32_t a_hi = smem_u32(ring_a + (size_t)as * C::A_STAGE), a_lo = a_hi + HALO_PLANE;
+          for (int tap = 0; tap < 9; ++tap) {
+            const uint32_t bs = gb % BS, bph = (gb / BS) & 1; ++gb;
+            mbar_wait_b(b_full + bs, bph);
+            fence_after_sync();
+            const int it = cb * 9 + tap;
+            const int chunk = it / KCB, kc = it - chunk * KCB;
+            const uint32_t gc = gch + (uint32_t)chunk;
+            if (kc == 0) {                     // the buffer pair must have been drained (two chunks ago)
+              mbar_wait_b(tmem_empty + (gc & 1), ((gc >> 1) & 1) ^ 1);
+              fence_after_sync();
+            }
+            const int dy = tap / 3, dx = tap - dy * 3;
+            const uint32_t shift = (uint32_t)((dy * HP + dx) * 128);
+            const uint64_t ah = make_sdesc128_sbo(a_hi + shift, HP * 128), al = make_sdesc128_sbo(a_lo + shift, HP * 128);
+            uint8_t *st = ring_b + (size_t)bs * C::B_STAGE;
+            const uint64_t bh = make_sdesc128(st), bl = make_sdesc128(st + C::B_PLANE);
+            const uint32_t dm = tmem_base + (uint32_t)((gc & 1) * 2 * NC), dc = dm + (uint32_t)NC;
+#pragma unroll
+            for (int kk = 0; kk < BK / 16; ++kk) {
+              const uint64_t o = (uint64_t)(kk * 2);
+              const uint32_t acc = (kc == 0 && kk == 0) ? 0u : 1u;
+              if constexpr (CG == 2) {
+                mma_f16_ss_pair(dc, al + o, bh + o, idesc, acc);
+                mma_f16_ss_pair(dc, ah + o, bl + o, idesc, 1u);
+                mma_f16_ss_pair(dm, ah + o, bh + o, idesc, acc);
+              } else {
+                mma_f16_ss(dc, al + o, bh + o, idesc, acc);
+                mma_f16_ss(dc, ah + o, bl + o, idesc, 1u);
+                mma_f16_ss(dm, ah + o, bh + o, idesc, acc);
+              }
+            }
+            const bool chunk_end = kc == KCB - 1 || it == kblocks - 1;
+            if constexpr (CG == 2) {
+              mma_commit_pair(b_empty + bs);
+              if (tap == 8) mma_commit_pair(a_empty + as);
+              if (chunk_end) mma_commit_pair(tmem_full + (gc & 1));
+            } else {
+              mma_commit(b_empty + bs);
+              if (tap == 8) mma_commit(a_empty + as);
+              if (chunk_end) mma_commit(tmem_full + (gc & 1));
+            }
+          }
+        }
+        gch += (uint32_t)nchunks;
+      }
+    }
+  } else {
+    // ===================== warps 2..9: thread <-> (pixel of the tile, half of the tile's channels) =====================
+    constexpr int HC = NC / 2;
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    const int row = q * 32 + lane;
+    const int ty = row >> 3, tx = row & 7;
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * HC);
+    uint32_t gch = 0, ovf = 0;
+    for (int item = unit; item < n_items; item += n_units) {
+      int cout0, n, h0, w0;
+      decode(item, cout0, n, h0, w0);
+      float acc[HC];
+#pragma unroll
+      for (int c = 0; c < HC; ++c) acc[c] = 0.f;
+      for (int ch = 0; ch < nchunks; ++ch, ++gch) {
+        const uint32_t b = gch & 1;
+        mbar_wait_b(tmem_full + b, (gch >> 1) & 1);
+        fence_after_sync();
+        __syncwarp();
+#pragma unroll
+        for (int c0 = 0; c0 < HC; c0 += 16) {
+          float v[16], w[16];
+          tmem_ld16(taddr + (uint32_t)(b * 2 * NC + c0), v);
+          tmem_ld16(taddr + (uint32_t)(b * 2 * NC + NC + c0), w);
+          tmem_wait_ld();
+#pragma unroll
+          for (int cc = 0; cc < 16; ++cc) acc[c0 + cc] += fmaf(w[cc], LO_INV, v[cc]);
+        }
+        fence_before_sync();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (CG == 2) mbar_arrive_cluster(mapa_u32(smem_u32(tmem_empty + b), 0)); else mbar_arrive(tmem_empty + b);
+        }
+      }
+      // ---- epilogue of this item (the MMA warp is already filling the ping-pong buffers with the next item) ----
+      const int cbase = cout0 + half * HC;
+#pragma unroll
+      for (int c = 0; c < HC; c += 4) {
+        const float4 bv = p.bias != nullptr ? ldg4(p.bias + cbase + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        acc[c] += bv.x; acc[c + 1] += bv.y; acc[c + 2] += bv.z; acc[c + 3] += bv.w;
+        if (p.relu) {
+          acc[c] = fmaxf(acc[c], 0.f); acc[c + 1] = fmaxf(acc[c + 1], 0.f);
+          acc[c + 2] = fmaxf(acc[c + 2], 0.f); acc[c + 3] = fmaxf(acc[c + 3], 0.f);
+        }
+      }
+      int y = h0 + ty, x = w0 + tx, Ho = p.H, Wo = p.W;
+      bool writer = true;
+      if (p.pool) {
+        // 2x2 windows live inside one warp: partner pixels are lanes ^ 1 (tx) and ^ 8 (ty)
+#pragma unroll
+        for (int c = 0; c < HC; ++c) {
+          float v = acc[c];
+          v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+          v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 8));
+          acc[c] = v;
+        }
+        writer = !(tx & 1) && !(ty & 1);
+        y >>= 1; x >>= 1; Ho >>= 1; Wo >>= 1;
+      }
+      if (writer && n < p.B && y < Ho && x < Wo) {
+        if (p.out_f32 != nullptr) {
+          float *dst = p.out_f32 + (((size_t)n * p.Cout + cbase) * Ho + y) * Wo + x;
+          const size_t cs = (size_t)Ho * Wo;
+#pragma unroll
+          for (int c = 0; c < HC; ++c) dst[(size_t)c * cs] = acc[c];
+        } else {
+          const size_t off = (((size_t)n * Ho + y) * Wo + x) * p.Cout + cbase;
+#pragma unroll
+          for (int c = 0; c < HC; c += 8) {
+            uint4 hi, lo;
+            split2(acc[c], acc[c + 1], hi.x, lo.x); split2(acc[c + 2], acc[c + 3], hi.y, lo.y);
+            split2(acc[c + 4], acc[c + 5], hi.z, lo.z); split2(acc[c + 6], acc[c + 7], hi.w, lo.w);
+            ovf |= f16x2_nonfinite(hi.x) | f16x2_nonfinite(hi.y) | f16x2_nonfinite(hi.z) | f16x2_nonfinite(hi.w);
+            *reinterpret_cast<uint4 *>(p.out_hi + off + c) = hi;
+            *reinterpret_cast<uint4 *>(p.out_lo + off + c) = lo;
+          }
+        }
+      }
+    }
+    if (ovf) atomicOr(&g_conv_overflow, 1u);
+  }
+  tc::fence_before_sync();
+  if constexpr (CG == 2) {
+    cluster_sync_all();
+    if (warp == 1) tmem_dealloc_pair(tmem_base, TMEM_COLS);
+  } else {
+    __syncthreads();
+    if (warp == 1) tc::tmem_dealloc(tmem_base, TMEM_COLS);
+  }
 }
 
 // First VGG layer: 3 -> Cout (64) channels, fp32 NCHW image in, relu(conv) as NHWC fp16 planes out.
@@ -334,12 +701,12 @@ __global__ void k_conv_weight_planes(const float *__restrict__ w, int Cout, int 
   }
 }
 
-static int make_tmap_4d(CUtensorMap *m, const void *base, int B, int H, int W, int Cc) {
+static int make_tmap_4d(CUtensorMap *m, const void *base, int B, int H, int W, int Cc, int box_w = TW, int box_h = TH) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return sgg_set_err(SGG_E_BADARG, "cuTensorMapEncodeTiled unavailable");
   cuuint64_t gdim[4] = {(cuuint64_t)Cc, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
   cuuint64_t gstr[3] = {(cuuint64_t)Cc * 2, (cuuint64_t)W * Cc * 2, (cuuint64_t)H * W * Cc * 2};
-  cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)TW, (cuuint32_t)TH, 1};
+  cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void *)base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -347,26 +714,97 @@ static int make_tmap_4d(CUtensorMap *m, const void *base, int B, int H, int W, i
   return 0;
 }
 
-template <int NC>
+// SGG_CONV_CG = 1 | 2 (default 2): CTAs per UMMA tile
+static int conv_cta_group() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("SGG_CONV_CG");
+    v = (e && atoi(e) == 1) ? 1 : 2;
+  }
+  return v;
+}
+
+template <int NC, int CG>
 static int launch_conv(const ConvParams &p, const __half *in_hi, const __half *in_lo, const __half *w_hi, const __half *w_lo,
                        cudaStream_t st) {
-  using C = CCfg<NC>;
+  using C = CCfg<NC, CG>;
   static bool attr = false;
   if (!attr) {
-    SGG_CUDA_TRY(cudaFuncSetAttribute(k_conv3x3<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    SGG_CUDA_TRY(cudaFuncSetAttribute(k_conv3x3<NC, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
     attr = true;
   }
   CUtensorMap tm[4];
   int rc;
   if ((rc = make_tmap_4d(&tm[0], in_hi, p.B, p.H, p.W, p.Cin))) return rc;
   if ((rc = make_tmap_4d(&tm[1], in_lo, p.B, p.H, p.W, p.Cin))) return rc;
-  if ((rc = make_tmap(&tm[2], w_hi, p.Cout, 9 * p.Cin, NC, 2))) return rc;
-  if ((rc = make_tmap(&tm[3], w_lo, p.Cout, 9 * p.Cin, NC, 2))) return rc;
+  if ((rc = make_tmap(&tm[2], w_hi, p.Cout, 9 * p.Cin, NC / CG, 2))) return rc;
+  if ((rc = make_tmap(&tm[3], w_lo, p.Cout, 9 * p.Cin, NC / CG, 2))) return rc;
   const long long tiles = (long long)p.tiles_w * p.tiles_h * p.B;
-  if (tiles > 0x7fffffffLL) return sgg_set_err(SGG_E_BADARG, "conv3x3: too many tiles");
-  dim3 grid((unsigned)tiles, p.Cout / NC);
-  k_conv3x3<NC><<<grid, NTHR, C::SMEM, st>>>(p, tm[0], tm[1], tm[2], tm[3]);
+  if (tiles > 0x7ffffff0LL) return sgg_set_err(SGG_E_BADARG, "conv3x3: too many tiles");
+  if (CG == 1) {
+    dim3 grid((unsigned)tiles, p.Cout / NC);
+    k_conv3x3<NC, CG><<<grid, NTHR, C::SMEM, st>>>(p, tm[0], tm[1], tm[2], tm[3]);
+  } else {
+    // pairs of adjacent tiles; an odd tile count is padded with a CTA whose image index is B: its loads are
+    // zero-filled (out of bounds) and its stores are masked
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)((tiles + 1) & ~1LL), p.Cout / NC);
+    cfg.blockDim = dim3(NTHR);
+    cfg.dynamicSmemBytes = C::SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    SGG_CUDA_TRY(cudaLaunchKernelEx(&cfg, k_conv3x3<NC, CG>, p, tm[0], tm[1], tm[2], tm[3]));
+  }
   SGG_RETURN_IF_LAUNCH_FAILED("k_conv3x3");
+  return 0;
+}
+
+// SGG_CONV_V = 1 | 2 (default 2): per-tap boxes / halo tiles + persistent CTAs
+static int conv_version() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("SGG_CONV_V");
+    v = (e && atoi(e) == 1) ? 1 : 2;
+  }
+  return v;
+}
+
+template <int NC, int CG>
+static int launch_conv_v2(ConvParams p, const __half *in_hi, const __half *in_lo, const __half *w_hi, const __half *w_lo,
+                          cudaStream_t st) {
+  using C = VCfg<NC, CG>;
+  static bool attr = false;
+  if (!attr) {
+    SGG_CUDA_TRY(cudaFuncSetAttribute(k_conv3x3_v2<NC, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    attr = true;
+  }
+  p.tiles_w = (p.W + VW - 1) / VW; p.tiles_h = (p.H + VH - 1) / VH;
+  CUtensorMap tm[4];
+  int rc;
+  if ((rc = make_tmap_4d(&tm[0], in_hi, p.B, p.H, p.W, p.Cin, HP, VH + 2))) return rc;
+  if ((rc = make_tmap_4d(&tm[1], in_lo, p.B, p.H, p.W, p.Cin, HP, VH + 2))) return rc;
+  if ((rc = make_tmap(&tm[2], w_hi, p.Cout, 9 * p.Cin, NC / CG, 2))) return rc;
+  if ((rc = make_tmap(&tm[3], w_lo, p.Cout, 9 * p.Cin, NC / CG, 2))) return rc;
+  const long long tiles = (long long)p.tiles_w * p.tiles_h * p.B;
+  const long long n_sp = (tiles + CG - 1) / CG;                 // spatial work units (tiles, or pairs of adjacent tiles)
+  const long long items = n_sp * (p.Cout / NC);
+  if (items > 0x7ffffff0LL) return sgg_set_err(SGG_E_BADARG, "conv3x3: too many tiles");
+  const int sms = sgg_num_sms();
+  const long long units = items < sms / CG ? items : sms / CG;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(units * CG));
+  cfg.blockDim = dim3(NTHR);
+  cfg.dynamicSmemBytes = C::SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CG; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  SGG_CUDA_TRY(cudaLaunchKernelEx(&cfg, k_conv3x3_v2<NC, CG>, p, (int)items, (int)n_sp, tm[0], tm[1], tm[2], tm[3]));
+  SGG_RETURN_IF_LAUNCH_FAILED("k_conv3x3_v2");
   return 0;
 }
 
@@ -419,8 +857,19 @@ extern "C" int sgg_conv3x3_tc(const void *in_planes, const void *w_planes, const
   p.out_lo = out_f32_nchw ? nullptr : (__half *)out_planes + n_out;
   p.out_f32 = out_f32_nchw;
   const size_t wn = (size_t)Cout * 9 * Cin;
-  if (Cout % 128 == 0) return launch_conv<128>(p, ih, ih + n_in, wh, wh + wn, (cudaStream_t)stream);
-  return launch_conv<64>(p, ih, ih + n_in, wh, wh + wn, (cudaStream_t)stream);
+  const bool pair = conv_cta_group() == 2;
+  if (conv_version() == 2) {
+    if (Cout % 128 == 0)
+      return pair ? launch_conv_v2<128, 2>(p, ih, ih + n_in, wh, wh + wn, (cudaStream_t)stream)
+                  : launch_conv_v2<128, 1>(p, ih, ih + n_in, wh, wh + wn, (cudaStream_t)stream);
+    return pair ? launch_conv_v2<64, 2>(p, ih, ih + n_in, wh, wh + wn, (cudaStream_t)stream)
+                : launch_conv_v2<64, 1>(p, ih, ih + n_in, wh, wh + wn, (cudaStream_t)stream);
+  }
+  if (Cout % 128 == 0)
+    return pair ? launch_conv<128, 2>(p, ih, ih + n_in, wh, wh + wn, (cudaStream_t)stream)
+                : launch_conv<128, 1>(p, ih, ih + n_in, wh, wh + wn, (cudaStream_t)stream);
+  return pair ? launch_conv<64, 2>(p, ih, ih + n_in, wh, wh + wn, (cudaStream_t)stream)
+              : launch_conv<64, 1>(p, ih, ih + n_in, wh, wh + wn, (cudaStream_t)stream);
 }
 
 extern "C" int sgg_conv_overflow(int reset) {

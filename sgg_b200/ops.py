@@ -645,7 +645,7 @@ def grad_sink(weight):
 # below min_rows / min_red the SIMT tiles (split-K) are faster.  engine: 'tc16' = 3xFP16 with an exact power-of-two scale
 # of the gradient operand (twice the MMA rate), 'tc32' = 3xTF32 (fp32 exponent range, no scale needed)
 import os as _os
-_TC_BWD = {'min_rows': 256, 'min_red': 1024, 'enabled': True, 'engine': _os.environ.get('SGG_BWD_ENGINE', 'tc16')}
+_TC_BWD = {'min_rows': 256, 'min_red': 256, 'enabled': True, 'engine': _os.environ.get('SGG_BWD_ENGINE', 'tc16')}
 
 
 def _pad32(n):
