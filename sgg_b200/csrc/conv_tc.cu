@@ -13,6 +13,7 @@
 // or, for the last layer, fp32 NCHW (the layout RelModel.fmap has in the reference).
 // The first layer (Cin = 3, K = 27) is a small SIMT kernel that also converts NCHW fp32 images to planes.
 #include <stdlib.h>
+#include <stdio.h>
 #include "tc16_common.cuh"
 
 namespace sgg {
@@ -26,6 +27,9 @@ struct ConvParams {
   int B, H, W, Cin, Cout;
   int tiles_w, tiles_h;
   int relu, pool;
+  int kcb;                                   // v2: k-blocks folded into TMEM before a drain
+  int dbg;                                   // v2: record g_conv_dbg
+  int dry;                                   // v2 experiment (SGG_CONV_DRY): 1 = MMAs without operand loads, 2 = loads without MMAs
   const float *bias;
   __half *out_hi, *out_lo;                   // NHWC planes [B, Ho, Wo, Cout] (nullable when out_f32 is set)
   float *out_f32;                            // nullable: fp32 NCHW [B, Cout, Ho, Wo]
@@ -195,6 +199,8 @@ k_conv3x3(const ConvParams p, const __grid_constant__ CUtensorMap tmAh, const __
     // ===================== MMA issuer =====================
     if (lane == 0 && rank == 0) {
       constexpr uint32_t idesc = make_idesc_f16(BM * CG, NC);
+      constexpr uint32_t idesc2 = make_idesc_f16(BM, 2 * NC);   // CG = 1 only
+      (void)idesc2;
       for (int it = 0; it < kblocks; ++it) {
         const int s = it % STAGES, ph = (it / STAGES) & 1;
         mbar_wait_b(full + s, ph);
@@ -217,9 +223,10 @@ k_conv3x3(const ConvParams p, const __grid_constant__ CUtensorMap tmAh, const __
             mma_f16_ss_pair(dc, ah + o, bl + o, idesc, 1u);
             mma_f16_ss_pair(dm, ah + o, bh + o, idesc, acc);
           } else {
-            mma_f16_ss(dc, al + o, bh + o, idesc, acc);
-            mma_f16_ss(dc, ah + o, bl + o, idesc, 1u);
-            mma_f16_ss(dm, ah + o, bh + o, idesc, acc);
+            // two instructions instead of three (tc16_common.cuh, "instruction floor"): the B_lo tile follows the B_hi
+            // tile in shared memory, so ONE N = 2 NC MMA forms [main | a_hi b_lo] in the adjacent column ranges
+            mma_f16_ss(dm, ah + o, bh + o, idesc2, acc);
+            mma_f16_ss(dc, al + o, bh + o, idesc, 1u);
           }
         }
         if constexpr (CG == 2) {
@@ -363,36 +370,45 @@ k_conv3x3(const ConvParams p, const __grid_constant__ CUtensorMap tmAh, const __
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// v2: halo tiles + persistent CTAs.
+// v2: column-shifted slabs + persistent CTAs.
 // The v1 kernel above fetches the A operand of every tap separately (nine shifted 128-pixel boxes per 64-channel block) and
-// runs one tile per CTA; ncu (profiles/r02_ncu_conv.md) shows the deep layers AT the L2 -> SM throughput cap (11.9 TB/s,
-// 6300 B/clk) with the tensor pipe 52 % busy, and the Cin = 64 layers bound by per-tile prologue / epilogue (18 %).
-// Here the output tile is 16 rows x 8 columns and ONE 18 x 10 pixel halo box per channel block serves all nine taps: the
-// UMMA shared-memory descriptor of tap (dy, dx) simply starts (dy * 10 + dx) pixel rows into the halo, with a stride of
-// 10 pixel rows (1280 B) between the 8-row groups.  The 128-byte swizzle is a function of the shared-memory ADDRESS, so a
-// descriptor may start at any 128-byte row of a TMA-written box and use any group stride (tools/ubench/umma_shift.cu,
-// measured on B200).  A bytes per tile and channel block drop from 288 KB to 46 KB.  CTAs are persistent: each loops over
-// (channel tile, spatial tile) work items, the TMEM ping-pong and both shared-memory rings run across item boundaries, and
-// the drain warps' epilogue (bias, ReLU, 2x2 max-pool by warp shuffles, stores) overlaps the next item's main loop.
-constexpr int VH = 16, VW = 8;               // output tile (rows x columns) = 128 pixels; GEMM row m = ty * 8 + tx
-constexpr int HP = VW + 2;                   // halo pitch (pixel rows per halo line)
-constexpr int HALO_ROWS = (VH + 2) * HP;     // 180 pixel rows of 128 B
-constexpr int HALO_PLANE = ((HALO_ROWS * 128 + 1023) / 1024) * 1024;   // 23552 B (1024-aligned plane base for the swizzle)
+// runs one tile per CTA; ncu (profiles/r02_ncu_conv.md) shows its deep layers at the L2 -> SM throughput cap (11.9 TB/s,
+// 6300 B/clk) and the Cin = 64 layers bound by per-tile prologue / epilogue (tensor pipe 18 %).
+// Here the output tile is 16 rows x 8 columns (GEMM row m = ty * 8 + tx, so an 8-row UMMA group is one tile line) and the
+// A operand of a 64-channel block is THREE slabs, one per horizontal tap offset dx: the 18 x 8 pixel box at column
+// w0 + dx - 1.  The three vertical taps of a slab are the same bytes read through a shared-memory descriptor that starts
+// dy lines (dy * 1024 B) into the slab — the 128-byte swizzle is a function of the shared-memory ADDRESS, so a descriptor
+// may start at any row of a TMA-written box (tools/ubench/umma_shift.cu).  A bytes per tile and channel block: 288 KB ->
+// 108 KB, every 8-row group still a whole 1024-byte swizzle atom.  (A single 18 x 10 halo read at row offsets dy * 10 + dx
+// is 46 KB and also exact, but its 8-row groups straddle two atoms and the tensor core then needs ~170 instead of ~102
+// cycles to fetch A: measured 340 cycles per K16 step instead of 258.)
+// CTAs are persistent: each loops over (channel tile, spatial tile) work items, the TMEM ping-pong and both shared-memory
+// rings run across item boundaries, and the drain warps' epilogue (bias, ReLU, 2x2 max-pool by warp shuffles, stores)
+// overlaps the next item's main loop.  k-block order inside a channel block: dx-major (tap = dy * 3 + dx).
+constexpr int VH = 16, VW = 8;               // output tile (rows x columns) = 128 pixels
+constexpr int SLAB_PLANE = (VH + 2) * VW * 128;   // 18432 B: 18 lines x 8 pixels x 64 channels (fp16), 1024-aligned
+
+// SGG_CONV_DBG=1: clock64 stamps of CTA 0 for its first 16 items: [item][0] MMA issue start, [1] MMA issue end,
+// [2] last chunk drained, [3] epilogue done
+__device__ long long g_conv_dbg[16 * 8];
+
+// K-major SWIZZLE_128B descriptor (SBO = 1024 B) from a shared-memory address
+__device__ __forceinline__ uint64_t make_sdesc128_addr(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
 
 template <int NC, int CG>
 struct VCfg {
-  static constexpr int A_STAGE = 2 * HALO_PLANE;            // hi + lo halo of one 64-channel block
-  static constexpr int A_STAGES = 2;
+  static constexpr int A_STAGE = 2 * SLAB_PLANE;            // hi + lo slab of one (channel block, dx)
+  static constexpr int A_STAGES = 3;
   static constexpr int B_PLANE = (NC / CG) * BK * 2;        // one tap, one plane (this CTA's share of the channel tile)
   static constexpr int B_STAGE = 2 * B_PLANE;
-  static constexpr int B_STAGES = (225 * 1024 - A_STAGES * A_STAGE) / B_STAGE > 8 ? 8 : (225 * 1024 - A_STAGES * A_STAGE) / B_STAGE;
+  static constexpr int B_FIT = (225 * 1024 - A_STAGES * A_STAGE) / B_STAGE;
+  static constexpr int B_STAGES = B_FIT > 8 ? 8 : B_FIT;
   static constexpr int RING = A_STAGES * A_STAGE + B_STAGES * B_STAGE;
   static constexpr int SMEM = RING + 1024 + 512;
+  static_assert(B_STAGES >= 3, "weight-tap ring too short");
 };
-
-__device__ __forceinline__ uint64_t make_sdesc128_sbo(uint32_t smem_addr, uint32_t sbo_bytes) {
-  return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) | (2ull << 61);
-}
 
 template <int NC, int CG>
 __global__ void __launch_bounds__(NTHR, 1)
@@ -400,7 +416,8 @@ k_conv3x3_v2(const ConvParams p, const int n_items, const int n_sp, const __grid
              const __grid_constant__ CUtensorMap tmAl, const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl) {
   using namespace tc;
   using C = VCfg<NC, CG>;
-  constexpr int AS = C::A_STAGES, BS = C::B_STAGES, KCB = 256 / BK;
+  constexpr int AS = C::A_STAGES, BS = C::B_STAGES;
+  const int KCB = p.kcb;                      // k-blocks per accumulation chunk (256 / BK unless overridden: SGG_CONV_KCB)
   constexpr uint32_t TMEM_COLS = 4 * NC <= 256 ? 256 : 512;
 
   extern __shared__ uint8_t smem_raw[];
@@ -447,102 +464,117 @@ k_conv3x3_v2(const ConvParams p, const int n_items, const int n_sp, const __grid
   };
 
   if (warp == 0) {
-    // ===================== TMA producer: per channel block one halo (hi, lo), then nine weight taps =====================
-    if (lane == 0) {
-      uint32_t ga = 0, gb = 0;                 // halos / taps issued so far (ring position and phase)
+    // ===================== TMA producer =====================
+    // Slab sequence k = 0, 1, ... over (item, channel block, dx); slab k + 2 is issued after the three weight taps of slab
+    // k, so an activation slab always has two slab times (six taps) to arrive.
+    if (lane == 0 && p.dry != 1) {
+      uint32_t ga = 0, gb = 0;                 // slabs / taps issued so far (ring position and phase)
+      int s_item = unit, s_cb = 0, s_dx = 0;   // cursor of the next slab to issue
+      auto issue_slab = [&]() {
+        if (s_item >= n_items) return;
+        int cout0, n, h0, w0;
+        decode(s_item, cout0, n, h0, w0);
+        const uint32_t s = ga % AS, ph = (ga / AS) & 1; ++ga;
+        mbar_wait_b(a_empty + s, ph ^ 1);
+        uint8_t *st = ring_a + (size_t)s * C::A_STAGE;
+        if constexpr (CG == 2) {
+          const uint32_t lbar = mapa_u32(smem_u32(a_full + s), 0);
+          if (rank == 0) mbar_arrive_expect_tx(a_full + s, 2 * C::A_STAGE); else mbar_arrive_cluster(lbar);
+          tma_load_4d_pair(st, &tmAh, lbar, s_cb * BK, w0 + s_dx - 1, h0 - 1, n);
+          tma_load_4d_pair(st + SLAB_PLANE, &tmAl, lbar, s_cb * BK, w0 + s_dx - 1, h0 - 1, n);
+        } else {
+          mbar_arrive_expect_tx(a_full + s, C::A_STAGE);
+          tma_load_4d(st, &tmAh, a_full + s, s_cb * BK, w0 + s_dx - 1, h0 - 1, n);
+          tma_load_4d(st + SLAB_PLANE, &tmAl, a_full + s, s_cb * BK, w0 + s_dx - 1, h0 - 1, n);
+        }
+        if (++s_dx == 3) { s_dx = 0; if (++s_cb == cblocks) { s_cb = 0; s_item += n_units; } }
+      };
+      issue_slab(); issue_slab();
       for (int item = unit; item < n_items; item += n_units) {
         int cout0, n, h0, w0;
         decode(item, cout0, n, h0, w0);
         const int brow = cout0 + (int)rank * (NC / CG);
-        for (int cb = 0; cb < cblocks; ++cb) {
-          {
-            const uint32_t s = ga % AS, ph = (ga / AS) & 1; ++ga;
-            mbar_wait_b(a_empty + s, ph ^ 1);
-            uint8_t *st = ring_a + (size_t)s * C::A_STAGE;
-            constexpr uint32_t HALO_TX = HALO_ROWS * 128;      // bytes one halo box delivers
-            if constexpr (CG == 2) {
-              const uint32_t lbar = mapa_u32(smem_u32(a_full + s), 0);
-              if (rank == 0) mbar_arrive_expect_tx(a_full + s, 4 * HALO_TX); else mbar_arrive_cluster(lbar);
-              tma_load_4d_pair(st, &tmAh, lbar, cb * BK, w0 - 1, h0 - 1, n);
-              tma_load_4d_pair(st + HALO_PLANE, &tmAl, lbar, cb * BK, w0 - 1, h0 - 1, n);
-            } else {
-              mbar_arrive_expect_tx(a_full + s, 2 * HALO_TX);
-              tma_load_4d(st, &tmAh, a_full + s, cb * BK, w0 - 1, h0 - 1, n);
-              tma_load_4d(st + HALO_PLANE, &tmAl, a_full + s, cb * BK, w0 - 1, h0 - 1, n);
+        for (int cb = 0; cb < cblocks; ++cb)
+          for (int dx = 0; dx < 3; ++dx) {
+            for (int dy = 0; dy < 3; ++dy) {
+              const int kcol = (dy * 3 + dx) * p.Cin + cb * BK;
+              const uint32_t s = gb % BS, ph = (gb / BS) & 1; ++gb;
+              mbar_wait_b(b_empty + s, ph ^ 1);
+              uint8_t *st = ring_b + (size_t)s * C::B_STAGE;
+              if constexpr (CG == 2) {
+                const uint32_t lbar = mapa_u32(smem_u32(b_full + s), 0);
+                if (rank == 0) mbar_arrive_expect_tx(b_full + s, 2 * C::B_STAGE); else mbar_arrive_cluster(lbar);
+                tma_load_2d_pair(st, &tmBh, lbar, kcol, brow);
+                tma_load_2d_pair(st + C::B_PLANE, &tmBl, lbar, kcol, brow);
+              } else {
+                mbar_arrive_expect_tx(b_full + s, C::B_STAGE);
+                tma_load_2d(st, &tmBh, b_full + s, kcol, brow);
+                tma_load_2d(st + C::B_PLANE, &tmBl, b_full + s, kcol, brow);
+              }
             }
+            issue_slab();
           }
-          for (int tap = 0; tap < 9; ++tap) {
-            const uint32_t s = gb % BS, ph = (gb / BS) & 1; ++gb;
-            mbar_wait_b(b_empty + s, ph ^ 1);
-            uint8_t *st = ring_b + (size_t)s * C::B_STAGE;
-            if constexpr (CG == 2) {
-              const uint32_t lbar = mapa_u32(smem_u32(b_full + s), 0);
-              if (rank == 0) mbar_arrive_expect_tx(b_full + s, 2 * C::B_STAGE); else mbar_arrive_cluster(lbar);
-              tma_load_2d_pair(st, &tmBh, lbar, tap * p.Cin + cb * BK, brow);
-              tma_load_2d_pair(st + C::B_PLANE, &tmBl, lbar, tap * p.Cin + cb * BK, brow);
-            } else {
-              mbar_arrive_expect_tx(b_full + s, C::B_STAGE);
-              tma_load_2d(st, &tmBh, b_full + s, tap * p.Cin + cb * BK, brow);
-              tma_load_2d(st + C::B_PLANE, &tmBl, b_full + s, tap * p.Cin + cb * BK, brow);
-            }
-          }
-        }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (pair: the leader only) =====================
     if (lane == 0 && rank == 0) {
       constexpr uint32_t idesc = make_idesc_f16(BM * CG, NC);
+      constexpr uint32_t idesc2 = make_idesc_f16(BM, 2 * NC);   // CG = 1 only
+      (void)idesc2;
       uint32_t ga = 0, gb = 0, gch = 0;
-      for (int item = unit; item < n_items; item += n_units) {
-        for (int cb = 0; cb < cblocks; ++cb) {
-          const uint32_t as = ga % AS, aph = (ga / AS) & 1; ++ga;
-          mbar_wait_b(a_full + as, aph);
-          const uint32_t a_hi = smem_u32(ring_a + (size_t)as * C::A_STAGE), a_lo = a_hi + HALO_PLANE;
-          for (int tap = 0; tap < 9; ++tap) {
-            const uint32_t bs = gb % BS, bph = (gb / BS) & 1; ++gb;
-            mbar_wait_b(b_full + bs, bph);
-            fence_after_sync();
-            const int it = cb * 9 + tap;
-            const int chunk = it / KCB, kc = it - chunk * KCB;
-            const uint32_t gc = gch + (uint32_t)chunk;
-            if (kc == 0) {                     // the buffer pair must have been drained (two chunks ago)
-              mbar_wait_b(tmem_empty + (gc & 1), ((gc >> 1) & 1) ^ 1);
+      int ord = 0;
+      for (int item = unit; item < n_items; item += n_units, ++ord) {
+        if (p.dbg && blockIdx.x == 0 && ord < 16) g_conv_dbg[ord * 8 + 0] = clock64();
+        int it = 0;
+        for (int cb = 0; cb < cblocks; ++cb)
+          for (int dx = 0; dx < 3; ++dx) {
+            const uint32_t as = ga % AS, aph = (ga / AS) & 1; ++ga;
+            if (p.dry != 1) mbar_wait_b(a_full + as, aph);
+            const uint32_t a_hi = smem_u32(ring_a + (size_t)as * C::A_STAGE), a_lo = a_hi + SLAB_PLANE;
+            for (int dy = 0; dy < 3; ++dy, ++it) {
+              const uint32_t bs = gb % BS, bph = (gb / BS) & 1; ++gb;
+              if (p.dry != 1) mbar_wait_b(b_full + bs, bph);
               fence_after_sync();
-            }
-            const int dy = tap / 3, dx = tap - dy * 3;
-            const uint32_t shift = (uint32_t)((dy * HP + dx) * 128);
-            const uint64_t ah = make_sdesc128_sbo(a_hi + shift, HP * 128), al = make_sdesc128_sbo(a_lo + shift, HP * 128);
-            uint8_t *st = ring_b + (size_t)bs * C::B_STAGE;
-            const uint64_t bh = make_sdesc128(st), bl = make_sdesc128(st + C::B_PLANE);
-            const uint32_t dm = tmem_base + (uint32_t)((gc & 1) * 2 * NC), dc = dm + (uint32_t)NC;
+              const int chunk = it / KCB, kc = it - chunk * KCB;
+              const uint32_t gc = gch + (uint32_t)chunk;
+              if (kc == 0) {                     // the buffer pair must have been drained (two chunks ago)
+                mbar_wait_b(tmem_empty + (gc & 1), ((gc >> 1) & 1) ^ 1);
+                fence_after_sync();
+              }
+              const uint32_t shift = (uint32_t)(dy * VW * 128);          // dy lines down: whole 1024-byte swizzle atoms
+              const uint64_t ah = make_sdesc128_addr(a_hi + shift), al = make_sdesc128_addr(a_lo + shift);
+              uint8_t *st = ring_b + (size_t)bs * C::B_STAGE;
+              const uint64_t bh = make_sdesc128(st), bl = make_sdesc128(st + C::B_PLANE);
+              const uint32_t dm = tmem_base + (uint32_t)((gc & 1) * 2 * NC), dc = dm + (uint32_t)NC;
 #pragma unroll
-            for (int kk = 0; kk < BK / 16; ++kk) {
-              const uint64_t o = (uint64_t)(kk * 2);
-              const uint32_t acc = (kc == 0 && kk == 0) ? 0u : 1u;
+              for (int kk = 0; kk < BK / 16; ++kk) {
+                if (p.dry == 2) break;
+                const uint64_t o = (uint64_t)(kk * 2);
+                const uint32_t acc = (kc == 0 && kk == 0) ? 0u : 1u;
+                if constexpr (CG == 2) {
+                  mma_f16_ss_pair(dc, al + o, bh + o, idesc, acc);
+                  mma_f16_ss_pair(dc, ah + o, bl + o, idesc, 1u);
+                  mma_f16_ss_pair(dm, ah + o, bh + o, idesc, acc);
+                } else {
+                  mma_f16_ss(dm, ah + o, bh + o, idesc2, acc);     // [main | a_hi b_lo]  (N = 2 NC: B_lo follows B_hi)
+                  mma_f16_ss(dc, al + o, bh + o, idesc, 1u);       // corr += a_lo b_hi
+                }
+              }
+              const bool chunk_end = kc == KCB - 1 || it == kblocks - 1;
               if constexpr (CG == 2) {
-                mma_f16_ss_pair(dc, al + o, bh + o, idesc, acc);
-                mma_f16_ss_pair(dc, ah + o, bl + o, idesc, 1u);
-                mma_f16_ss_pair(dm, ah + o, bh + o, idesc, acc);
+                mma_commit_pair(b_empty + bs);
+                if (dy == 2) mma_commit_pair(a_empty + as);
+                if (chunk_end) mma_commit_pair(tmem_full + (gc & 1));
               } else {
-                mma_f16_ss(dc, al + o, bh + o, idesc, acc);
-                mma_f16_ss(dc, ah + o, bl + o, idesc, 1u);
-                mma_f16_ss(dm, ah + o, bh + o, idesc, acc);
+                mma_commit(b_empty + bs);
+                if (dy == 2) mma_commit(a_empty + as);
+                if (chunk_end) mma_commit(tmem_full + (gc & 1));
               }
             }
-            const bool chunk_end = kc == KCB - 1 || it == kblocks - 1;
-            if constexpr (CG == 2) {
-              mma_commit_pair(b_empty + bs);
-              if (tap == 8) mma_commit_pair(a_empty + as);
-              if (chunk_end) mma_commit_pair(tmem_full + (gc & 1));
-            } else {
-              mma_commit(b_empty + bs);
-              if (tap == 8) mma_commit(a_empty + as);
-              if (chunk_end) mma_commit(tmem_full + (gc & 1));
-            }
           }
-        }
         gch += (uint32_t)nchunks;
+        if (p.dbg && blockIdx.x == 0 && ord < 16) g_conv_dbg[ord * 8 + 1] = clock64();
       }
     }
   } else {
@@ -553,7 +585,8 @@ k_conv3x3_v2(const ConvParams p, const int n_items, const int n_sp, const __grid
     const int ty = row >> 3, tx = row & 7;
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * HC);
     uint32_t gch = 0, ovf = 0;
-    for (int item = unit; item < n_items; item += n_units) {
+    int ord = 0;
+    for (int item = unit; item < n_items; item += n_units, ++ord) {
       int cout0, n, h0, w0;
       decode(item, cout0, n, h0, w0);
       float acc[HC];
@@ -579,6 +612,7 @@ k_conv3x3_v2(const ConvParams p, const int n_items, const int n_sp, const __grid
           if constexpr (CG == 2) mbar_arrive_cluster(mapa_u32(smem_u32(tmem_empty + b), 0)); else mbar_arrive(tmem_empty + b);
         }
       }
+      if (p.dbg && blockIdx.x == 0 && threadIdx.x == 64 && ord < 16) g_conv_dbg[ord * 8 + 2] = clock64();
       // ---- epilogue of this item (the MMA warp is already filling the ping-pong buffers with the next item) ----
       const int cbase = cout0 + half * HC;
 #pragma unroll
@@ -623,6 +657,7 @@ k_conv3x3_v2(const ConvParams p, const int n_items, const int n_sp, const __grid
           }
         }
       }
+      if (p.dbg && blockIdx.x == 0 && threadIdx.x == 64 && ord < 16) g_conv_dbg[ord * 8 + 3] = clock64();
     }
     if (ovf) atomicOr(&g_conv_overflow, 1u);
   }
@@ -714,12 +749,14 @@ static int make_tmap_4d(CUtensorMap *m, const void *base, int B, int H, int W, i
   return 0;
 }
 
-// SGG_CONV_CG = 1 | 2 (default 2): CTAs per UMMA tile
+// SGG_CONV_CG = 1 | 2 (default 1): CTAs per UMMA tile.  The cta_group::2 variants are exact and halve the weight bytes each SM
+// stages, but measured no faster (profiles/r02_conv_experiments.md): these kernels are bound by the tensor pipe's
+// per-instruction floor, not by shared-memory or L2 bandwidth, and the pair cannot use the fused two-instruction pattern.
 static int conv_cta_group() {
   static int v = -1;
   if (v < 0) {
     const char *e = getenv("SGG_CONV_CG");
-    v = (e && atoi(e) == 1) ? 1 : 2;
+    v = (e && atoi(e) == 2) ? 2 : 1;
   }
   return v;
 }
@@ -782,10 +819,16 @@ static int launch_conv_v2(ConvParams p, const __half *in_hi, const __half *in_lo
     attr = true;
   }
   p.tiles_w = (p.W + VW - 1) / VW; p.tiles_h = (p.H + VH - 1) / VH;
+  static const int kcb_env = getenv("SGG_CONV_KCB") ? atoi(getenv("SGG_CONV_KCB")) : 0;   // experiment knob
+  p.kcb = kcb_env > 0 ? kcb_env : 256 / BK;
+  static const int dry_env = getenv("SGG_CONV_DRY") ? atoi(getenv("SGG_CONV_DRY")) : 0;
+  p.dry = dry_env;
+  static const int dbg_env = getenv("SGG_CONV_DBG") ? atoi(getenv("SGG_CONV_DBG")) : 0;
+  p.dbg = dbg_env;
   CUtensorMap tm[4];
   int rc;
-  if ((rc = make_tmap_4d(&tm[0], in_hi, p.B, p.H, p.W, p.Cin, HP, VH + 2))) return rc;
-  if ((rc = make_tmap_4d(&tm[1], in_lo, p.B, p.H, p.W, p.Cin, HP, VH + 2))) return rc;
+  if ((rc = make_tmap_4d(&tm[0], in_hi, p.B, p.H, p.W, p.Cin, VW, VH + 2))) return rc;
+  if ((rc = make_tmap_4d(&tm[1], in_lo, p.B, p.H, p.W, p.Cin, VW, VH + 2))) return rc;
   if ((rc = make_tmap(&tm[2], w_hi, p.Cout, 9 * p.Cin, NC / CG, 2))) return rc;
   if ((rc = make_tmap(&tm[3], w_lo, p.Cout, 9 * p.Cin, NC / CG, 2))) return rc;
   const long long tiles = (long long)p.tiles_w * p.tiles_h * p.B;
@@ -805,6 +848,15 @@ static int launch_conv_v2(ConvParams p, const __half *in_hi, const __half *in_lo
   cfg.attrs = at; cfg.numAttrs = 1;
   SGG_CUDA_TRY(cudaLaunchKernelEx(&cfg, k_conv3x3_v2<NC, CG>, p, (int)items, (int)n_sp, tm[0], tm[1], tm[2], tm[3]));
   SGG_RETURN_IF_LAUNCH_FAILED("k_conv3x3_v2");
+  if (p.dbg) {                                  // debugging aid: print CTA 0's phase stamps relative to its first one
+    long long h[16 * 8];
+    if (cudaDeviceSynchronize() == cudaSuccess && cudaMemcpyFromSymbol(h, g_conv_dbg, sizeof(h)) == cudaSuccess) {
+      fprintf(stderr, "[conv dbg] Cin %d Cout %d H %d: item: mma-start mma-end | drained epilogue-done (cycles since first stamp)\n", p.Cin, p.Cout, p.H);
+      const long long t0 = h[0];
+      for (int i = 0; i < 10; ++i)
+        fprintf(stderr, "[conv dbg] %2d: %7lld %7lld | %7lld %7lld\n", i, h[i * 8] - t0, h[i * 8 + 1] - t0, h[i * 8 + 2] - t0, h[i * 8 + 3] - t0);
+    }
+  }
   return 0;
 }
 

@@ -550,7 +550,7 @@ k_mp_pre(const PreParams p, const __grid_constant__ CUtensorMap tmA0h, const __g
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_f16(BM, LCOL);
+      constexpr uint32_t idesc = make_idesc_f16(BM, LCOL), idesc2 = make_idesc_f16(BM, 2 * LCOL);
       for (int it = 0; it < kblocks; ++it) {
         const int s = it % L_STAGES, ph = (it / L_STAGES) & 1;
         mbar_wait_b(full + s, ph);
@@ -565,9 +565,8 @@ k_mp_pre(const PreParams p, const __grid_constant__ CUtensorMap tmA0h, const __g
         for (int kk = 0; kk < BK / 16; ++kk) {
           const uint64_t o = (uint64_t)(kk * 2);
           const uint32_t acc = (kc == 0 && kk == 0) ? 0u : 1u;
-          mma_f16_ss(dc, al + o, bh + o, idesc, acc);
-          mma_f16_ss(dc, ah + o, bl + o, idesc, 1u);
-          mma_f16_ss(dm, ah + o, bh + o, idesc, acc);
+          mma_f16_ss(dm, ah + o, bh + o, idesc2, acc);     // [main | a_hi b_lo]: one N = 2 LCOL MMA (B_lo follows B_hi in the stage)
+          mma_f16_ss(dc, al + o, bh + o, idesc, 1u);       // corr += a_lo b_hi
         }
         mma_commit(empty + s);
         if (kc == KCB - 1 || it == kblocks - 1) mma_commit(tmem_full + chunk);

@@ -186,6 +186,8 @@ k_tc16(Params p, const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     // ===================== MMA issuer =====================
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_f16(BM, NCOL);
+      constexpr uint32_t idesc2 = make_idesc_f16(BM, CHUNKED ? 2 * NCOL : NCOL);
+      (void)idesc2;
       for (int it = 0; it < total; ++it) {
         const int s = it % STAGES, ph = (it / STAGES) & 1;
         mbar_wait(full + s, ph);
@@ -214,9 +216,17 @@ k_tc16(Params p, const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         for (int kk = 0; kk < BK / 16; ++kk) {
           const uint64_t o = (uint64_t)(kk * 2);     // 16 fp16 = 32 bytes >> 4
           const uint32_t acc = (first && kk == 0) ? 0u : 1u;
-          mma_f16_ss(dc, al + o, bh + o, idesc, acc);      // corrections -> CORR
-          mma_f16_ss(dc, ah + o, bl + o, idesc, 1u);
-          mma_f16_ss(dm, ah + o, bh + o, idesc, acc);      // large term  -> MAIN
+          if constexpr (CHUNKED) {
+            // LINEAR: the B_lo tile follows the B_hi tile and CORR follows MAIN, so ONE N = 2 NCOL instruction forms
+            // [main | a_hi b_lo]; an SS MMA costs >= ~102 cycles whatever its N (tools/ubench/umma_rate.cu), so two
+            // instructions per K16 step instead of three is 1.2x (N = 128) to 1.6x (N = 96) fewer tensor-pipe cycles
+            mma_f16_ss(dm, ah + o, bh + o, idesc2, acc);
+            mma_f16_ss(dc, al + o, bh + o, idesc, 1u);
+          } else {
+            mma_f16_ss(dc, al + o, bh + o, idesc, acc);      // corrections -> CORR
+            mma_f16_ss(dc, ah + o, bl + o, idesc, 1u);
+            mma_f16_ss(dm, ah + o, bh + o, idesc, acc);      // large term  -> MAIN
+          }
         }
         mma_commit(empty + s);
         if (CHUNKED && (kc == KCB - 1 || it == total - 1)) mma_commit(tmem_full + (chunk & 1));

@@ -1,0 +1,8 @@
+#!/bin/bash
+mkdir -p gpurun_out
+echo "=== pytest"; timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r3f_pytest.log 2>&1; tail -4 gpurun_out/r3f_pytest.log
+echo "=== conv V=2 CG=1"; SGG_CONV_V=2 SGG_CONV_CG=1 timeout 300 python tools/conv_check.py 2>&1 | grep -v "^layers" | tail -4
+SGG_CONV_V=2 SGG_CONV_CG=1 timeout 300 python tools/conv_layers.py 2>&1 | tail -13 | cut -c1-60
+echo "=== conv V=1 CG=1"; SGG_CONV_V=1 SGG_CONV_CG=1 timeout 300 python tools/conv_layers.py 2>&1 | tail -13 | cut -c1-60
+echo "=== bench"; SGG_CONV_CG=1 SGG_BENCH_WATCHDOG=500 timeout 600 python bench.py --steps 50 --warmup 5 > gpurun_out/r3f_bench.json 2> gpurun_out/r3f_bench.err; echo rc=$?; grep -E "^\[bench" gpurun_out/r3f_bench.err | tail -9
+echo "=== tc16_check"; timeout 300 python tools/tc16_check.py 2>&1 | tail -18
