@@ -29,7 +29,8 @@ struct ConvParams {
   int relu, pool;
   int kcb;                                   // v2: k-blocks folded into TMEM before a drain
   int dbg;                                   // v2: record g_conv_dbg
-  int dry;                                   // v2 experiment (SGG_CONV_DRY): 1 = MMAs without operand loads, 2 = loads without MMAs
+  int dry;                                   // v2 experiment (SGG_CONV_DRY): 1 = MMAs without operand loads, 2 = loads without MMAs,
+                                             // 3 = weight loads only, 4 = activation loads only (both without MMAs)
   const float *bias;
   __half *out_hi, *out_lo;                   // NHWC planes [B, Ho, Wo, Cout] (nullable when out_f32 is set)
   float *out_f32;                            // nullable: fp32 NCHW [B, Cout, Ho, Wo]
@@ -171,13 +172,14 @@ k_conv3x3(const ConvParams p, const __grid_constant__ CUtensorMap tmAh, const __
 
   if (warp == 0) {
     // ===================== TMA producer: k-block it = (channel block cb, tap) =====================
-    if (lane == 0) {
+    {                                          // whole warp runs the loop, one elected lane issues
       for (int it = 0; it < kblocks; ++it) {
         const int s = it % STAGES, ph = (it / STAGES) & 1;
         mbar_wait_b(empty + s, ph ^ 1);
         const int cb = it / 9, tap = it - cb * 9;
         const int dy = tap / 3, dx = tap - dy * 3;
         uint8_t *st = smem + (size_t)s * STAGE;
+        if (elect_one()) {
         if constexpr (CG == 2) {
           const uint32_t lbar = mapa_u32(smem_u32(full + s), 0);
           if (rank == 0) mbar_arrive_expect_tx(full + s, 2 * STAGE); else mbar_arrive_cluster(lbar);
@@ -193,11 +195,13 @@ k_conv3x3(const ConvParams p, const __grid_constant__ CUtensorMap tmAh, const __
           tma_load_2d(st + 2 * C::A_PLANE, &tmBh, full + s, tap * p.Cin + cb * BK, cout0);
           tma_load_2d(st + 2 * C::A_PLANE + C::B_PLANE, &tmBl, full + s, tap * p.Cin + cb * BK, cout0);
         }
+        }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0 && rank == 0) {
+    if (rank == 0) {                          // whole warp runs the loop, one elected lane issues (see k_conv3x3_v2)
       constexpr uint32_t idesc = make_idesc_f16(BM * CG, NC);
       constexpr uint32_t idesc2 = make_idesc_f16(BM, 2 * NC);   // CG = 1 only
       (void)idesc2;
@@ -214,6 +218,7 @@ k_conv3x3(const ConvParams p, const __grid_constant__ CUtensorMap tmAh, const __
           fence_after_sync();
         }
         const uint32_t dm = tmem_base + (uint32_t)((chunk & 1) * 2 * NC), dc = dm + (uint32_t)NC;
+        if (elect_one()) {
 #pragma unroll
         for (int kk = 0; kk < BK / 16; ++kk) {
           const uint64_t o = (uint64_t)(kk * 2);
@@ -236,6 +241,8 @@ k_conv3x3(const ConvParams p, const __grid_constant__ CUtensorMap tmAh, const __
           mma_commit(empty + s);
           if (kc == KCB - 1 || it == kblocks - 1) mma_commit(tmem_full + (chunk & 1));
         }
+        }
+        __syncwarp();
       }
     }
   } else {
@@ -467,7 +474,7 @@ k_conv3x3_v2(const ConvParams p, const int n_items, const int n_sp, const __grid
     // ===================== TMA producer =====================
     // Slab sequence k = 0, 1, ... over (item, channel block, dx); slab k + 2 is issued after the three weight taps of slab
     // k, so an activation slab always has two slab times (six taps) to arrive.
-    if (lane == 0 && p.dry != 1) {
+    if (p.dry != 1) {                          // whole warp runs the loops, one elected lane issues
       uint32_t ga = 0, gb = 0;                 // slabs / taps issued so far (ring position and phase)
       int s_item = unit, s_cb = 0, s_dx = 0;   // cursor of the next slab to issue
       auto issue_slab = [&]() {
@@ -477,16 +484,21 @@ k_conv3x3_v2(const ConvParams p, const int n_items, const int n_sp, const __grid
         const uint32_t s = ga % AS, ph = (ga / AS) & 1; ++ga;
         mbar_wait_b(a_empty + s, ph ^ 1);
         uint8_t *st = ring_a + (size_t)s * C::A_STAGE;
+        if (elect_one()) {
         if constexpr (CG == 2) {
           const uint32_t lbar = mapa_u32(smem_u32(a_full + s), 0);
           if (rank == 0) mbar_arrive_expect_tx(a_full + s, 2 * C::A_STAGE); else mbar_arrive_cluster(lbar);
           tma_load_4d_pair(st, &tmAh, lbar, s_cb * BK, w0 + s_dx - 1, h0 - 1, n);
           tma_load_4d_pair(st + SLAB_PLANE, &tmAl, lbar, s_cb * BK, w0 + s_dx - 1, h0 - 1, n);
+        } else if (p.dry == 3) {                 // experiment: no activation loads
+          mbar_arrive(a_full + s);
         } else {
           mbar_arrive_expect_tx(a_full + s, C::A_STAGE);
           tma_load_4d(st, &tmAh, a_full + s, s_cb * BK, w0 + s_dx - 1, h0 - 1, n);
           tma_load_4d(st + SLAB_PLANE, &tmAl, a_full + s, s_cb * BK, w0 + s_dx - 1, h0 - 1, n);
         }
+        }
+        __syncwarp();
         if (++s_dx == 3) { s_dx = 0; if (++s_cb == cblocks) { s_cb = 0; s_item += n_units; } }
       };
       issue_slab(); issue_slab();
@@ -501,16 +513,21 @@ k_conv3x3_v2(const ConvParams p, const int n_items, const int n_sp, const __grid
               const uint32_t s = gb % BS, ph = (gb / BS) & 1; ++gb;
               mbar_wait_b(b_empty + s, ph ^ 1);
               uint8_t *st = ring_b + (size_t)s * C::B_STAGE;
+              if (elect_one()) {
               if constexpr (CG == 2) {
                 const uint32_t lbar = mapa_u32(smem_u32(b_full + s), 0);
                 if (rank == 0) mbar_arrive_expect_tx(b_full + s, 2 * C::B_STAGE); else mbar_arrive_cluster(lbar);
                 tma_load_2d_pair(st, &tmBh, lbar, kcol, brow);
                 tma_load_2d_pair(st + C::B_PLANE, &tmBl, lbar, kcol, brow);
+              } else if (p.dry == 4) {           // experiment: no weight loads
+                mbar_arrive(b_full + s);
               } else {
                 mbar_arrive_expect_tx(b_full + s, C::B_STAGE);
                 tma_load_2d(st, &tmBh, b_full + s, kcol, brow);
                 tma_load_2d(st + C::B_PLANE, &tmBl, b_full + s, kcol, brow);
               }
+              }
+              __syncwarp();
             }
             issue_slab();
           }
@@ -518,14 +535,17 @@ k_conv3x3_v2(const ConvParams p, const int n_items, const int n_sp, const __grid
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (pair: the leader only) =====================
-    if (lane == 0 && rank == 0) {
+    // The whole warp runs the loop (warp-uniform control flow and operands); one elected lane issues.  With the loop under
+    // `if (lane == 0)` the compiler cannot prove the descriptors uniform and wraps every UTCHMMA in an
+    // ELECT / R2UR.BROADCAST / BRA.U.ANY loop, which made the issue thread — not the tensor pipe — the bound.
+    if (rank == 0) {
       constexpr uint32_t idesc = make_idesc_f16(BM * CG, NC);
       constexpr uint32_t idesc2 = make_idesc_f16(BM, 2 * NC);   // CG = 1 only
       (void)idesc2;
       uint32_t ga = 0, gb = 0, gch = 0;
       int ord = 0;
       for (int item = unit; item < n_items; item += n_units, ++ord) {
-        if (p.dbg && blockIdx.x == 0 && ord < 16) g_conv_dbg[ord * 8 + 0] = clock64();
+        if (p.dbg && blockIdx.x == 0 && ord < 16 && lane == 0) g_conv_dbg[ord * 8 + 0] = clock64();
         int it = 0;
         for (int cb = 0; cb < cblocks; ++cb)
           for (int dx = 0; dx < 3; ++dx) {
@@ -547,34 +567,37 @@ k_conv3x3_v2(const ConvParams p, const int n_items, const int n_sp, const __grid
               uint8_t *st = ring_b + (size_t)bs * C::B_STAGE;
               const uint64_t bh = make_sdesc128(st), bl = make_sdesc128(st + C::B_PLANE);
               const uint32_t dm = tmem_base + (uint32_t)((gc & 1) * 2 * NC), dc = dm + (uint32_t)NC;
+              const bool chunk_end = kc == KCB - 1 || it == kblocks - 1;
+              if (elect_one()) {
 #pragma unroll
-              for (int kk = 0; kk < BK / 16; ++kk) {
-                if (p.dry == 2) break;
-                const uint64_t o = (uint64_t)(kk * 2);
-                const uint32_t acc = (kc == 0 && kk == 0) ? 0u : 1u;
+                for (int kk = 0; kk < BK / 16; ++kk) {
+                  if (p.dry >= 2) break;
+                  const uint64_t o = (uint64_t)(kk * 2);
+                  const uint32_t acc = (kc == 0 && kk == 0) ? 0u : 1u;
+                  if constexpr (CG == 2) {
+                    mma_f16_ss_pair(dc, al + o, bh + o, idesc, acc);
+                    mma_f16_ss_pair(dc, ah + o, bl + o, idesc, 1u);
+                    mma_f16_ss_pair(dm, ah + o, bh + o, idesc, acc);
+                  } else {
+                    mma_f16_ss(dm, ah + o, bh + o, idesc2, acc);     // [main | a_hi b_lo]  (N = 2 NC: B_lo follows B_hi)
+                    mma_f16_ss(dc, al + o, bh + o, idesc, 1u);       // corr += a_lo b_hi
+                  }
+                }
                 if constexpr (CG == 2) {
-                  mma_f16_ss_pair(dc, al + o, bh + o, idesc, acc);
-                  mma_f16_ss_pair(dc, ah + o, bl + o, idesc, 1u);
-                  mma_f16_ss_pair(dm, ah + o, bh + o, idesc, acc);
+                  mma_commit_pair(b_empty + bs);
+                  if (dy == 2) mma_commit_pair(a_empty + as);
+                  if (chunk_end) mma_commit_pair(tmem_full + (gc & 1));
                 } else {
-                  mma_f16_ss(dm, ah + o, bh + o, idesc2, acc);     // [main | a_hi b_lo]  (N = 2 NC: B_lo follows B_hi)
-                  mma_f16_ss(dc, al + o, bh + o, idesc, 1u);       // corr += a_lo b_hi
+                  mma_commit(b_empty + bs);
+                  if (dy == 2) mma_commit(a_empty + as);
+                  if (chunk_end) mma_commit(tmem_full + (gc & 1));
                 }
               }
-              const bool chunk_end = kc == KCB - 1 || it == kblocks - 1;
-              if constexpr (CG == 2) {
-                mma_commit_pair(b_empty + bs);
-                if (dy == 2) mma_commit_pair(a_empty + as);
-                if (chunk_end) mma_commit_pair(tmem_full + (gc & 1));
-              } else {
-                mma_commit(b_empty + bs);
-                if (dy == 2) mma_commit(a_empty + as);
-                if (chunk_end) mma_commit(tmem_full + (gc & 1));
-              }
+              __syncwarp();
             }
           }
         gch += (uint32_t)nchunks;
-        if (p.dbg && blockIdx.x == 0 && ord < 16) g_conv_dbg[ord * 8 + 1] = clock64();
+        if (p.dbg && blockIdx.x == 0 && ord < 16 && lane == 0) g_conv_dbg[ord * 8 + 1] = clock64();
       }
     }
   } else {

@@ -268,7 +268,7 @@ k_mp_gru(const GruParams p, const __grid_constant__ CUtensorMap tmAh0, const __g
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    {                                          // whole warp runs the loop, one elected lane issues (uniform operands)
       // NODE tiles read the ctx planes written by the preceding launch A; EDGE / INIT operands are older
       if (p.pdl && R.mode == MODE_NODE) { griddep_wait(); asm volatile("fence.proxy.async;" ::: "memory"); }
       for (int it = 0; it < kblocks; ++it) {
@@ -276,40 +276,48 @@ k_mp_gru(const GruParams p, const __grid_constant__ CUtensorMap tmAh0, const __g
         mbar_wait_b(empty + s, ph ^ 1);
         uint8_t *st = smem + (size_t)s * STAGE;
         const int k0 = it * BKT;
-        mbar_arrive_expect_tx(full + s, STAGE);
-        tma_load_2d(st, tAh, full + s, k0, m0);
-        tma_load_2d(st + C::A_PLANE, tAl, full + s, k0, m0);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(full + s, STAGE);
+          tma_load_2d(st, tAh, full + s, k0, m0);
+          tma_load_2d(st + C::A_PLANE, tAl, full + s, k0, m0);
 #pragma unroll
-        for (int b = 0; b < 3; ++b) {
-          tma_load_2d(st + 2 * C::A_PLANE + b * C::B_BLK, tBh, full + s, k0, b * H + j0);
-          tma_load_2d(st + 2 * C::A_PLANE + C::B_PLANE + b * C::B_BLK, tBl, full + s, k0, b * H + j0);
+          for (int b = 0; b < 3; ++b) {
+            tma_load_2d(st + 2 * C::A_PLANE + b * C::B_BLK, tBh, full + s, k0, b * H + j0);
+            tma_load_2d(st + 2 * C::A_PLANE + C::B_PLANE + b * C::B_BLK, tBl, full + s, k0, b * H + j0);
+          }
         }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // The whole warp runs the loop and ONE ELECTED lane issues: with the loop under `if (lane == 0)` the compiler cannot
+    // prove the descriptors warp-uniform and wraps every UTCHMMA in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop.
+    {
       constexpr uint32_t idesc = make_idesc_f16(BM, NCOL);
       const uint32_t dm = tmem_base, dc = tmem_base + (uint32_t)CORR;
       for (int it = 0; it < kblocks; ++it) {
         const int s = it % STAGES, ph = (it / STAGES) & 1;
         mbar_wait_b(full + s, ph);
         fence_after_sync();
-        if (it == 0) MPF_DBG(2);
+        if (it == 0 && lane == 0) MPF_DBG(2);
         uint8_t *st = smem + (size_t)s * STAGE;
         const uint64_t ah = make_sdesc_k<BKT>(st), al = make_sdesc_k<BKT>(st + C::A_PLANE);
         const uint64_t bh = make_sdesc_k<BKT>(st + 2 * C::A_PLANE), bl = make_sdesc_k<BKT>(st + 2 * C::A_PLANE + C::B_PLANE);
+        if (elect_one()) {
 #pragma unroll
-        for (int kk = 0; kk < BKT / 16; ++kk) {
-          const uint64_t o = (uint64_t)(kk * 2);           // 16 fp16 = 32 bytes >> 4
-          const uint32_t acc = (it == 0 && kk == 0) ? 0u : 1u;
-          mma_f16_ss(dc, al + o, bh + o, idesc, acc);      // corrections -> CORR
-          mma_f16_ss(dc, ah + o, bl + o, idesc, 1u);
-          mma_f16_ss(dm, ah + o, bh + o, idesc, acc);      // large term  -> MAIN
+          for (int kk = 0; kk < BKT / 16; ++kk) {
+            const uint64_t o = (uint64_t)(kk * 2);           // 16 fp16 = 32 bytes >> 4
+            const uint32_t acc = (it == 0 && kk == 0) ? 0u : 1u;
+            mma_f16_ss(dc, al + o, bh + o, idesc, acc);      // corrections -> CORR
+            mma_f16_ss(dc, ah + o, bl + o, idesc, 1u);
+            mma_f16_ss(dm, ah + o, bh + o, idesc, acc);      // large term  -> MAIN
+          }
+          mma_commit(empty + s);
+          if (it == kblocks - 1) mma_commit(tmem_full);
         }
-        mma_commit(empty + s);
+        __syncwarp();
       }
-      mma_commit(tmem_full);
     }
   } else {
     // ===================== warps 2..9 =====================
@@ -535,41 +543,47 @@ k_mp_pre(const PreParams p, const __grid_constant__ CUtensorMap tmA0h, const __g
   if (threadIdx.x == 0) PRE_DBG(1);
 
   if (warp == 0) {
-    if (lane == 0) {
+    {                                          // whole warp runs the loop, one elected lane issues
       for (int it = 0; it < kblocks; ++it) {
         const int s = it % L_STAGES, ph = (it / L_STAGES) & 1;
         mbar_wait_b(empty + s, ph ^ 1);
         uint8_t *st = smem + (size_t)s * L_STAGE;
         const int k0 = it * BK;
-        mbar_arrive_expect_tx(full + s, L_STAGE);
-        tma_load_2d(st, tAh, full + s, k0, m0);
-        tma_load_2d(st + A_PLANE, tAl, full + s, k0, m0);
-        tma_load_2d(st + 2 * A_PLANE, tBh, full + s, k0, j0);
-        tma_load_2d(st + 2 * A_PLANE + B_PLANE, tBl, full + s, k0, j0);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(full + s, L_STAGE);
+          tma_load_2d(st, tAh, full + s, k0, m0);
+          tma_load_2d(st + A_PLANE, tAl, full + s, k0, m0);
+          tma_load_2d(st + 2 * A_PLANE, tBh, full + s, k0, j0);
+          tma_load_2d(st + 2 * A_PLANE + B_PLANE, tBl, full + s, k0, j0);
+        }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {                                          // whole warp runs the loop, one elected lane issues (see k_mp_gru)
       constexpr uint32_t idesc = make_idesc_f16(BM, LCOL), idesc2 = make_idesc_f16(BM, 2 * LCOL);
       for (int it = 0; it < kblocks; ++it) {
         const int s = it % L_STAGES, ph = (it / L_STAGES) & 1;
         mbar_wait_b(full + s, ph);
         fence_after_sync();
-        if (it == 0) PRE_DBG(2);
+        if (it == 0 && lane == 0) PRE_DBG(2);
         uint8_t *st = smem + (size_t)s * L_STAGE;
         const uint64_t ah = make_sdesc128(st), al = make_sdesc128(st + A_PLANE);
         const uint64_t bh = make_sdesc128(st + 2 * A_PLANE), bl = make_sdesc128(st + 2 * A_PLANE + B_PLANE);
         const int chunk = it / KCB, kc = it - chunk * KCB;
         const uint32_t dm = tmem_base + (uint32_t)(chunk * 2 * LCOL), dc = dm + (uint32_t)LCOL;
+        if (elect_one()) {
 #pragma unroll
-        for (int kk = 0; kk < BK / 16; ++kk) {
-          const uint64_t o = (uint64_t)(kk * 2);
-          const uint32_t acc = (kc == 0 && kk == 0) ? 0u : 1u;
-          mma_f16_ss(dm, ah + o, bh + o, idesc2, acc);     // [main | a_hi b_lo]: one N = 2 LCOL MMA (B_lo follows B_hi in the stage)
-          mma_f16_ss(dc, al + o, bh + o, idesc, 1u);       // corr += a_lo b_hi
+          for (int kk = 0; kk < BK / 16; ++kk) {
+            const uint64_t o = (uint64_t)(kk * 2);
+            const uint32_t acc = (kc == 0 && kk == 0) ? 0u : 1u;
+            mma_f16_ss(dm, ah + o, bh + o, idesc2, acc);     // [main | a_hi b_lo]: one N = 2 LCOL MMA (B_lo follows B_hi in the stage)
+            mma_f16_ss(dc, al + o, bh + o, idesc, 1u);       // corr += a_lo b_hi
+          }
+          mma_commit(empty + s);
+          if (kc == KCB - 1 || it == kblocks - 1) mma_commit(tmem_full + chunk);
         }
-        mma_commit(empty + s);
-        if (kc == KCB - 1 || it == kblocks - 1) mma_commit(tmem_full + chunk);
+        __syncwarp();
       }
     }
   } else {

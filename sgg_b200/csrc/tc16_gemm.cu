@@ -150,7 +150,7 @@ k_tc16(Params p, const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    {                                          // whole warp runs the loop, one elected lane issues (uniform operands)
       for (int it = 0; it < total; ++it) {
         const int s = it % STAGES, ph = (it / STAGES) & 1;
         mbar_wait(empty + s, ph ^ 1);
@@ -162,6 +162,7 @@ k_tc16(Params p, const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           k0 = (gk - t * kbt) * BK; am0 = (t / p.sk_ct) * BM; bj0 = (t % p.sk_ct) * NCOL;
         }
         uint8_t *st = stage_ptr(s);
+        if (elect_one()) {
         mbar_arrive_expect_tx(full + s, (DIRECT ? 0 : A_BYTES) + 2 * B_BYTES);
         const CUtensorMap *ta = (NSEG > 1 && seg == 1) ? &tmA1 : &tmA0;
         const CUtensorMap *tbh = (NSEG > 1 && seg == 1) ? &tmBh1 : &tmBh0;
@@ -180,11 +181,15 @@ k_tc16(Params p, const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           tma_load_2d(st + A_BYTES + b * (NBR * BK * 2), tbh, full + s, k0, row);
           tma_load_2d(st + A_BYTES + B_BYTES + b * (NBR * BK * 2), tbl, full + s, k0, row);
         }
+        }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // whole warp runs the loop, one ELECTED lane issues: keeps the descriptors in uniform registers (under `if (lane == 0)`
+    // every UTCHMMA is wrapped in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop)
+    {
       constexpr uint32_t idesc = make_idesc_f16(BM, NCOL);
       constexpr uint32_t idesc2 = make_idesc_f16(BM, CHUNKED ? 2 * NCOL : NCOL);
       (void)idesc2;
@@ -193,7 +198,7 @@ k_tc16(Params p, const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         mbar_wait(full + s, ph);
         mbar_wait(ready + s, ph);
         fence_after_sync();
-        if (it == 0) SGG_DBG(2);
+        if (it == 0 && lane == 0) SGG_DBG(2);
         const int seg = CHUNKED ? 0 : it / kblocks, kb = it - seg * kblocks;
         uint8_t *st = stage_ptr(s);
         const uint64_t ah = make_sdesc128(st), al = make_sdesc128(st + A_HALF);
@@ -212,6 +217,7 @@ k_tc16(Params p, const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           first = (kb == 0) ? 1u : 0u;
         }
         const uint32_t dc = dm + (uint32_t)CORR;
+        if (elect_one()) {
 #pragma unroll
         for (int kk = 0; kk < BK / 16; ++kk) {
           const uint64_t o = (uint64_t)(kk * 2);     // 16 fp16 = 32 bytes >> 4
@@ -230,8 +236,10 @@ k_tc16(Params p, const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         }
         mma_commit(empty + s);
         if (CHUNKED && (kc == KCB - 1 || it == total - 1)) mma_commit(tmem_full + (chunk & 1));
+        if (!CHUNKED && it == total - 1) mma_commit(tmem_full);
+        }
+        __syncwarp();
       }
-      if (!CHUNKED) mma_commit(tmem_full);
     }
   } else {
     // ===================== warps 2..9: convert A (fp32 -> fp16 [hi | lo], in place); LINEAR: + chunk drains =====================

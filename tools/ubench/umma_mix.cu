@@ -7,6 +7,9 @@
 //   bit 4: the issuing thread does one mbarrier.try_wait on an already completed barrier per k-block
 //   bit 5: warps 2..9 stream 16-byte shared-memory stores into an unrelated 64 KB region (stand-in for TMA writes)
 //   bit 6: warps 2..9 stream tcgen05.ld from the SAME columns the MMAs accumulate into
+//   bit 7: operands rotate through a ring of three A stages and three B stages (fresh shared-memory addresses every k-block)
+//   bit 8: the accumulators ping-pong between two TMEM buffer pairs every 4 k-blocks, first MMA of a chunk overwrites (acc = 0)
+//   bit 9: shared memory holds random fp16 data instead of zeros
 #include <cstdio>
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -31,8 +34,13 @@ __device__ __forceinline__ uint32_t try_wait(uint64_t *bar, uint32_t parity) {
 __global__ void __launch_bounds__(320, 1) k_mix(int mode, int kblocks, long long *cycles) {
   extern __shared__ uint8_t raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~(uintptr_t)1023);
-  for (int i = threadIdx.x; i < (160 * 1024) / 16; i += blockDim.x) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + 160 * 1024);   // [0] end, [1] done-at-start, [2..5] commit ring
+  for (int i = threadIdx.x; i < (192 * 1024) / 16; i += blockDim.x) {
+    uint32_t h = (uint32_t)i * 2654435761u;
+    // random fp16 pairs with small exponents (|x| < 2): sign/exponent bits masked
+    const uint32_t v = (mode & 512) ? ((h & 0x83FF83FFu) | 0x38003800u) : 0u;
+    reinterpret_cast<uint4 *>(smem)[i] = make_uint4(v, v ^ 0x00110011u, v ^ 0x01010101u, v);
+  }
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + 192 * 1024);   // [0] end, [1] done-at-start, [2..5] commit ring
   uint32_t *slot = reinterpret_cast<uint32_t *>(bars + 8);
   volatile int *stop = reinterpret_cast<volatile int *>(bars + 9);
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -54,17 +62,20 @@ __global__ void __launch_bounds__(320, 1) k_mix(int mode, int kblocks, long long
   if (warp == 1) {
     if (lane == 0) {
       const uint32_t base = smem_u32(smem);
-      const uint64_t ah = sdesc(base), al = sdesc(base + 16384), bh = sdesc(base + 32768);
       const uint32_t id2 = idesc(128, 256), id1 = idesc(128, 128);
       const long long t0 = clock64();
       for (int kb = 0; kb < kblocks; ++kb) {
         if (mode & 16) { while (!try_wait(bars + 1, 0)) {} }
         if (mode & 2) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t st = (mode & 128) ? (uint32_t)(kb % 3) : 0u;
+        const uint64_t ah = sdesc(base + st * 32768), al = sdesc(base + st * 32768 + 16384), bh = sdesc(base + 98304 + st * 32768);
+        const uint32_t d = tm + ((mode & 256) ? (uint32_t)(((kb >> 2) & 1) * 256) : 0u);
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
           const uint64_t o = (uint64_t)(kk * 2);
-          mma(tm, ah + o, bh + o, id2, 1);
-          mma(tm + 128, al + o, bh + o, id1, 1);
+          const uint32_t acc = ((mode & 256) && (kb & 3) == 0 && kk == 0) ? 0u : 1u;
+          mma(d, ah + o, bh + o, id2, acc);
+          mma(d + 128, al + o, bh + o, id1, 1);
         }
         if (mode & 1) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bars + 2 + (kb & 3))) : "memory");
       }
@@ -90,7 +101,7 @@ __global__ void __launch_bounds__(320, 1) k_mix(int mode, int kblocks, long long
         sink += r[0] + r[15];
       }
     } else if (mode & 32) {
-      uint8_t *dst = smem + 96 * 1024;
+      uint8_t *dst = smem + 128 * 1024;
       uint32_t i = threadIdx.x;
       while (!*stop) {
         *reinterpret_cast<uint4 *>(dst + ((i * 16) & 0xFFFF)) = make_uint4(i, i, i, i);
@@ -107,12 +118,12 @@ __global__ void __launch_bounds__(320, 1) k_mix(int mode, int kblocks, long long
 int main() {
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
-  const int smem = 160 * 1024 + 1024 + 256;
+  const int smem = 192 * 1024 + 1024 + 256;
   cudaFuncSetAttribute(k_mix, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   long long *dc;
   cudaMalloc(&dc, sms * 8);
   long long hc[256];
-  const int modes[] = {0, 1, 2, 3, 4, 8, 16, 32, 64, 1 | 2 | 16, 1 | 2 | 16 | 4, 1 | 2 | 16 | 8, 1 | 2 | 16 | 64, 1 | 2 | 16 | 32};
+  const int modes[] = {0, 128, 256, 512, 128 | 512, 128 | 256 | 512, 128 | 256 | 512 | 1 | 2 | 16, 128 | 256 | 512 | 1 | 2 | 16 | 64, 128 | 256 | 512 | 1 | 2 | 16 | 32, 128 | 256 | 512 | 1 | 2 | 16 | 32 | 64};
   for (int mode : modes) {
     const int kblocks = 4000;
     k_mix<<<sms, 320, smem>>>(mode, 400, dc);
@@ -123,9 +134,9 @@ int main() {
     double c = 0;
     for (int i = 0; i < sms; ++i) c += hc[i];
     c /= sms;
-    printf("mode %3d (%s%s%s%s%s%s%s): %7.1f cycles per k-block of 8 MMAs (floor 1024)\n", mode, mode & 1 ? "commit " : "", mode & 2 ? "fence " : "",
+    printf("mode %4d (%s%s%s%s%s%s%s%s%s%s): %7.1f cycles per k-block of 8 MMAs (tensor floor 768)\n", mode, mode & 1 ? "commit " : "", mode & 2 ? "fence " : "",
            mode & 4 ? "spinners " : "", mode & 8 ? "tmem-ld-other " : "", mode & 16 ? "issuer-try_wait " : "", mode & 32 ? "smem-stores " : "",
-           mode & 64 ? "tmem-ld-same " : "", c / kblocks);
+           mode & 64 ? "tmem-ld-same " : "", mode & 128 ? "rotate-stages " : "", mode & 256 ? "tmem-pingpong " : "", mode & 512 ? "random-data " : "", c / kblocks);
   }
   return 0;
 }
