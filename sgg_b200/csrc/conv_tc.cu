@@ -398,6 +398,7 @@ constexpr int SLAB_PLANE = (VH + 2) * VW * 128;   // 18432 B: 18 lines x 8 pixel
 // SGG_CONV_DBG=1: clock64 stamps of CTA 0 for its first 16 items: [item][0] MMA issue start, [1] MMA issue end,
 // [2] last chunk drained, [3] epilogue done
 __device__ long long g_conv_dbg[16 * 8];
+__device__ long long g_conv_cta[256 * 4];     // per CTA: items, cycles, start ns, end ns (SGG_CONV_DBG=1)
 
 // K-major SWIZZLE_128B descriptor (SBO = 1024 B) from a shared-memory address
 __device__ __forceinline__ uint64_t make_sdesc128_addr(uint32_t smem_addr) {
@@ -458,6 +459,8 @@ k_conv3x3_v2(const ConvParams p, const int n_items, const int n_sp, const __grid
   if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  long long dbg_c0 = 0, dbg_n0 = 0;
+  if (p.dbg && threadIdx.x == 64) { dbg_c0 = clock64(); asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_n0)); }
 
   // work item -> (channel tile, image, tile row, tile column) of THIS CTA; spatial index n_sp.. is padding (n = B: loads are
   // zero-filled by TMA, stores are masked)
@@ -670,19 +673,32 @@ k_conv3x3_v2(const ConvParams p, const int n_items, const int n_sp, const __grid
         } else {
           const size_t off = (((size_t)n * Ho + y) * Wo + x) * p.Cout + cbase;
 #pragma unroll
-          for (int c = 0; c < HC; c += 8) {
-            uint4 hi, lo;
-            split2(acc[c], acc[c + 1], hi.x, lo.x); split2(acc[c + 2], acc[c + 3], hi.y, lo.y);
-            split2(acc[c + 4], acc[c + 5], hi.z, lo.z); split2(acc[c + 6], acc[c + 7], hi.w, lo.w);
-            ovf |= f16x2_nonfinite(hi.x) | f16x2_nonfinite(hi.y) | f16x2_nonfinite(hi.z) | f16x2_nonfinite(hi.w);
-            *reinterpret_cast<uint4 *>(p.out_hi + off + c) = hi;
-            *reinterpret_cast<uint4 *>(p.out_lo + off + c) = lo;
+          for (int c = 0; c < HC; c += 16) {
+            uint4 hi[2], lo[2];
+#pragma unroll
+            for (int k = 0; k < 16; k += 8) {
+              uint4 &h = hi[k >> 3], &l = lo[k >> 3];
+              split2(acc[c + k], acc[c + k + 1], h.x, l.x); split2(acc[c + k + 2], acc[c + k + 3], h.y, l.y);
+              split2(acc[c + k + 4], acc[c + k + 5], h.z, l.z); split2(acc[c + k + 6], acc[c + k + 7], h.w, l.w);
+              ovf |= f16x2_nonfinite(h.x) | f16x2_nonfinite(h.y) | f16x2_nonfinite(h.z) | f16x2_nonfinite(h.w);
+            }
+            stg256(p.out_hi + off + c, hi[0], hi[1]);
+            stg256(p.out_lo + off + c, lo[0], lo[1]);
           }
         }
       }
       if (p.dbg && blockIdx.x == 0 && threadIdx.x == 64 && ord < 16) g_conv_dbg[ord * 8 + 3] = clock64();
     }
     if (ovf) atomicOr(&g_conv_overflow, 1u);
+    if (p.dbg && threadIdx.x == 64) {
+      long long n1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(n1));
+      if (blockIdx.x == 0) { g_conv_dbg[15 * 8 + 5] = ord; g_conv_dbg[15 * 8 + 6] = clock64() - dbg_c0; g_conv_dbg[15 * 8 + 7] = n1 - dbg_n0; }
+      if (blockIdx.x < 256) {
+        g_conv_cta[blockIdx.x * 4] = ord; g_conv_cta[blockIdx.x * 4 + 1] = clock64() - dbg_c0;
+        g_conv_cta[blockIdx.x * 4 + 2] = dbg_n0; g_conv_cta[blockIdx.x * 4 + 3] = n1;
+      }
+    }
   }
   tc::fence_before_sync();
   if constexpr (CG == 2) {
@@ -695,23 +711,29 @@ k_conv3x3_v2(const ConvParams p, const int n_items, const int n_sp, const __grid
 }
 
 // First VGG layer: 3 -> Cout (64) channels, fp32 NCHW image in, relu(conv) as NHWC fp16 planes out.
-// thread <-> (pixel, 16 output channels); weights [Cout][27] + bias staged in shared memory.
+// thread <-> one pixel, ALL output channels: every lane of a warp reads the same weight, so the [27][COUT] weight table in
+// shared memory is read with broadcast LDS.128 (four channels per load, no bank conflicts) and the 27 input loads of a warp
+// are 128-byte coalesced rows of the NCHW image.  (The first version mapped a thread to 16 channels of a pixel: four
+// different weight rows per warp load, 2-way bank conflicts, one LDS per FMA — 5.25 ms at 32 x 608 x 608, LSU-bound;
+// the 3 GB of output planes are 0.55 ms of HBM time.)
 template <int COUT>
 __global__ void __launch_bounds__(256) k_conv_first(const float *__restrict__ img, const float *__restrict__ w,
                                                     const float *__restrict__ bias, int B, int H, int W,
                                                     __half *__restrict__ out_hi, __half *__restrict__ out_lo) {
-  __shared__ float sw[COUT * 27 + COUT];
-  for (int i = threadIdx.x; i < COUT * 27; i += blockDim.x) sw[i] = w[i];
-  for (int i = threadIdx.x; i < COUT; i += blockDim.x) sw[COUT * 27 + i] = bias[i];
+  __shared__ __align__(16) float sw[27 * COUT + COUT];     // [j = c * 9 + dy * 3 + dx][cout], then bias
+  for (int i = threadIdx.x; i < COUT * 27; i += blockDim.x) {
+    const int co = i / 27, j = i - co * 27;
+    sw[j * COUT + co] = w[i];
+  }
+  for (int i = threadIdx.x; i < COUT; i += blockDim.x) sw[27 * COUT + i] = bias[i];
   __syncthreads();
-  constexpr int GROUPS = COUT / 16;
-  const size_t total = (size_t)B * H * W * GROUPS;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int gq = (int)(i % GROUPS);
-    size_t pix = i / GROUPS;
-    const int x = (int)(pix % W); pix /= W;
-    const int y = (int)(pix % H);
-    const int n = (int)(pix / H);
+  const size_t total = (size_t)B * H * W;
+  uint32_t ovf = 0;
+  for (size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x; pix < total; pix += (size_t)gridDim.x * blockDim.x) {
+    const int x = (int)(pix % W);
+    const size_t r = pix / W;
+    const int y = (int)(r % H);
+    const int n = (int)(r / H);
     float in[27];
 #pragma unroll
     for (int c = 0; c < 3; ++c)
@@ -722,27 +744,37 @@ __global__ void __launch_bounds__(256) k_conv_first(const float *__restrict__ im
           const int yy = y + dy - 1, xx = x + dx - 1;
           in[c * 9 + dy * 3 + dx] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(img + (((size_t)n * 3 + c) * H + yy) * W + xx) : 0.f;
         }
-    float o[16];
+    const size_t off = pix * COUT;
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      const float *wk = sw + (gq * 16 + k) * 27;
-      float s = sw[COUT * 27 + gq * 16 + k];
+    for (int g = 0; g < COUT; g += 16) {                    // 16 channels at a time: 16 accumulators live
+      float o[16];
 #pragma unroll
-      for (int j = 0; j < 27; ++j) s = fmaf(in[j], wk[j], s);
-      o[k] = fmaxf(s, 0.f);
-    }
-    const size_t off = (((size_t)n * H + y) * W + x) * COUT + gq * 16;
+      for (int k = 0; k < 16; k += 4) {
+        const float4 bv = *reinterpret_cast<const float4 *>(sw + 27 * COUT + g + k);
+        o[k] = bv.x; o[k + 1] = bv.y; o[k + 2] = bv.z; o[k + 3] = bv.w;
+      }
 #pragma unroll
-    for (int k = 0; k < 16; k += 8) {
-      uint4 hi, lo;
-      split2(o[k], o[k + 1], hi.x, lo.x); split2(o[k + 2], o[k + 3], hi.y, lo.y);
-      split2(o[k + 4], o[k + 5], hi.z, lo.z); split2(o[k + 6], o[k + 7], hi.w, lo.w);
-      if (f16x2_nonfinite(hi.x) | f16x2_nonfinite(hi.y) | f16x2_nonfinite(hi.z) | f16x2_nonfinite(hi.w))
-        atomicOr(&g_conv_overflow, 1u);
-      *reinterpret_cast<uint4 *>(out_hi + off + k) = hi;
-      *reinterpret_cast<uint4 *>(out_lo + off + k) = lo;
+      for (int j = 0; j < 27; ++j) {
+#pragma unroll
+        for (int k = 0; k < 16; k += 4) {
+          const float4 wv = *reinterpret_cast<const float4 *>(sw + j * COUT + g + k);   // same address in every lane: broadcast
+          o[k] = fmaf(in[j], wv.x, o[k]); o[k + 1] = fmaf(in[j], wv.y, o[k + 1]);
+          o[k + 2] = fmaf(in[j], wv.z, o[k + 2]); o[k + 3] = fmaf(in[j], wv.w, o[k + 3]);
+        }
+      }
+      uint4 hi[2], lo[2];
+#pragma unroll
+      for (int k = 0; k < 16; k += 8) {
+        uint4 &h = hi[k >> 3], &l = lo[k >> 3];
+        split2(fmaxf(o[k], 0.f), fmaxf(o[k + 1], 0.f), h.x, l.x); split2(fmaxf(o[k + 2], 0.f), fmaxf(o[k + 3], 0.f), h.y, l.y);
+        split2(fmaxf(o[k + 4], 0.f), fmaxf(o[k + 5], 0.f), h.z, l.z); split2(fmaxf(o[k + 6], 0.f), fmaxf(o[k + 7], 0.f), h.w, l.w);
+        ovf |= f16x2_nonfinite(h.x) | f16x2_nonfinite(h.y) | f16x2_nonfinite(h.z) | f16x2_nonfinite(h.w);
+      }
+      stg256(out_hi + off + g, hi[0], hi[1]);                // 16 channels = one 32-byte sector per plane
+      stg256(out_lo + off + g, lo[0], lo[1]);
     }
   }
+  if (ovf) atomicOr(&g_conv_overflow, 1u);
 }
 
 // w [Cout, Cin, 3, 3] fp32 -> planes [Cout][tap][Cin] fp16 (hi, lo * 2^11): the K order of the implicit GEMM
@@ -878,6 +910,24 @@ static int launch_conv_v2(ConvParams p, const __half *in_hi, const __half *in_lo
       const long long t0 = h[0];
       for (int i = 0; i < 10; ++i)
         fprintf(stderr, "[conv dbg] %2d: %7lld %7lld | %7lld %7lld\n", i, h[i * 8] - t0, h[i * 8 + 1] - t0, h[i * 8 + 2] - t0, h[i * 8 + 3] - t0);
+      long long c[256 * 4];
+      if (cudaMemcpyFromSymbol(c, g_conv_cta, sizeof(c)) == cudaSuccess) {
+        const int nb = (int)(units * CG) < 256 ? (int)(units * CG) : 256;
+        long long tmin = c[2], tmax = c[3], cmin = c[1], cmax = c[1], first_end = c[3];
+        for (int b = 0; b < nb; ++b) {
+          if (c[b * 4 + 2] < tmin) tmin = c[b * 4 + 2];
+          if (c[b * 4 + 3] > tmax) tmax = c[b * 4 + 3];
+          if (c[b * 4 + 3] < first_end) first_end = c[b * 4 + 3];
+          if (c[b * 4 + 1] < cmin) cmin = c[b * 4 + 1];
+          if (c[b * 4 + 1] > cmax) cmax = c[b * 4 + 1];
+        }
+        long long smax = 0;
+        for (int b = 0; b < nb; ++b) if (c[b * 4 + 2] - tmin > smax) smax = c[b * 4 + 2] - tmin;
+        fprintf(stderr, "[conv dbg] %d CTAs: span %lld ns (first start -> last end), last CTA start +%lld ns, first end +%lld ns, cycles min %lld max %lld\n", nb,
+                tmax - tmin, smax, first_end - tmin, cmin, cmax);
+      }
+      fprintf(stderr, "[conv dbg] CTA 0: %lld items in %lld cycles = %lld ns (%.2f GHz): %.0f cycles / item\n", h[15 * 8 + 5], h[15 * 8 + 6], h[15 * 8 + 7],
+              (double)h[15 * 8 + 6] / (double)h[15 * 8 + 7], (double)h[15 * 8 + 6] / (double)(h[15 * 8 + 5] ? h[15 * 8 + 5] : 1));
     }
   }
   return 0;
@@ -905,7 +955,7 @@ extern "C" int sgg_conv3x3_first(const float *img, const float *w, const float *
   if (Cout != 64) return sgg_set_err(SGG_E_BADARG, "conv3x3_first: Cout must be 64");
   const size_t n = (size_t)B * H * W * 64;
   __half *hi = (__half *)out_planes;
-  const size_t threads = (size_t)B * H * W * 4;
+  const size_t threads = (size_t)B * H * W;
   const int blocks = (int)((threads + 255) / 256 < 148 * 16 ? (threads + 255) / 256 : 148 * 16);
   sgg::conv::k_conv_first<64><<<blocks, 256, 0, (cudaStream_t)stream>>>(img, w, bias, B, H, W, hi, hi + n);
   SGG_RETURN_IF_LAUNCH_FAILED("k_conv_first");

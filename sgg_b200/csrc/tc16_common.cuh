@@ -35,6 +35,12 @@ __device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint64_t adesc, uint
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// 32-byte global store (sm_100: STG.256), address 32-byte aligned: one full sector per thread and instruction
+__device__ __forceinline__ void stg256(void *p, const uint4 &a, const uint4 &b) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y),
+               "r"(b.z), "r"(b.w)
+               : "memory");
+}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

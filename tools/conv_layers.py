@@ -27,6 +27,12 @@ for li, (wt, bs, pool) in enumerate(layers[1:], start=1):
     for _ in range(3): run()
     b.record(); torch.cuda.synchronize()
     ms = a.elapsed_time(b) / 3
+    if os.environ.get('CEACH'):
+        each = []
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize(); e0.record(); run(); e1.record(); torch.cuda.synchronize(); each.append(round(e0.elapsed_time(e1), 3))
+        print('   single launches (ms):', each, ' free/total GB: %.1f / %.1f' % tuple(v / 1e9 for v in torch.cuda.mem_get_info()))
     fl = 2.0 * B * h * w * cout * 9 * cin
     tiles = ((h + 7) // 8) * ((w + 15) // 16) * B * (cout // (128 if cout % 128 == 0 else 64))
     kb = 9 * cin // 64

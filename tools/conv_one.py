@@ -54,3 +54,9 @@ else:
     for _ in range(reps): run()
     torch.cuda.synchronize()
     print('done layer', L, (cin, cout, h, w))
+if os.environ.get('CEACH'):
+    for i in range(4):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(); t0 = time.time()
+        a.record(); run(); b.record(); torch.cuda.synchronize(); t1 = time.time()
+        print('launch %d: events %.3f ms, wall %.3f ms' % (i, a.elapsed_time(b), (t1 - t0) * 1e3))
