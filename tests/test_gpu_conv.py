@@ -84,3 +84,36 @@ def test_model_backbone_uses_the_tensor_core_stack_and_matches_cudnn():
             del os.environ['SGG_BACKBONE']
     assert m._vgg_layers and a.shape == b.shape == (2, 512, 4, 6)
     assert float((a - b).abs().max()) <= 1e-4 * max(1.0, float(b.abs().max()))
+
+
+_VARIANT_CHECK = r'''
+import sys, torch, torch.nn as nn
+sys.path.insert(0, %r)
+from sgg_b200 import ops
+from sgg_b200.model import _vgg16_parts
+torch.manual_seed(0)
+feats, _ = _vgg16_parts()
+feats = feats.cuda().eval()
+layers = ops.vgg_layers(feats)
+x = torch.rand(3, 3, 48, 80, device='cuda', generator=torch.Generator(device='cuda').manual_seed(1))
+with torch.no_grad(), torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+    for n_conv, upto in ((4, 10), (13, len(list(feats.children())))):     # a pooled prefix (odd tile count) and the whole stack
+        r = nn.Sequential(*list(feats.children())[:upto])(x)
+        y = ops.vgg_features(x, layers[:n_conv])
+        err = float((y - r).abs().max()) / float(r.abs().max())
+        assert y.shape == r.shape and err <= 1e-4, (n_conv, err)
+assert ops._lib.load().sgg_conv_overflow(1) == 0
+print('ok')
+'''
+
+
+@pytest.mark.parametrize('env', [{'SGG_CONV_V': '1', 'SGG_CONV_CG': '1'}, {'SGG_CONV_V': '1', 'SGG_CONV_CG': '2'},
+                                 {'SGG_CONV_V': '2', 'SGG_CONV_CG': '2'}])
+def test_conv_kernel_variants_vs_cudnn_fp32(env):
+    """The non-default kernels stay exact: v1 (per-tap boxes, one tile per CTA) and the cta_group::2 pairs of both versions.
+    The variant is chosen once per process (environment), hence the subprocess."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    e = dict(os.environ); e.update(env)
+    out = subprocess.run([sys.executable, '-c', _VARIANT_CHECK % root], env=e, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and out.stdout.strip().endswith('ok'), (out.stdout[-400:], out.stderr[-800:])
