@@ -854,14 +854,18 @@ static int launch_conv(const ConvParams &p, const __half *in_hi, const __half *i
   return 0;
 }
 
-// SGG_CONV_V = 1 | 2 (default 2): per-tap boxes / halo tiles + persistent CTAs
-static int conv_version() {
+// SGG_CONV_V = 1 | 2: force a kernel version; default 0 = per layer: v2 (slabs + persistent CTAs) up to 256 input channels,
+// v1 (per-tap boxes, one tile per CTA) from 512 — measured inside the stack at 32 x 608^2 (profiles/r02_conv_experiments.md
+// section 8): v2 wins 4.58 -> 3.87, 1.96 -> 1.27, 1.40 -> 1.19 ms on the K = 576 / 1152 layers, v1 wins 2.40 -> 2.2 and
+// 0.72 -> 0.65 ms on the 512-channel layers (72 k-blocks per tile amortise its prologue; less control per k-block).
+static int conv_version(int Cin) {
   static int v = -1;
   if (v < 0) {
     const char *e = getenv("SGG_CONV_V");
-    v = (e && atoi(e) == 1) ? 1 : 2;
+    v = e ? atoi(e) : 0;
+    if (v < 0 || v > 2) v = 0;
   }
-  return v;
+  return v ? v : (Cin >= 512 ? 1 : 2);
 }
 
 template <int NC, int CG>
@@ -983,7 +987,7 @@ extern "C" int sgg_conv3x3_tc(const void *in_planes, const void *w_planes, const
   p.out_f32 = out_f32_nchw;
   const size_t wn = (size_t)Cout * 9 * Cin;
   const bool pair = conv_cta_group() == 2;
-  if (conv_version() == 2) {
+  if (conv_version(Cin) == 2) {
     if (Cout % 128 == 0)
       return pair ? launch_conv_v2<128, 2>(p, ih, ih + n_in, wh, wh + wn, (cudaStream_t)stream)
                   : launch_conv_v2<128, 1>(p, ih, ih + n_in, wh, wh + wn, (cudaStream_t)stream);

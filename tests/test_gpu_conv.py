@@ -108,9 +108,10 @@ print('ok')
 
 
 @pytest.mark.parametrize('env', [{'SGG_CONV_V': '1', 'SGG_CONV_CG': '1'}, {'SGG_CONV_V': '1', 'SGG_CONV_CG': '2'},
-                                 {'SGG_CONV_V': '2', 'SGG_CONV_CG': '2'}])
+                                 {'SGG_CONV_V': '2', 'SGG_CONV_CG': '1'}, {'SGG_CONV_V': '2', 'SGG_CONV_CG': '2'}])
 def test_conv_kernel_variants_vs_cudnn_fp32(env):
-    """The non-default kernels stay exact: v1 (per-tap boxes, one tile per CTA) and the cta_group::2 pairs of both versions.
+    """Every kernel stays exact on every layer (the default picks v1 or v2 per layer): v1 (per-tap boxes, one tile per CTA),
+    v2 (slabs, persistent CTAs) and the cta_group::2 pairs of both.
     The variant is chosen once per process (environment), hence the subprocess."""
     import os, subprocess, sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
