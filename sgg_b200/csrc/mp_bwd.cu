@@ -12,6 +12,7 @@
 //   k_node_bwd         CTA per node (CSR, fixed order): dP[n] = sum_out g_sub dgi_e + sum_in g_obj dgi_e;
 //                      da[n,k] = sum of edge dlogits; dV[n] += sum_k da[n,k] w_k[:H]
 // All reductions are deterministic (no float atomics).
+#include <string.h>
 #include <stdlib.h>
 #include "common.cuh"
 #include "kernels.h"
@@ -213,7 +214,7 @@ static int launch_add(float *c, const float *t, size_t n, cudaStream_t st) {    
   return 0;
 }
 constexpr int TC_BWD_MIN_ROWS = 256;     // dX-type GEMMs with fewer rows stay on the SIMT tiles
-constexpr int TC_BWD_MIN_K = 2048;       // dW-type GEMMs with a shorter reduction stay on the SIMT tiles (split-K)
+constexpr int TC_BWD_MIN_K = 256;        // dW-type GEMMs with a shorter reduction stay on the SIMT tiles (split-K)
 static inline int pad32(int x) { return (x + 31) & ~31; }
 
 struct BwdScratch {
@@ -221,6 +222,8 @@ struct BwdScratch {
   size_t sk_floats;
   // tensor-core backward: W^T splits (node_ih, node_hh, edge_ih, edge_hh), transposed operands, GEMM output, split-K partials
   float *wt[4], *xT, *bT, *tmp, *lin;
+  // scaled 3xFP16 engine (default): s * dY (exact power-of-two scale from the device-side abs-max), scale pair, abs-max partials
+  float *dys, *sc, *p2;
 };
 constexpr int SPLITK_MAX = 4;      // split-K slices of the [3H,H] weight-gradient GEMMs (reduction over E or N rows)
 static size_t bwd_layout(BwdScratch *s, void *ws, int N, int E, int H) {
@@ -246,7 +249,13 @@ static size_t bwd_layout(BwdScratch *s, void *ws, int N, int E, int H) {
   const size_t l1 = tc32_linear_workspace_floats((int)e1, H, 3 * H), l2 = tc32_linear_workspace_floats((int)n1, H, 3 * H);
   if (l1 > lin) lin = l1;
   if (l2 > lin) lin = l2;
+  const size_t l3 = tc16::linear_workspace_floats(3 * H, H, mp), l4 = tc16::linear_workspace_floats((int)big, H, 3 * H);
+  if (l3 > lin) lin = l3;
+  if (l4 > lin) lin = l4;
   s->lin = ar.take<float>(lin > 0 ? lin : 1);
+  s->dys = ar.take<float>(big * 3 * H);
+  s->sc = ar.take<float>(4);
+  s->p2 = ar.take<float>(sgg_pow2_scale_workspace_bytes() / sizeof(float));
   return ar.off;
 }
 
@@ -287,15 +296,38 @@ extern "C" int sgg_mp_backward(const float *obj_rep, const float *rel_rep, const
   static const bool tc_env = [] { const char *v = getenv("SGG_BWD_TC"); return v == nullptr || atoi(v) != 0; }();
   const bool tc_on = tc_env && w->edge_w_hh_split != nullptr && w->node_w_hh_split != nullptr;
   enum { WT_NODE_IH = 0, WT_NODE_HH = 1, WT_EDGE_IH = 2, WT_EDGE_HH = 3 };
-  if (tc_on) {      // W [3H,H] -> split(W^T) [H,3H], once per backward call (4 x 3 MB)
+  // engine of the tensor-core routes: scaled 3xFP16 (default; the gradient operand is multiplied by an exact power of two
+  // so that max|s dY| lies in [1024, 2048) — same scheme as ops.linear_backward) or 3xTF32 (SGG_BWD_ENGINE=tc32)
+  static const bool tc16_env = [] { const char *v = getenv("SGG_BWD_ENGINE"); return v == nullptr || strcmp(v, "tc32") != 0; }();
+  const bool use16 = tc_on && tc16_env;
+  if (tc_on) {      // W [3H,H] -> W^T [H,3H] operand planes, once per backward call
     const float *ws4[4] = {w->node_w_ih, w->node_w_hh, w->edge_w_ih, w->edge_w_hh};
-    for (int i = 0; i < 4; ++i)
-      if ((rc = launch_transpose(ws4[i], 3 * H, H, s.wt[i], 3 * H, true, st))) return rc;
+    for (int i = 0; i < 4; ++i) {
+      if (use16) rc = sgg_bwd_transpose16(ws4[i], H, 3 * H, H, s.wt[i], 3 * H, 1, nullptr, st);     // fp16 [hi | lo] planes
+      else rc = launch_transpose(ws4[i], 3 * H, H, s.wt[i], 3 * H, true, st);                        // 3xTF32 [hi | lo]
+      if (rc) return rc;
+    }
   }
+  // scaled copy of a gradient operand: s.sc = (s, 1/s), s.dys = s * dY.  One call serves the dX and the dW GEMM of dY.
+  const float *scaled_of = nullptr;
+  auto scale16 = [&](const float *dY, int M) -> int {
+    if (scaled_of == dY) return 0;
+    const long long n = (long long)M * 3 * H;
+    int r = sgg_pow2_scale(dY, n, s.sc, s.p2, sgg_pow2_scale_workspace_bytes(), st);
+    if (r == 0) r = sgg_scale_by(dY, n, s.sc, s.dys, st);
+    scaled_of = r == 0 ? dY : nullptr;
+    return r;
+  };
   // dX[M,H] (=|+=) dY[M,3H] W[3H,H]
   auto gemm_dx = [&](const float *dY, int wi, const float *W, float *out, int M, bool acc) -> int {
     if (!tc_on || M < TC_BWD_MIN_ROWS) return gemm(dY, 3 * H, false, W, H, true, out, H, M, H, 3 * H, acc);
-    int r = tc32_linear(dY, s.wt[wi], nullptr, acc ? s.tmp : out, M, H, 3 * H, 0, s.lin, st);
+    int r;
+    if (use16) {
+      if ((r = scale16(dY, M))) return r;
+      r = tc16::linear_scaled(s.dys, s.wt[wi], acc ? s.tmp : out, M, H, 3 * H, s.sc + 1, s.lin, st);
+    } else {
+      r = tc32_linear(dY, s.wt[wi], nullptr, acc ? s.tmp : out, M, H, 3 * H, 0, s.lin, st);
+    }
     if (r == 0 && acc) r = launch_add(out, s.tmp, (size_t)M * H, st);
     return r;
   };
@@ -303,9 +335,17 @@ extern "C" int sgg_mp_backward(const float *obj_rep, const float *rel_rep, const
   auto gemm_dw = [&](const float *dY, const float *X, float *dW, int M) -> int {
     if (!tc_on || M < TC_BWD_MIN_K) return gemm(dY, 3 * H, true, X, H, true, dW, H, 3 * H, H, M, true);
     const int mp = pad32(M);
-    int r = launch_transpose(dY, M, 3 * H, s.xT, mp, false, st);
-    if (r == 0) r = launch_transpose(X, M, H, s.bT, mp, true, st);
-    if (r == 0) r = tc32_linear(s.xT, s.bT, nullptr, s.tmp, 3 * H, H, mp, 0, s.lin, st);
+    int r;
+    if (use16) {
+      if ((r = scale16(dY, M))) return r;
+      r = sgg_bwd_transpose16(s.dys, 3 * H, M, 3 * H, s.xT, mp, 0, nullptr, st);                     // (s dY)^T  [3H, mp] fp32
+      if (r == 0) r = sgg_bwd_transpose16(X, H, M, H, s.bT, mp, 1, nullptr, st);                     // X^T planes [H, mp]
+      if (r == 0) r = tc16::linear_scaled(s.xT, s.bT, s.tmp, 3 * H, H, mp, s.sc + 1, s.lin, st);
+    } else {
+      r = launch_transpose(dY, M, 3 * H, s.xT, mp, false, st);
+      if (r == 0) r = launch_transpose(X, M, H, s.bT, mp, true, st);
+      if (r == 0) r = tc32_linear(s.xT, s.bT, nullptr, s.tmp, 3 * H, H, mp, 0, s.lin, st);
+    }
     if (r == 0) r = launch_add(dW, s.tmp, (size_t)3 * H * H, st);
     return r;
   };
@@ -321,20 +361,23 @@ extern "C" int sgg_mp_backward(const float *obj_rep, const float *rel_rep, const
     if (N > 0) {
       k_gru_bwd<<<ew_blocks(vN / 4), 256, 0, st>>>(dVn, tp.cacheV + (size_t)(t + 1) * N * 4 * H, V, N, H, s.dgi_n, s.dgh_n, dV);
       SGG_RETURN_IF_LAUNCH_FAILED("k_gru_bwd");
+      scaled_of = nullptr;                  // the gradient buffers were just rewritten
+      // the dW and the dX GEMM of one gradient operand back to back: they share its scaled copy
       if (grads->node_w_ih && (rc = gemm_dw(s.dgi_n, ctx, grads->node_w_ih, N))) return rc;
+      if ((rc = gemm_dx(s.dgi_n, WT_NODE_IH, w->node_w_ih, s.dctx, N, false))) return rc;
       if (grads->node_w_hh && (rc = gemm_dw(s.dgh_n, V, grads->node_w_hh, N))) return rc;
+      if ((rc = gemm_dx(s.dgh_n, WT_NODE_HH, w->node_w_hh, dV, N, true))) return rc;
       if ((rc = colsum(s.dgi_n, N, 3 * H, grads->node_b_ih))) return rc;
       if ((rc = colsum(s.dgh_n, N, 3 * H, grads->node_b_hh))) return rc;
-      if ((rc = gemm_dx(s.dgi_n, WT_NODE_IH, w->node_w_ih, s.dctx, N, false))) return rc;
-      if ((rc = gemm_dx(s.dgh_n, WT_NODE_HH, w->node_w_hh, dV, N, true))) return rc;
     }
     if (E > 0) {
       k_gru_bwd<<<ew_blocks(eN / 4), 256, 0, st>>>(dEn, tp.cacheE + (size_t)(t + 1) * E * 4 * H, Eh, E, H, s.dgi_e, s.dgh_e, dE);
       SGG_RETURN_IF_LAUNCH_FAILED("k_gru_bwd");
+      scaled_of = nullptr;
       if (grads->edge_w_hh && (rc = gemm_dw(s.dgh_e, Eh, grads->edge_w_hh, E))) return rc;
+      if ((rc = gemm_dx(s.dgh_e, WT_EDGE_HH, w->edge_w_hh, dE, E, true))) return rc;
       if ((rc = colsum(s.dgh_e, E, 3 * H, grads->edge_b_hh))) return rc;
       if ((rc = colsum(s.dgi_e, E, 3 * H, grads->edge_b_ih))) return rc;
-      if ((rc = gemm_dx(s.dgh_e, WT_EDGE_HH, w->edge_w_hh, dE, E, true))) return rc;
       k_edge_bwd<<<(int)(((size_t)E * 32 + 255) / 256), 256, 0, st>>>(s.dgi_e, P, s.dctx, Eh, gt, g.subj, g.obj, E, H,
                                                                     w->gate_w[0], w->gate_w[1], w->gate_w[2],
                                                                     w->gate_w[3], s.dl, dE);
@@ -348,6 +391,7 @@ extern "C" int sgg_mp_backward(const float *obj_rep, const float *rel_rep, const
         k_node_bwd<<<N, 128, 0, st>>>(s.dgi_e, gt, s.dl, g.out_ptr, g.out_idx, g.in_ptr, g.in_idx, H, w->gate_w[0],
                                       w->gate_w[1], w->gate_w[2], w->gate_w[3], s.dP, s.da, dV);
         SGG_RETURN_IF_LAUNCH_FAILED("k_node_bwd");
+        scaled_of = nullptr;
         if (grads->edge_w_ih && (rc = gemm_dw(s.dP, V, grads->edge_w_ih, N))) return rc;
         if ((rc = gemm_dx(s.dP, WT_EDGE_IH, w->edge_w_ih, dV, N, true))) return rc;
         if ((rc = launch_wsum4(s.da, V, N, H, s.tV, true, s.ws4, st))) return rc;      // tV[k] += sum_n da[n][k] V[n]
@@ -361,18 +405,20 @@ extern "C" int sgg_mp_backward(const float *obj_rep, const float *rel_rep, const
   if (N > 0) {
     k_gru_bwd<<<ew_blocks(vN / 4), 256, 0, st>>>(dVn, tp.cacheV, nullptr, N, H, s.dgi_n, s.dgh_n, nullptr);
     SGG_RETURN_IF_LAUNCH_FAILED("k_gru_bwd");
+    scaled_of = nullptr;
     if (grads->node_w_ih && (rc = gemm_dw(s.dgi_n, obj_rep, grads->node_w_ih, N))) return rc;
+    if (d_obj_rep && (rc = gemm_dx(s.dgi_n, WT_NODE_IH, w->node_w_ih, d_obj_rep, N, false))) return rc;
     if ((rc = colsum(s.dgi_n, N, 3 * H, grads->node_b_ih))) return rc;
     if ((rc = colsum(s.dgh_n, N, 3 * H, grads->node_b_hh))) return rc;
-    if (d_obj_rep && (rc = gemm_dx(s.dgi_n, WT_NODE_IH, w->node_w_ih, d_obj_rep, N, false))) return rc;
   }
   if (E > 0) {
     k_gru_bwd<<<ew_blocks(eN / 4), 256, 0, st>>>(dEn, tp.cacheE, nullptr, E, H, s.dgi_e, s.dgh_e, nullptr);
     SGG_RETURN_IF_LAUNCH_FAILED("k_gru_bwd");
+    scaled_of = nullptr;
     if (grads->edge_w_ih && (rc = gemm_dw(s.dgi_e, rel_rep, grads->edge_w_ih, E))) return rc;
+    if (d_rel_rep && (rc = gemm_dx(s.dgi_e, WT_EDGE_IH, w->edge_w_ih, d_rel_rep, E, false))) return rc;
     if ((rc = colsum(s.dgi_e, E, 3 * H, grads->edge_b_ih))) return rc;
     if ((rc = colsum(s.dgh_e, E, 3 * H, grads->edge_b_hh))) return rc;
-    if (d_rel_rep && (rc = gemm_dx(s.dgi_e, WT_EDGE_IH, w->edge_w_ih, d_rel_rep, E, false))) return rc;
   }
   k_gate_grad_finish<<<(4 * H + 255) / 256, 256, 0, st>>>(s.tV, s.tE, s.gb, H, grads->gate_w[0], grads->gate_w[1],
                                                           grads->gate_w[2], grads->gate_w[3], grads->gate_b[0],
