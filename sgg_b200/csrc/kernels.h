@@ -33,10 +33,12 @@ int tc_gru(int mode, const float *x, const float *h, const float *w_ih_split, co
 namespace tc16 {
 // LINEAR whose epilogue / reducer also writes the fp16 [hi | lo * 2^11] planes of y (nullable; Nout % 4 == 0)
 int linear_planes(const float *x, const float *w_split, const float *b, float *y, __half *y_hi, __half *y_lo, int M,
-                  int Nout, int K, int relu, float *ws, cudaStream_t st, const float *out_scale = nullptr);
-// y = out_scale[0] * (x w^T) on the 3xFP16 engine whatever the process-wide engine is (scaled backward GEMMs)
+                  int Nout, int K, int relu, float *ws, cudaStream_t st, const float *out_scale = nullptr,
+                  const float *in_scale = nullptr);
+// y = out_scale[0] * ((in_scale[0] * x) w^T) on the 3xFP16 engine whatever the process-wide engine is (scaled backward
+// GEMMs; in_scale nullable: the A operand is multiplied by it inside the kernel's fp32 -> fp16 split)
 int linear_scaled(const float *x, const float *w_split, float *y, int M, int Nout, int K, const float *out_scale, float *ws,
-                  cudaStream_t st);
+                  cudaStream_t st, const float *in_scale = nullptr);
 size_t linear_workspace_floats(int M, int Nout, int K);
 }  // namespace tc16
 // Fused message-passing loop of the 3xFP16 engine (mp_fused.cu): 2 launches per iteration.

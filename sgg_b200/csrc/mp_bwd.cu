@@ -222,8 +222,8 @@ struct BwdScratch {
   size_t sk_floats;
   // tensor-core backward: W^T splits (node_ih, node_hh, edge_ih, edge_hh), transposed operands, GEMM output, split-K partials
   float *wt[4], *xT, *bT, *tmp, *lin;
-  // scaled 3xFP16 engine (default): s * dY (exact power-of-two scale from the device-side abs-max), scale pair, abs-max partials
-  float *dys, *sc, *p2;
+  // scaled 3xFP16 engine (default): exact power-of-two scale pair (s, 1/s) from the device-side abs-max, abs-max partials
+  float *sc, *p2;
 };
 constexpr int SPLITK_MAX = 4;      // split-K slices of the [3H,H] weight-gradient GEMMs (reduction over E or N rows)
 static size_t bwd_layout(BwdScratch *s, void *ws, int N, int E, int H) {
@@ -253,7 +253,6 @@ static size_t bwd_layout(BwdScratch *s, void *ws, int N, int E, int H) {
   if (l3 > lin) lin = l3;
   if (l4 > lin) lin = l4;
   s->lin = ar.take<float>(lin > 0 ? lin : 1);
-  s->dys = ar.take<float>(big * 3 * H);
   s->sc = ar.take<float>(4);
   s->p2 = ar.take<float>(sgg_pow2_scale_workspace_bytes() / sizeof(float));
   return ar.off;
@@ -308,13 +307,12 @@ extern "C" int sgg_mp_backward(const float *obj_rep, const float *rel_rep, const
       if (rc) return rc;
     }
   }
-  // scaled copy of a gradient operand: s.sc = (s, 1/s), s.dys = s * dY.  One call serves the dX and the dW GEMM of dY.
+  // power-of-two scale pair of a gradient operand: s.sc = (s, 1/s).  One computation serves the dX and the dW GEMM of dY;
+  // the scale is applied inside the consumers (the LINEAR kernel's fp32 -> fp16 split, the transpose).
   const float *scaled_of = nullptr;
   auto scale16 = [&](const float *dY, int M) -> int {
     if (scaled_of == dY) return 0;
-    const long long n = (long long)M * 3 * H;
-    int r = sgg_pow2_scale(dY, n, s.sc, s.p2, sgg_pow2_scale_workspace_bytes(), st);
-    if (r == 0) r = sgg_scale_by(dY, n, s.sc, s.dys, st);
+    const int r = sgg_pow2_scale(dY, (long long)M * 3 * H, s.sc, s.p2, sgg_pow2_scale_workspace_bytes(), st);
     scaled_of = r == 0 ? dY : nullptr;
     return r;
   };
@@ -324,7 +322,7 @@ extern "C" int sgg_mp_backward(const float *obj_rep, const float *rel_rep, const
     int r;
     if (use16) {
       if ((r = scale16(dY, M))) return r;
-      r = tc16::linear_scaled(s.dys, s.wt[wi], acc ? s.tmp : out, M, H, 3 * H, s.sc + 1, s.lin, st);
+      r = tc16::linear_scaled(dY, s.wt[wi], acc ? s.tmp : out, M, H, 3 * H, s.sc + 1, s.lin, st, s.sc);
     } else {
       r = tc32_linear(dY, s.wt[wi], nullptr, acc ? s.tmp : out, M, H, 3 * H, 0, s.lin, st);
     }
@@ -338,7 +336,7 @@ extern "C" int sgg_mp_backward(const float *obj_rep, const float *rel_rep, const
     int r;
     if (use16) {
       if ((r = scale16(dY, M))) return r;
-      r = sgg_bwd_transpose16(s.dys, 3 * H, M, 3 * H, s.xT, mp, 0, nullptr, st);                     // (s dY)^T  [3H, mp] fp32
+      r = sgg_bwd_transpose16(dY, 3 * H, M, 3 * H, s.xT, mp, 0, s.sc, st);                          // (s dY)^T  [3H, mp] fp32
       if (r == 0) r = sgg_bwd_transpose16(X, H, M, H, s.bT, mp, 1, nullptr, st);                     // X^T planes [H, mp]
       if (r == 0) r = tc16::linear_scaled(s.xT, s.bT, s.tmp, 3 * H, H, mp, s.sc + 1, s.lin, st);
     } else {

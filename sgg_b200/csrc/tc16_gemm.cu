@@ -56,6 +56,7 @@ struct Params {
   const int *subj, *obj;      // GRU_EDGE
   float *cache;               // GRU: nullable [M,4,H] (r, z, n, gh_n) for the backward pass
   const float *out_scale;     // LINEAR: nullable device scalar multiplied into the result before bias / ReLU (backward GEMMs)
+  const float *in_scale;      // LINEAR: nullable device scalar multiplied into the A operand before the fp16 split (power of two: exact)
   __half *out_hi, *out_lo;    // LINEAR: nullable fp16 planes [hi | lo * 2^11] of the final output (consumed via TMA by mp_fused.cu)
   long long *dbg;             // nullable: per-CTA phase timestamps (SGG_TC_TIMING=1, tools/tc16_phases.py)
 };
@@ -252,6 +253,7 @@ k_tc16(Params p, const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     const int c = lane & 7, b = c >> 2;                    // output chunk; source box
     const int ca = 2 * (c & 3);                            // first raw chunk (logical) inside the box
     uint32_t ovf = 0;                                      // fp16 range guard (sticky flag raised after the main loop)
+    const float isc = (CHUNKED && p.in_scale != nullptr) ? __ldg(p.in_scale) : 1.0f;
     auto convert = [&](int it) {
       const int s = it % STAGES, ph = (it / STAGES) & 1;
       mbar_wait(full + s, ph);
@@ -271,10 +273,10 @@ k_tc16(Params p, const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         const int g = APW * wc + (i >> 1), r = (lane >> 3) + 4 * (i & 1);
         const uint4 f0 = b ? v[2 * i + 1] : v[2 * i], f1 = b ? v[2 * i] : v[2 * i + 1];   // floats 0-3, 4-7 of the chunk
         uint4 hi, lo;
-        split2(__uint_as_float(f0.x), __uint_as_float(f0.y), hi.x, lo.x);
-        split2(__uint_as_float(f0.z), __uint_as_float(f0.w), hi.y, lo.y);
-        split2(__uint_as_float(f1.x), __uint_as_float(f1.y), hi.z, lo.z);
-        split2(__uint_as_float(f1.z), __uint_as_float(f1.w), hi.w, lo.w);
+        split2(__uint_as_float(f0.x) * isc, __uint_as_float(f0.y) * isc, hi.x, lo.x);
+        split2(__uint_as_float(f0.z) * isc, __uint_as_float(f0.w) * isc, hi.y, lo.y);
+        split2(__uint_as_float(f1.x) * isc, __uint_as_float(f1.y) * isc, hi.z, lo.z);
+        split2(__uint_as_float(f1.z) * isc, __uint_as_float(f1.w) * isc, hi.w, lo.w);
         ovf |= f16x2_nonfinite(hi.x) | f16x2_nonfinite(hi.y) | f16x2_nonfinite(hi.z) | f16x2_nonfinite(hi.w);
         const uint32_t dst = a_addr + (uint32_t)(g * 1024 + r * 128 + (((c ^ r) & 7) << 4));
         sts128u(dst, hi);
@@ -319,8 +321,8 @@ k_tc16(Params p, const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         const int g = APW * wc + (i >> 1), r = (lane >> 3) + 4 * (i & 1);
         const float4 f0 = pre[2 * i], f1 = pre[2 * i + 1];
         uint4 hi, lo;
-        split2(f0.x, f0.y, hi.x, lo.x); split2(f0.z, f0.w, hi.y, lo.y);
-        split2(f1.x, f1.y, hi.z, lo.z); split2(f1.z, f1.w, hi.w, lo.w);
+        split2(f0.x * isc, f0.y * isc, hi.x, lo.x); split2(f0.z * isc, f0.w * isc, hi.y, lo.y);
+        split2(f1.x * isc, f1.y * isc, hi.z, lo.z); split2(f1.z * isc, f1.w * isc, hi.w, lo.w);
         ovf |= f16x2_nonfinite(hi.x) | f16x2_nonfinite(hi.y) | f16x2_nonfinite(hi.z) | f16x2_nonfinite(hi.w);
         const uint32_t dst = a_addr + (uint32_t)(g * 1024 + r * 128 + (((c ^ r) & 7) << 4));
         sts128u(dst, hi);
@@ -785,14 +787,14 @@ int linear(const float *x, const float *w_split, const float *b, float *y, int M
   return linear_planes(x, w_split, b, y, nullptr, nullptr, M, Nout, K, relu, ws, st);
 }
 int linear_scaled(const float *x, const float *w_split, float *y, int M, int Nout, int K, const float *out_scale, float *ws,
-                  cudaStream_t st) {
-  return linear_planes(x, w_split, nullptr, y, nullptr, nullptr, M, Nout, K, 0, ws, st, out_scale);
+                  cudaStream_t st, const float *in_scale) {
+  return linear_planes(x, w_split, nullptr, y, nullptr, nullptr, M, Nout, K, 0, ws, st, out_scale, in_scale);
 }
 
 // same, and the epilogue (or the split-K / stream-K reducer) also writes the fp16 [hi | lo * 2^11] planes of y
 // (Nout % 4 == 0 required when planes are requested)
 int linear_planes(const float *x, const float *w_split, const float *b, float *y, __half *y_hi, __half *y_lo, int M,
-                  int Nout, int K, int relu, float *ws, cudaStream_t st, const float *out_scale) {
+                  int Nout, int K, int relu, float *ws, cudaStream_t st, const float *out_scale, const float *in_scale) {
   if (M <= 0 || Nout <= 0) return 0;
   if (y_hi != nullptr && (Nout & 3)) return sgg_set_err(SGG_E_BADARG, "tc16 linear: planes need Nout %% 4 == 0");
   if ((K & 7) || !ok16(x) || !ok16(w_split)) return sgg_set_err(SGG_E_BADARG, "tc16 linear: K %% 8 / alignment");
@@ -801,7 +803,7 @@ int linear_planes(const float *x, const float *w_split, const float *b, float *y
   const __half *wh = reinterpret_cast<const __half *>(w_split);
   Seg sg[2] = {{x, wh, wh + (size_t)Nout * K, Nout}, {}};
   Params p{}; p.M = M; p.K = K; p.Nout = Nout; p.relu = relu; p.bias = b; p.dbg = dbg_ptr();
-  p.out_hi = y_hi; p.out_lo = y_lo; p.out_scale = out_scale;
+  p.out_hi = y_hi; p.out_lo = y_lo; p.out_scale = out_scale; p.in_scale = in_scale;
   static const int pf_env = getenv("SGG_TC16_PF") ? atoi(getenv("SGG_TC16_PF")) : 0;
   p.pf = kblocks >= 32 ? pf_env : 0;
   // tried and NOT adopted (opt-in, SGG_TC16_DIRECT=1): 62 -> 65 us on the cfg2 edge-unary GEMM, 166 -> 180 us at M = 9600.

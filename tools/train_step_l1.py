@@ -60,3 +60,21 @@ if rank == 0:
                       'n_gpus': world, 'images_per_s': B * world * steps / dt, 'ms_per_step': dt * 1e3 / steps,
                       'loss_first': ls[0], 'loss_last': ls[-1], 'finite': bool(np.isfinite(ls).all())}))
 if dist is not None: dist.destroy_process_group()
+if os.environ.get('PROFILE') and rank == 0:
+    # GPU-busy fraction of the step: sum of kernel durations (torch profiler, CUPTI) against the wall time of the same steps
+    from torch.profiler import profile, ProfilerActivity
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        t0 = time.perf_counter()
+        for i in range(5):
+            step(i)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+    ev = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+    busy = sum(e.device_time for e in ev) / 5e3
+    print('profile: %.3f ms wall per step (under CUPTI), %.3f ms of kernel time per step, %d kernels per step' % (dt * 1e3 / 5, busy, len(ev) // 5))
+    agg = {}
+    for e in ev:
+        agg.setdefault(e.name[:60], [0, 0.0]); agg[e.name[:60]][0] += 1; agg[e.name[:60]][1] += e.device_time
+    for k, (c, t) in sorted(agg.items(), key=lambda x: -x[1][1])[:14]:
+        print('  %-62s %4d %8.1f us/step' % (k, c // 5, t / 5))
