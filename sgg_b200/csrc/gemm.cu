@@ -341,7 +341,9 @@ __global__ void __launch_bounds__(256) k_absmax_partial(const float *__restrict_
   }
 }
 // sc[0] = s = 2^(10 - floor(log2 amax)), sc[1] = 1 / s; s = 1 when amax == 0
-__global__ void k_pow2_scale(const float *__restrict__ part, int nparts, float *__restrict__ sc) {
+// blockIdx.x selects one of several independent reductions (partials `part_stride` apart, results 4 floats apart)
+__global__ void k_pow2_scale(const float *__restrict__ part, int nparts, float *__restrict__ sc, int part_stride = 0) {
+  part += (size_t)blockIdx.x * part_stride; sc += 4 * blockIdx.x;
   float m = 0.f;
   for (int i = threadIdx.x; i < nparts; i += 32) m = fmaxf(m, part[i]);
 #pragma unroll
@@ -396,6 +398,14 @@ __global__ void k_scale_by(const float4 *__restrict__ x, size_t n4, const float 
 }  // namespace sgg
 
 /* sc[0] = 2^k with max|x| * 2^k in [1024, 2048), sc[1] = 2^-k (device floats; ws: sgg_pow2_scale_workspace_bytes()) */
+namespace sgg {
+// (s, 1/s) from per-block abs-max partials a producer kernel already wrote (mp_bwd.cu: k_gru_bwd)
+int launch_pow2_from_parts(const float *parts, int nparts, float *sc, int count, int part_stride, cudaStream_t st) {
+  k_pow2_scale<<<count, 32, 0, st>>>(parts, nparts, sc, part_stride);
+  SGG_RETURN_IF_LAUNCH_FAILED("k_pow2_scale");
+  return 0;
+}
+}  // namespace sgg
 extern "C" size_t sgg_pow2_scale_workspace_bytes(void) { return sgg::P2_PARTS * sizeof(float); }
 extern "C" int sgg_pow2_scale(const float *x, long long n, float *sc, void *ws, size_t ws_bytes, void *stream) {
   if (!x || !sc || !ws || n <= 0 || ws_bytes < sgg_pow2_scale_workspace_bytes()) return sgg_set_err(SGG_E_BADARG, "pow2_scale: bad argument");

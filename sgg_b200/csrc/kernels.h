@@ -13,6 +13,8 @@ int launch_gemm(const float *A, int lda, bool a_col, const float *B, int ldb, bo
 size_t wsum4_workspace_floats(int rows, int cols);
 int launch_wsum4(const float *W4, const float *X, int rows, int cols, float *out, bool accumulate, float *ws,
                  cudaStream_t st);
+// `count` independent (s, 1/s) pairs (4 floats apart) from abs-max partials `part_stride` floats apart
+int launch_pow2_from_parts(const float *parts, int nparts, float *sc, int count, int part_stride, cudaStream_t st);
 size_t colsum_workspace_floats(int rows, int cols);
 int launch_colsum(const float *X, int ld, int rows, int cols, float *out, bool accumulate, float *ws, cudaStream_t st);
 // 3xTF32 engine (tc_gemm.cu), callable directly: fp32 exponent range, used by the backward GEMMs whatever the

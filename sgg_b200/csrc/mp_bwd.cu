@@ -20,10 +20,14 @@
 namespace sgg {
 
 // dgi [rows,3H], dgh [rows,3H], dh_prev [rows,H] (= dh' * z, overwritten)
+// amax_gi / amax_gh (nullable, [gridDim.x]): per-block max |dgi|, max |dgh| — the abs-max pass of the scaled 3xFP16 GEMMs
+// that consume these tensors, folded into their producer (blockDim.x = 256)
 __global__ void k_gru_bwd(const float *__restrict__ dh_next, const float *__restrict__ cache,
                           const float *__restrict__ h_prev, int rows, int H, float *__restrict__ dgi,
-                          float *__restrict__ dgh, float *__restrict__ dh_prev) {
+                          float *__restrict__ dgh, float *__restrict__ dh_prev, float *__restrict__ amax_gi,
+                          float *__restrict__ amax_gh) {
   const size_t total = (size_t)rows * (H / 4);
+  float mi = 0.f, mh = 0.f;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const size_t m = i / (H / 4);
     const int j = (int)(i % (H / 4)) * 4;
@@ -46,6 +50,9 @@ __global__ void k_gru_bwd(const float *__restrict__ dh_next, const float *__rest
       pr[c] = dr * r[c] * (1.f - r[c]);
       pz[c] = dz * z[c] * (1.f - z[c]);
       dp[c] = d[c] * z[c];
+      const float mrz = fmaxf(fabsf(pr[c]), fabsf(pz[c]));
+      mi = fmaxf(mi, fmaxf(mrz, fabsf(pn[c])));
+      mh = fmaxf(mh, fmaxf(mrz, fabsf(pnr[c])));
     }
     float *gi = dgi + m * 3 * H + j, *gh = dgh + m * 3 * H + j;
     const float4 vr = make_float4(pr[0], pr[1], pr[2], pr[3]), vz = make_float4(pz[0], pz[1], pz[2], pz[3]);
@@ -56,6 +63,21 @@ __global__ void k_gru_bwd(const float *__restrict__ dh_next, const float *__rest
     *reinterpret_cast<float4 *>(gh + H) = vz;
     *reinterpret_cast<float4 *>(gh + 2 * H) = make_float4(pnr[0], pnr[1], pnr[2], pnr[3]);
     if (dh_prev != nullptr) *reinterpret_cast<float4 *>(dh_prev + m * H + j) = make_float4(dp[0], dp[1], dp[2], dp[3]);
+  }
+  if (amax_gi != nullptr) {
+    __shared__ float smi[8], smh[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mi = fmaxf(mi, __shfl_xor_sync(0xffffffffu, mi, o));
+      mh = fmaxf(mh, __shfl_xor_sync(0xffffffffu, mh, o));
+    }
+    if ((threadIdx.x & 31) == 0) { smi[threadIdx.x >> 5] = mi; smh[threadIdx.x >> 5] = mh; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float a = smi[0], b = smh[0];
+      for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { a = fmaxf(a, smi[w]); b = fmaxf(b, smh[w]); }
+      amax_gi[blockIdx.x] = a; amax_gh[blockIdx.x] = b;
+    }
   }
 }
 
@@ -224,6 +246,8 @@ struct BwdScratch {
   float *wt[4], *xT, *bT, *tmp, *lin;
   // scaled 3xFP16 engine (default): exact power-of-two scale pair (s, 1/s) from the device-side abs-max, abs-max partials
   float *sc, *p2;
+  float *amax;            // [2][4096] per-block abs-max partials of k_gru_bwd (dgi, dgh)
+  float *sc_gi, *sc_gh;   // (s, 1/s) of the current dgi / dgh
 };
 constexpr int SPLITK_MAX = 4;      // split-K slices of the [3H,H] weight-gradient GEMMs (reduction over E or N rows)
 static size_t bwd_layout(BwdScratch *s, void *ws, int N, int E, int H) {
@@ -254,6 +278,8 @@ static size_t bwd_layout(BwdScratch *s, void *ws, int N, int E, int H) {
   if (l4 > lin) lin = l4;
   s->lin = ar.take<float>(lin > 0 ? lin : 1);
   s->sc = ar.take<float>(4);
+  s->amax = ar.take<float>(2 * 4096);
+  s->sc_gi = ar.take<float>(8); s->sc_gh = s->sc_gi + 4;
   s->p2 = ar.take<float>(sgg_pow2_scale_workspace_bytes() / sizeof(float));
   return ar.off;
 }
@@ -317,12 +343,13 @@ extern "C" int sgg_mp_backward(const float *obj_rep, const float *rel_rep, const
     return r;
   };
   // dX[M,H] (=|+=) dY[M,3H] W[3H,H]
-  auto gemm_dx = [&](const float *dY, int wi, const float *W, float *out, int M, bool acc) -> int {
+  // `scp`: the (s, 1/s) pair of dY when its producer already reduced the abs-max (k_gru_bwd), else computed here
+  auto gemm_dx = [&](const float *dY, int wi, const float *W, float *out, int M, bool acc, const float *scp) -> int {
     if (!tc_on || M < TC_BWD_MIN_ROWS) return gemm(dY, 3 * H, false, W, H, true, out, H, M, H, 3 * H, acc);
     int r;
     if (use16) {
-      if ((r = scale16(dY, M))) return r;
-      r = tc16::linear_scaled(dY, s.wt[wi], acc ? s.tmp : out, M, H, 3 * H, s.sc + 1, s.lin, st, s.sc);
+      if (scp == nullptr) { if ((r = scale16(dY, M))) return r; scp = s.sc; }
+      r = tc16::linear_scaled(dY, s.wt[wi], acc ? s.tmp : out, M, H, 3 * H, scp + 1, s.lin, st, scp);
     } else {
       r = tc32_linear(dY, s.wt[wi], nullptr, acc ? s.tmp : out, M, H, 3 * H, 0, s.lin, st);
     }
@@ -330,15 +357,15 @@ extern "C" int sgg_mp_backward(const float *obj_rep, const float *rel_rep, const
     return r;
   };
   // dW[3H,H] += dY[M,3H]^T X[M,H]
-  auto gemm_dw = [&](const float *dY, const float *X, float *dW, int M) -> int {
+  auto gemm_dw = [&](const float *dY, const float *X, float *dW, int M, const float *scp) -> int {
     if (!tc_on || M < TC_BWD_MIN_K) return gemm(dY, 3 * H, true, X, H, true, dW, H, 3 * H, H, M, true);
     const int mp = pad32(M);
     int r;
     if (use16) {
-      if ((r = scale16(dY, M))) return r;
-      r = sgg_bwd_transpose16(dY, 3 * H, M, 3 * H, s.xT, mp, 0, s.sc, st);                          // (s dY)^T  [3H, mp] fp32
+      if (scp == nullptr) { if ((r = scale16(dY, M))) return r; scp = s.sc; }
+      r = sgg_bwd_transpose16(dY, 3 * H, M, 3 * H, s.xT, mp, 0, scp, st);                           // (s dY)^T  [3H, mp] fp32
       if (r == 0) r = sgg_bwd_transpose16(X, H, M, H, s.bT, mp, 1, nullptr, st);                     // X^T planes [H, mp]
-      if (r == 0) r = tc16::linear_scaled(s.xT, s.bT, s.tmp, 3 * H, H, mp, s.sc + 1, s.lin, st);
+      if (r == 0) r = tc16::linear_scaled(s.xT, s.bT, s.tmp, 3 * H, H, mp, scp + 1, s.lin, st);
     } else {
       r = launch_transpose(dY, M, 3 * H, s.xT, mp, false, st);
       if (r == 0) r = launch_transpose(X, M, H, s.bT, mp, true, st);
@@ -351,29 +378,39 @@ extern "C" int sgg_mp_backward(const float *obj_rep, const float *rel_rep, const
     return out ? launch_colsum(X, cols, rows, cols, out, true, s.cs, st) : 0;
   };
 
+  // GRUCell backward of `rows` rows; with the 3xFP16 engine it also leaves the scale pairs of dgi / dgh in s.sc_gi / s.sc_gh
+  auto gru_bwd = [&](const float *dh_next, const float *cache, const float *h_prev, int rows, float *dgi, float *dgh,
+                     float *dh_prev) -> int {
+    const int blocks = ew_blocks((size_t)rows * H / 4);
+    const bool fuse = use16 && rows >= TC_BWD_MIN_ROWS;
+    k_gru_bwd<<<blocks, 256, 0, st>>>(dh_next, cache, h_prev, rows, H, dgi, dgh, dh_prev, fuse ? s.amax : nullptr,
+                                      fuse ? s.amax + 4096 : nullptr);
+    SGG_RETURN_IF_LAUNCH_FAILED("k_gru_bwd");
+    scaled_of = nullptr;                  // the gradient buffers were just rewritten
+    return fuse ? launch_pow2_from_parts(s.amax, blocks, s.sc_gi, 2, 4096, st) : 0;
+  };
+  auto sc_of = [&](int rows, const float *scp) -> const float * { return (use16 && rows >= TC_BWD_MIN_ROWS) ? scp : nullptr; };
+
   const float *dVn = dV_T, *dEn = dE_T;   // grads w.r.t. V_{t+1}, E_{t+1}
   for (int t = T - 1; t >= 0; --t) {
     float *dV = s.dV[t & 1], *dE = s.dE[t & 1];
     const float *V = Vt(t), *Eh = Et(t);
     const float *gt = tp.gates + (size_t)t * E * 4, *ctx = tp.ctx + (size_t)t * N * H, *P = tp.P + (size_t)t * N * 3 * H;
     if (N > 0) {
-      k_gru_bwd<<<ew_blocks(vN / 4), 256, 0, st>>>(dVn, tp.cacheV + (size_t)(t + 1) * N * 4 * H, V, N, H, s.dgi_n, s.dgh_n, dV);
-      SGG_RETURN_IF_LAUNCH_FAILED("k_gru_bwd");
-      scaled_of = nullptr;                  // the gradient buffers were just rewritten
-      // the dW and the dX GEMM of one gradient operand back to back: they share its scaled copy
-      if (grads->node_w_ih && (rc = gemm_dw(s.dgi_n, ctx, grads->node_w_ih, N))) return rc;
-      if ((rc = gemm_dx(s.dgi_n, WT_NODE_IH, w->node_w_ih, s.dctx, N, false))) return rc;
-      if (grads->node_w_hh && (rc = gemm_dw(s.dgh_n, V, grads->node_w_hh, N))) return rc;
-      if ((rc = gemm_dx(s.dgh_n, WT_NODE_HH, w->node_w_hh, dV, N, true))) return rc;
+      if ((rc = gru_bwd(dVn, tp.cacheV + (size_t)(t + 1) * N * 4 * H, V, N, s.dgi_n, s.dgh_n, dV))) return rc;
+      const float *sgi = sc_of(N, s.sc_gi), *sgh = sc_of(N, s.sc_gh);
+      if (grads->node_w_ih && (rc = gemm_dw(s.dgi_n, ctx, grads->node_w_ih, N, sgi))) return rc;
+      if ((rc = gemm_dx(s.dgi_n, WT_NODE_IH, w->node_w_ih, s.dctx, N, false, sgi))) return rc;
+      if (grads->node_w_hh && (rc = gemm_dw(s.dgh_n, V, grads->node_w_hh, N, sgh))) return rc;
+      if ((rc = gemm_dx(s.dgh_n, WT_NODE_HH, w->node_w_hh, dV, N, true, sgh))) return rc;
       if ((rc = colsum(s.dgi_n, N, 3 * H, grads->node_b_ih))) return rc;
       if ((rc = colsum(s.dgh_n, N, 3 * H, grads->node_b_hh))) return rc;
     }
     if (E > 0) {
-      k_gru_bwd<<<ew_blocks(eN / 4), 256, 0, st>>>(dEn, tp.cacheE + (size_t)(t + 1) * E * 4 * H, Eh, E, H, s.dgi_e, s.dgh_e, dE);
-      SGG_RETURN_IF_LAUNCH_FAILED("k_gru_bwd");
-      scaled_of = nullptr;
-      if (grads->edge_w_hh && (rc = gemm_dw(s.dgh_e, Eh, grads->edge_w_hh, E))) return rc;
-      if ((rc = gemm_dx(s.dgh_e, WT_EDGE_HH, w->edge_w_hh, dE, E, true))) return rc;
+      if ((rc = gru_bwd(dEn, tp.cacheE + (size_t)(t + 1) * E * 4 * H, Eh, E, s.dgi_e, s.dgh_e, dE))) return rc;
+      const float *sgh = sc_of(E, s.sc_gh);
+      if (grads->edge_w_hh && (rc = gemm_dw(s.dgh_e, Eh, grads->edge_w_hh, E, sgh))) return rc;
+      if ((rc = gemm_dx(s.dgh_e, WT_EDGE_HH, w->edge_w_hh, dE, E, true, sgh))) return rc;
       if ((rc = colsum(s.dgh_e, E, 3 * H, grads->edge_b_hh))) return rc;
       if ((rc = colsum(s.dgi_e, E, 3 * H, grads->edge_b_ih))) return rc;
       k_edge_bwd<<<(int)(((size_t)E * 32 + 255) / 256), 256, 0, st>>>(s.dgi_e, P, s.dctx, Eh, gt, g.subj, g.obj, E, H,
@@ -390,8 +427,8 @@ extern "C" int sgg_mp_backward(const float *obj_rep, const float *rel_rep, const
                                       w->gate_w[1], w->gate_w[2], w->gate_w[3], s.dP, s.da, dV);
         SGG_RETURN_IF_LAUNCH_FAILED("k_node_bwd");
         scaled_of = nullptr;
-        if (grads->edge_w_ih && (rc = gemm_dw(s.dP, V, grads->edge_w_ih, N))) return rc;
-        if ((rc = gemm_dx(s.dP, WT_EDGE_IH, w->edge_w_ih, dV, N, true))) return rc;
+        if (grads->edge_w_ih && (rc = gemm_dw(s.dP, V, grads->edge_w_ih, N, nullptr))) return rc;
+        if ((rc = gemm_dx(s.dP, WT_EDGE_IH, w->edge_w_ih, dV, N, true, nullptr))) return rc;
         if ((rc = launch_wsum4(s.da, V, N, H, s.tV, true, s.ws4, st))) return rc;      // tV[k] += sum_n da[n][k] V[n]
         if ((rc = launch_wsum4(s.dl, Eh, E, H, s.tE, true, s.ws4, st))) return rc;     // tE[k] += sum_e dl[e][k] E[e]
         if ((rc = launch_colsum(s.dl, 4, E, 4, s.gb, true, s.cs, st))) return rc;
@@ -401,20 +438,18 @@ extern "C" int sgg_mp_backward(const float *obj_rep, const float *rel_rep, const
   }
   // initial step (h = 0): rel_model_stanford.py:68-72
   if (N > 0) {
-    k_gru_bwd<<<ew_blocks(vN / 4), 256, 0, st>>>(dVn, tp.cacheV, nullptr, N, H, s.dgi_n, s.dgh_n, nullptr);
-    SGG_RETURN_IF_LAUNCH_FAILED("k_gru_bwd");
-    scaled_of = nullptr;
-    if (grads->node_w_ih && (rc = gemm_dw(s.dgi_n, obj_rep, grads->node_w_ih, N))) return rc;
-    if (d_obj_rep && (rc = gemm_dx(s.dgi_n, WT_NODE_IH, w->node_w_ih, d_obj_rep, N, false))) return rc;
+    if ((rc = gru_bwd(dVn, tp.cacheV, nullptr, N, s.dgi_n, s.dgh_n, nullptr))) return rc;
+    const float *sgi = sc_of(N, s.sc_gi);
+    if (grads->node_w_ih && (rc = gemm_dw(s.dgi_n, obj_rep, grads->node_w_ih, N, sgi))) return rc;
+    if (d_obj_rep && (rc = gemm_dx(s.dgi_n, WT_NODE_IH, w->node_w_ih, d_obj_rep, N, false, sgi))) return rc;
     if ((rc = colsum(s.dgi_n, N, 3 * H, grads->node_b_ih))) return rc;
     if ((rc = colsum(s.dgh_n, N, 3 * H, grads->node_b_hh))) return rc;
   }
   if (E > 0) {
-    k_gru_bwd<<<ew_blocks(eN / 4), 256, 0, st>>>(dEn, tp.cacheE, nullptr, E, H, s.dgi_e, s.dgh_e, nullptr);
-    SGG_RETURN_IF_LAUNCH_FAILED("k_gru_bwd");
-    scaled_of = nullptr;
-    if (grads->edge_w_ih && (rc = gemm_dw(s.dgi_e, rel_rep, grads->edge_w_ih, E))) return rc;
-    if (d_rel_rep && (rc = gemm_dx(s.dgi_e, WT_EDGE_IH, w->edge_w_ih, d_rel_rep, E, false))) return rc;
+    if ((rc = gru_bwd(dEn, tp.cacheE, nullptr, E, s.dgi_e, s.dgh_e, nullptr))) return rc;
+    const float *sgi = sc_of(E, s.sc_gi);
+    if (grads->edge_w_ih && (rc = gemm_dw(s.dgi_e, rel_rep, grads->edge_w_ih, E, sgi))) return rc;
+    if (d_rel_rep && (rc = gemm_dx(s.dgi_e, WT_EDGE_IH, w->edge_w_ih, d_rel_rep, E, false, sgi))) return rc;
     if ((rc = colsum(s.dgi_e, E, 3 * H, grads->edge_b_ih))) return rc;
     if ((rc = colsum(s.dgh_e, E, 3 * H, grads->edge_b_hh))) return rc;
   }
