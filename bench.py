@@ -266,17 +266,23 @@ def measure_other_configs(args, dev, dparams):
 
         def step():
             geom = ops.union_geom(rois, rel[:, 1:3], P)
-            nf, ef2 = ops.node_edge_features(fmap, rois, rel[:, 1:3], edge_add=geom)
-            h = ops.linear(ef2.view(E, -1), P['roi_fmap.1.0.weight'], P['roi_fmap.1.0.bias'], relu=True)
-            e4096 = ops.linear(h, P['roi_fmap.1.3.weight'], P['roi_fmap.1.3.bias'])
-            hn = ops.linear(nf.view(N, -1), P['roi_fmap_obj.0.weight'], P['roi_fmap_obj.0.bias'], relu=True)
-            n4096 = ops.linear(hn, P['roi_fmap_obj.3.weight'], P['roi_fmap_obj.3.bias'], relu=True)
+            # RoIAlign emits the fp16 operand planes of its rows, fc6 those of its output: both fc layers of both heads
+            # run on pre-split operands (csrc/lin16p.cu), exactly what RelModelStanford.forward does in eval mode
+            _, _, npl, epl = ops.node_edge_features(fmap, rois, rel[:, 1:3], edge_add=geom, planes='only')
+            h, hpl = ops.linear(None, P['roi_fmap.1.0.weight'], P['roi_fmap.1.0.bias'], relu=True, x_planes=epl, out_planes=True)
+            e4096 = ops.linear(h, P['roi_fmap.1.3.weight'], P['roi_fmap.1.3.bias'], x_planes=hpl)
+            hn, hnpl = ops.linear(None, P['roi_fmap_obj.0.weight'], P['roi_fmap_obj.0.bias'], relu=True, x_planes=npl,
+                                  out_planes=True)
+            n4096 = ops.linear(hn, P['roi_fmap_obj.3.weight'], P['roi_fmap_obj.3.bias'], relu=True, x_planes=hnpl)
             return ops.l1_forward(n4096, e4096, gr, P, 3)
         step()
         ms = timeit(step, 5)
-        nf, ef2 = ops.node_edge_features(fmap, rois, rel[:, 1:3])
-        st['fc6_edge_ms'] = timeit(lambda: ops.linear(ef2.view(E, -1), P['roi_fmap.1.0.weight'], P['roi_fmap.1.0.bias'], relu=True), 3)
-        st['roi_align_ms'] = timeit(lambda: ops.node_edge_features(fmap, rois, rel[:, 1:3]), 3)
+        nf, ef2, npl, epl = ops.node_edge_features(fmap, rois, rel[:, 1:3], planes=True)
+        st['fc6_edge_ms'] = timeit(lambda: ops.linear(ef2.view(E, -1), P['roi_fmap.1.0.weight'], P['roi_fmap.1.0.bias'], relu=True,
+                                                      x_planes=epl), 3)
+        st['fc6_edge_fp32_input_ms'] = timeit(lambda: ops.linear(ef2.view(E, -1), P['roi_fmap.1.0.weight'],
+                                                                 P['roi_fmap.1.0.bias'], relu=True), 3)
+        st['roi_align_ms'] = timeit(lambda: ops.node_edge_features(fmap, rois, rel[:, 1:3], planes='only'), 3)
         out['cfg3_feature_head'] = {'workload': 'B=32 x 30 boxes x 300 edges: RoIAlign (objects + union boxes) + geometry + '
                                                 'fc6/fc7 (both heads) + L1, fmap [32,512,38,38] resident (N=%d, E=%d)' % (N, E),
                                     'ms_per_step': ms, 'images_per_s': B / (ms * 1e-3), 'stage_ms': st,

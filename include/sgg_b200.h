@@ -161,6 +161,12 @@ SGG_API int sgg_scale_by(const float *x, long long n, const float *sc, float *y,
 SGG_API size_t sgg_tc16_linear_workspace_bytes(int M, int Nout, int K);
 SGG_API int sgg_tc16_linear_scaled(const float *x, const void *w_split16, float *y, int M, int Nout, int K,
                            const float *out_scale, void *ws, size_t ws_bytes, void *stream);
+/* nn.Linear forward on tcgen05 with BOTH operands pre-split (lin16p.cu): x_planes = fp16 [hi | lo * 2^11] planes of
+ * x [M,K] (2 * M * K halves, written by sgg_node_edge_features_planes or as y_planes of a previous call), w_split16 =
+ * planes of w [Nout,K] (sgg_tc_split_weights, 3xFP16 layout).  y [M,Nout] fp32; y_planes nullable (2 * M * Nout halves).
+ * K % 8 == 0, Nout % 4 == 0.  Replaces F.linear of rel_model_stanford.py:100-101 on RoIAlign rows. */
+SGG_API int sgg_tc16_linear_pre(const void *x_planes, const void *w_split16, const float *bias, float *y, void *y_planes,
+                                int M, int Nout, int K, int relu, void *stream);
 
 /* ---- tensor-core (tcgen05 / TMEM / TMA) variants -----------------------------------------
  * fp32 in, fp32 out, fp32-grade accuracy through a 3-pass operand split.  Two engines:
@@ -304,6 +310,17 @@ SGG_API int sgg_node_edge_features_add(const float *fmap, int B, int C, int Hf, 
                                const int64_t *union_inds, int64_t row_stride, int col_subj, int col_obj, int E,
                                float spatial_scale, int pool, int sampling_ratio, const float *edge_add,
                                float *node_feat, float *edge_feat, void *ws, size_t ws_bytes, void *stream);
+/* Same, and the fp16 [hi | lo * 2^11] operand planes of the rows for sgg_tc16_linear_pre (the fc6 layers of
+ * rel_model_stanford.py:100-101 / rel_model_base.py:166-170 then skip their in-kernel fp32 -> fp16 conversion):
+ * node_planes 2 * N * C * pool^2 halves, edge_planes 2 * E * C * pool^2 halves, each nullable; with planes given the
+ * fp32 rows of that side (node_feat / edge_feat) may be NULL and are then not written.  Planes need the
+ * channel-last fast path: workspace given, sampling_ratio = 2, C % 4 == 0 (SGG_E_BADARG otherwise). */
+SGG_API int sgg_node_edge_features_planes(const float *fmap, int B, int C, int Hf, int Wf,
+                               const float *rois, int N,
+                               const int64_t *union_inds, int64_t row_stride, int col_subj, int col_obj, int E,
+                               float spatial_scale, int pool, int sampling_ratio, const float *edge_add,
+                               float *node_feat, float *edge_feat, void *node_planes, void *edge_planes,
+                               void *ws, size_t ws_bytes, void *stream);
 
 /* ==== evaluation tail: lib/surgery.py:17-55 filter_dets ========================================
  * score[e] = max_{p>=1} prob[e,p] * obj_scores[subj] * obj_scores[obj]; edges are ordered by descending score (ties by

@@ -92,6 +92,8 @@ SIGNATURES = {
     'sgg_tc16_linear_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     'sgg_tc16_linear_scaled': (C.c_int, [c_f, C.c_void_p, c_f, C.c_int, C.c_int, C.c_int, c_f, C.c_void_p, C.c_size_t,
                                          C.c_void_p]),
+    'sgg_tc16_linear_pre': (C.c_int, [C.c_void_p, C.c_void_p, c_f, c_f, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                      C.c_void_p]),
     'sgg_tc16_overflow': (C.c_int, [C.c_int]),
     'sgg_bn_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int]),
     'sgg_bn_train_forward': (C.c_int, [c_f, C.c_int, C.c_int, C.c_int, c_f, c_f, c_f, c_f, C.c_float, C.c_float, c_f, c_f,
@@ -129,6 +131,9 @@ SIGNATURES = {
     'sgg_node_edge_features_add': (C.c_int, [c_f, C.c_int, C.c_int, C.c_int, C.c_int, c_f, C.c_int, c_i64p, C.c_int64,
                                              C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, c_f, c_f, c_f,
                                              C.c_void_p, C.c_size_t, C.c_void_p]),
+    'sgg_node_edge_features_planes': (C.c_int, [c_f, C.c_int, C.c_int, C.c_int, C.c_int, c_f, C.c_int, c_i64p, C.c_int64,
+                                                C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, c_f, c_f, c_f,
+                                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     'sgg_rank_relations_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int]),
     'sgg_rank_relations': (C.c_int, [c_f, C.c_int, c_f, c_i64p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                      C.c_int, c_i64p, c_f, c_f, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),

@@ -35,12 +35,19 @@ class _LinearFn(torch.autograd.Function):
         return dx, dw, db, None
 
 
-def linear(x, weight, bias=None, relu=False):
-    """nn.Linear (+ReLU) with CUDA forward/backward.  Inference (no grad) skips the autograd graph."""
+def linear(x, weight, bias=None, relu=False, x_planes=None, out_planes=False):
+    """nn.Linear (+ReLU) with CUDA forward/backward.  Inference (no grad) skips the autograd graph; there ``x_planes`` /
+    ``out_planes`` (ops.linear) route the GEMM to the pre-split tcgen05 kernel.  With gradients the planes are ignored
+    (``out_planes`` then returns ``(y, None)``)."""
+    if x is None:                  # planes-only activations (eval): there is nothing to differentiate through
+        if torch.is_grad_enabled() and (weight.requires_grad or (bias is not None and bias.requires_grad)):
+            raise NotImplementedError('linear: planes-only input inside an autograd region')
+        return ops.linear(None, weight, bias, relu=relu, x_planes=x_planes, out_planes=out_planes)
     x = x.contiguous()
     if torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad or (bias is not None and bias.requires_grad)):
-        return _LinearFn.apply(x, weight, bias, relu)
-    return ops.linear(x, weight, bias, relu=relu)
+        y = _LinearFn.apply(x, weight, bias, relu)
+        return (y, None) if out_planes else y
+    return ops.linear(x, weight, bias, relu=relu, x_planes=x_planes, out_planes=out_planes)
 
 
 class _MessagePassFn(torch.autograd.Function):
@@ -75,14 +82,14 @@ def message_pass(rel_rep, obj_rep, rel_inds, params, mp_iter=3):
     return ops.message_pass(rel_rep, obj_rep, graph, params, mp_iter)
 
 
-def node_edge_features(fmap, rois, union_inds, spatial_scale, pool=7, sampling_ratio=2, edge_add=None):
+def node_edge_features(fmap, rois, union_inds, spatial_scale, pool=7, sampling_ratio=2, edge_add=None, planes=False):
     """RoIAlign of objects and union boxes.  ``fmap`` is produced under no_grad and detached by the caller
     (rel_model_stanford.py:125-131), so no backward is defined; a differentiable fmap (GAN ``-attachG``
     path, out of scope) is rejected loudly rather than silently dropping its gradient."""
     if torch.is_grad_enabled() and fmap.requires_grad:
         raise NotImplementedError('node_edge_features: gradient w.r.t. fmap (GAN -attachG path) is not implemented')
     return ops.node_edge_features(fmap.detach(), rois.detach(), union_inds, spatial_scale, pool, sampling_ratio,
-                                  edge_add=edge_add)
+                                  edge_add=edge_add, planes=planes)
 
 
 def _conv_params(conv):

@@ -6,8 +6,10 @@
 // tensor and the per-image roi lists of convert_roi_to_list (:303-307, a host sync)
 // never exist.
 #include "common.cuh"
+#include "tc16_common.cuh"
 
 namespace sgg {
+__device__ unsigned int g_roi_overflow = 0;   // sticky: an emitted operand plane left the fp16 range (sgg_tc16_overflow, bit 0)
 
 // Indices come from the caller (rel_inds / im_inds): clamp them so a bad value can never become an out-of-bounds read
 // (graph.cu flags the same situation for the message-passing graph; here the result for such a row is simply that of
@@ -181,7 +183,7 @@ __global__ void __launch_bounds__(256)
 k_roi_align_nhwc4(const float *__restrict__ fmap /*[B,Hf,Wf,C]*/, int B, int C, int Hf, int Wf, const float *__restrict__ rois,
                   int N, const int64_t *__restrict__ ui, int64_t stride, int cs, int co, int E, float scale, int pool,
                   float *__restrict__ node_out, float *__restrict__ edge_out, int r_begin,
-                  const float *__restrict__ edge_add) {
+                  const float *__restrict__ edge_add, __half *__restrict__ node_planes, __half *__restrict__ edge_planes) {
   extern __shared__ __align__(16) float s_out[];          // [C][pool*pool]
   __shared__ int s_lo[2][RA_MAXS], s_hi[2][RA_MAXS];
   __shared__ float s_l[2][RA_MAXS], s_h[2][RA_MAXS];
@@ -189,16 +191,19 @@ k_roi_align_nhwc4(const float *__restrict__ fmap /*[B,Hf,Wf,C]*/, int B, int C, 
   const int pp = pool * pool, ns = pool * SR;
   float x1, y1, x2, y2; int b;
   float *dst;
+  __half *pl_hi = nullptr, *pl_lo = nullptr;             // fp16 [hi | lo * 2^11] planes of the same row (nullable)
   if (r < N) {
     const float *q = rois + (size_t)r * 5;
     b = clamp_idx((long long)q[0], B); x1 = q[1]; y1 = q[2]; x2 = q[3]; y2 = q[4];
-    dst = node_out + (size_t)r * C * pp;
+    dst = node_out != nullptr ? node_out + (size_t)r * C * pp : nullptr;       // fp32 rows are optional when planes are emitted
+    if (node_planes != nullptr) { pl_hi = node_planes + (size_t)r * C * pp; pl_lo = pl_hi + (size_t)N * C * pp; }
   } else {
     const size_t e = (size_t)(r - N);
     const float *qs = rois + (size_t)clamp_idx(ui[e * stride + cs], N) * 5, *qo = rois + (size_t)clamp_idx(ui[e * stride + co], N) * 5;
     b = clamp_idx((long long)qs[0], B);
     x1 = fminf(qs[1], qo[1]); y1 = fminf(qs[2], qo[2]); x2 = fmaxf(qs[3], qo[3]); y2 = fmaxf(qs[4], qo[4]);
-    dst = edge_out + e * C * pp;
+    dst = edge_out != nullptr ? edge_out + e * C * pp : nullptr;
+    if (edge_planes != nullptr) { pl_hi = edge_planes + e * C * pp; pl_lo = pl_hi + (size_t)E * C * pp; }
   }
   if (threadIdx.x < 2 * ns) {
     const int axis = threadIdx.x / ns, i = threadIdx.x % ns;     // axis 0 = y, 1 = x
@@ -256,12 +261,38 @@ k_roi_align_nhwc4(const float *__restrict__ fmap /*[B,Hf,Wf,C]*/, int B, int C, 
   }
   __syncthreads();
   const int total = C * pp;
-  if ((total & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+  if (dst == nullptr) {
+    // planes only
+  } else if ((total & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
     const float4 *s4 = reinterpret_cast<const float4 *>(s_out);
     float4 *d4 = reinterpret_cast<float4 *>(dst);
     for (int i = threadIdx.x; i < total / 4; i += blockDim.x) __stcs(d4 + i, s4[i]);
   } else {
     for (int i = threadIdx.x; i < total; i += blockDim.x) dst[i] = s_out[i];
+  }
+  if (pl_hi != nullptr) {
+    // the operand planes of the fc layer that consumes this row (lin16p.cu): x = hi + 2^-11 lo
+    unsigned int ovf = 0;
+    if ((total & 3) == 0 && (reinterpret_cast<uintptr_t>(pl_hi) & 7) == 0 && (reinterpret_cast<uintptr_t>(pl_lo) & 7) == 0) {
+      const float4 *s4 = reinterpret_cast<const float4 *>(s_out);
+      for (int i = threadIdx.x; i < total / 4; i += blockDim.x) {
+        const float4 v = s4[i];
+        uint2 hi, lo;
+        tc16::split2(v.x, v.y, hi.x, lo.x); tc16::split2(v.z, v.w, hi.y, lo.y);
+        ovf |= tc16::f16x2_nonfinite(hi.x) | tc16::f16x2_nonfinite(hi.y);
+        *reinterpret_cast<uint2 *>(pl_hi + 4 * (size_t)i) = hi;
+        *reinterpret_cast<uint2 *>(pl_lo + 4 * (size_t)i) = lo;
+      }
+    } else {
+      for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        const float v = s_out[i];
+        const __half h = __float2half_rn(v);
+        pl_hi[i] = h;
+        pl_lo[i] = __float2half_rn((v - __half2float(h)) * tc16::LO_SCALE);
+        ovf |= (unsigned int)(__hisinf(h) || __hisnan(h));
+      }
+    }
+    if (ovf) atomicOr(&g_roi_overflow, 1u);
   }
 }
 
@@ -285,9 +316,25 @@ extern "C" int sgg_node_edge_features_add(const float *fmap, int B, int C, int H
                                           int E, float spatial_scale, int pool, int sampling_ratio,
                                           const float *edge_add, float *node_feat, float *edge_feat, void *ws,
                                           size_t ws_bytes, void *stream) {
+  return sgg_node_edge_features_planes(fmap, B, C, Hf, Wf, rois, N, union_inds, row_stride, col_subj, col_obj, E,
+                                       spatial_scale, pool, sampling_ratio, edge_add, node_feat, edge_feat, nullptr,
+                                       nullptr, ws, ws_bytes, stream);
+}
+
+/* Same, and the fp16 [hi | lo * 2^11] operand planes of the rows (node_planes: 2 * N * C * pool^2 halves, edge_planes:
+ * 2 * E * C * pool^2 halves; each nullable) for sgg_tc16_linear_pre.  Planes need the channel-last fast path
+ * (workspace given, sampling_ratio = 2, C % 4 == 0). */
+extern "C" int sgg_node_edge_features_planes(const float *fmap, int B, int C, int Hf, int Wf, const float *rois, int N,
+                                             const int64_t *union_inds, int64_t row_stride, int col_subj, int col_obj,
+                                             int E, float spatial_scale, int pool, int sampling_ratio,
+                                             const float *edge_add, float *node_feat, float *edge_feat,
+                                             void *node_planes, void *edge_planes, void *ws, size_t ws_bytes,
+                                             void *stream) {
   if (B <= 0 || C <= 0 || Hf <= 0 || Wf <= 0 || N < 0 || E < 0 || pool <= 0 || sampling_ratio <= 0)
     return sgg_set_err(SGG_E_BADARG, "node_edge_features: bad shape");
-  const int do_node = node_feat != nullptr && N > 0, do_edge = edge_feat != nullptr && E > 0;
+  // a side is produced when its fp32 rows or its planes are requested (planes alone: the fp32 rows are not written)
+  const int do_node = (node_feat != nullptr || node_planes != nullptr) && N > 0;
+  const int do_edge = (edge_feat != nullptr || edge_planes != nullptr) && E > 0;
   if (!do_node && !do_edge) return 0;
   if (!fmap || !rois || (do_edge && !union_inds)) return sgg_set_err(SGG_E_BADARG, "node_edge_features: null pointer");
   const size_t smem_need = (size_t)C * pool * pool * sizeof(float);
@@ -313,16 +360,19 @@ extern "C" int sgg_node_edge_features_add(const float *fmap, int B, int C, int H
         attr4 = true;
       }
       sgg::k_roi_align_nhwc4<2><<<r1 - r0, 256, smem_need, st>>>(nhwc, B, C, Hf, Wf, rois, N, union_inds, row_stride, col_subj,
-                                                              col_obj, E, spatial_scale, pool, node_feat, edge_feat, r0, edge_add);
+                                                              col_obj, E, spatial_scale, pool, node_feat, edge_feat, r0, edge_add,
+                                                              (__half *)node_planes, (__half *)edge_planes);
       SGG_RETURN_IF_LAUNCH_FAILED("k_roi_align_nhwc4");
       return 0;
     }
+    if (node_planes || edge_planes) return sgg_set_err(SGG_E_BADARG, "node_edge_features: planes need sampling_ratio 2 and C %% 4 == 0");
     sgg::k_roi_align_nhwc<<<r1 - r0, 256, smem_need, st>>>(nhwc, B, C, Hf, Wf, rois, N, union_inds, row_stride, col_subj,
                                                           col_obj, E, spatial_scale, pool, sampling_ratio, node_feat,
                                                           edge_feat, r0, edge_add);
     SGG_RETURN_IF_LAUNCH_FAILED("k_roi_align_nhwc");
     return 0;
   }
+  if (node_planes || edge_planes) return sgg_set_err(SGG_E_BADARG, "node_edge_features: planes need the channel-last path (workspace)");
   const size_t total = ((size_t)(do_node ? N : 0) + (do_edge ? E : 0)) * C * pool * pool;
   int blocks = (int)((total + 255) / 256 < (size_t)sgg_num_sms() * 32 ? (total + 255) / 256 : (size_t)sgg_num_sms() * 32);
   sgg::k_roi_align<<<blocks, 256, 0, (cudaStream_t)stream>>>(fmap, B, C, Hf, Wf, rois, N, union_inds, row_stride,
@@ -331,3 +381,17 @@ extern "C" int sgg_node_edge_features_add(const float *fmap, int B, int C, int H
   SGG_RETURN_IF_LAUNCH_FAILED("k_roi_align");
   return 0;
 }
+
+namespace sgg {
+int roi_overflow_flag(int reset, unsigned int *out) {
+  unsigned int v = 0;
+  if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+  if (cudaMemcpyFromSymbol(&v, g_roi_overflow, sizeof(v)) != cudaSuccess) return -1;
+  if (reset) {
+    const unsigned int z = 0;
+    if (cudaMemcpyToSymbol(g_roi_overflow, &z, sizeof(z)) != cudaSuccess) return -1;
+  }
+  *out = v;
+  return 0;
+}
+}  // namespace sgg

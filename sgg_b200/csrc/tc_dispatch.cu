@@ -101,10 +101,13 @@ extern "C" int sgg_mpf_debug_timing(long long *host_out, int n_ctas, int which) 
   return sgg::mpf::debug_timing(host_out, n_ctas, which);
 }
 
+namespace sgg { namespace lin16p { int overflow_flag(int reset, unsigned int *out); } int roi_overflow_flag(int reset, unsigned int *out); }
 /* fp16 range guard of the 3xFP16 engine (|x| must stay below 65504): returns the sticky flag (0 = every operand was in
  * range since the last reset; bit 0 activations, bit 1 emitted planes, bit 2 weights), negative on error. */
 extern "C" int sgg_tc16_overflow(int reset) {
-  unsigned int v = 0;
-  const int rc = sgg::tc16::overflow_flag(reset, &v);
-  return rc ? -1 : (int)v;
+  unsigned int v = 0, v2 = 0, v3 = 0;
+  int rc = sgg::tc16::overflow_flag(reset, &v);
+  if (rc == 0) rc = sgg::lin16p::overflow_flag(reset, &v2);     // pre-split LINEAR (lin16p.cu): emitted planes
+  if (rc == 0) rc = sgg::roi_overflow_flag(reset, &v3);         // RoIAlign rows emitted as operand planes
+  return rc ? -1 : (int)(v | v2 | v3);
 }

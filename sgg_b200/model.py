@@ -205,14 +205,15 @@ class RelModelBase(nn.Module):
         scales = [2.0 ** round(math.log2(float(fs) / float(os_))) for fs, os_ in ((fmap.shape[-2], mh), (fmap.shape[-1], mw))]
         return scales[0]
 
-    def node_edge_features(self, fmap, rois, union_inds, im_sizes, edge_add=None):
+    def node_edge_features(self, fmap, rois, union_inds, im_sizes, edge_add=None, planes=False):
         """rel_model_base.py:245-260: 7x7 RoIAlign features of the objects and of the union box of every pair.
-        ``edge_add`` [E,C] (internal, eval forward only): geometry embedding folded into the edge rows."""
+        ``edge_add`` [E,C] (internal, eval forward only): geometry embedding folded into the edge rows.
+        ``planes`` (internal, eval forward only): also return the fp16 operand planes of both outputs for the fc6 layers."""
         assert union_inds.shape[1] == 2, union_inds.shape
         if isinstance(fmap, dict):
             fmap = fmap['0']
         return K.node_edge_features(fmap, rois, union_inds, self._spatial_scale(fmap, im_sizes), self.pool_sz, 2,
-                                    edge_add=edge_add)
+                                    edge_add=edge_add, planes=planes)
 
     def get_scaled_boxes(self, boxes, im_inds, im_sizes):
         """rel_model_base.py:263-274: boxes / (w, h, w, h) of their image."""
@@ -260,22 +261,28 @@ class RelModelStanford(RelModelBase):
         edge_feat = ub(pools, rois, rel_inds[:, 1:], im_sizes)
         return self._predict_pooled(node_feat, edge_feat, rel_inds)
 
-    def _predict_pooled(self, node_feat, edge_feat, rel_inds, geom=None):
+    def _predict_pooled(self, node_feat, edge_feat, rel_inds, geom=None, planes=None):
         """rel_model_stanford.py:100-107: everything after ``self.union_boxes`` (edge_feat already carries the
-        union-box geometry, or ``geom`` [E,C] is still to be broadcast-added to it)."""
-        E = edge_feat.shape[0]
+        union-box geometry, or ``geom`` [E,C] is still to be broadcast-added to it).  ``planes`` = (node_planes,
+        edge_planes) from ``node_edge_features(planes=True)`` (eval): fc6 and fc7 of both heads then run on pre-split
+        operands, each layer's epilogue emitting the planes of the next."""
         fo, fe = self.roi_fmap_obj, self.roi_fmap[1]
         drop = self.training
-        n = K.linear(node_feat.reshape(node_feat.shape[0], -1), fo[0].weight, fo[0].bias, relu=True)
+        npl, epl = planes if (planes is not None and not drop) else (None, None)
+        # eval with planes: the fp32 RoIAlign rows may not exist at all (node_edge_features(planes='only'))
+        n, npl = K.linear(None if node_feat is None else node_feat.reshape(node_feat.shape[0], -1), fo[0].weight,
+                          fo[0].bias, relu=True, x_planes=npl, out_planes=True)
         n = F.dropout(n, self.dropout_p, drop)
-        n = K.linear(n, fo[3].weight, fo[3].bias, relu=True)
+        n = K.linear(n, fo[3].weight, fo[3].bias, relu=True, x_planes=npl)
         n = F.dropout(n, self.dropout_p, drop)
         if geom is not None:
             e = K.fc_broadcast(edge_feat, geom, fe[0].weight, fe[0].bias)
+            epl = None
         else:
-            e = K.linear(edge_feat.reshape(E, -1), fe[0].weight, fe[0].bias, relu=True)
+            e, epl = K.linear(None if edge_feat is None else edge_feat.reshape(edge_feat.shape[0], -1), fe[0].weight,
+                              fe[0].bias, relu=True, x_planes=epl, out_planes=True)
         e = F.dropout(e, self.dropout_p, drop)
-        e = K.linear(e, fe[3].weight, fe[3].bias, relu=False)
+        e = K.linear(e, fe[3].weight, fe[3].bias, relu=False, x_planes=None if drop else epl)
         n = K.linear(n, self.obj_unary.weight, self.obj_unary.bias)
         e = K.linear(e, self.edge_unary.weight, self.edge_unary.bias, relu=True)
         v, eh = self.message_pass(e, n, rel_inds[:, 1:3])
@@ -308,9 +315,13 @@ class RelModelStanford(RelModelBase):
             # embedding [E,C] is computed first and added inside the RoIAlign kernel: the [E,C,7,7] tensor is written
             # once instead of written, re-read and re-written (lib/get_union_boxes.py:101)
             geom = ops.union_geom(rois, rel_inds[:, 1:], K._conv_params(ub.conv))
-            result.node_feat, result.edge_feat = self.node_edge_features(result.fmap, rois, rel_inds[:, 1:],
-                                                                         im_sizes=result.im_sizes, edge_add=geom)
-            result.rm_obj_dists, result.rel_dists = self._predict_pooled(result.node_feat, result.edge_feat, rel_inds)
+            use_planes = ops._use_tc() and ops.tc_engine() == 'tc16' and result.fmap.shape[1] % 4 == 0
+            # with planes, the 963 MB of fp32 union-box rows are not written either: only the fc6 layers read them
+            feats = self.node_edge_features(result.fmap, rois, rel_inds[:, 1:], im_sizes=result.im_sizes, edge_add=geom,
+                                            planes='only' if use_planes else False)
+            result.node_feat, result.edge_feat = feats[0], feats[1]
+            result.rm_obj_dists, result.rel_dists = self._predict_pooled(result.node_feat, result.edge_feat, rel_inds,
+                                                                         planes=feats[2:] if use_planes else None)
         else:
             result.node_feat, result.edge_feat = self.node_edge_features(result.fmap, rois, rel_inds[:, 1:],
                                                                          im_sizes=result.im_sizes)

@@ -350,19 +350,46 @@ class MpProbe(object):
                                               self.nbytes, _stream()), 'sgg_mp_probe_launch')
 
 
-def linear(x, weight, bias=None, relu=False):
-    """nn.Linear forward (+ReLU) — y = act(x @ weight.T + bias)."""
+def linear(x, weight, bias=None, relu=False, x_planes=None, out_planes=False):
+    """nn.Linear forward (+ReLU) — y = act(x @ weight.T + bias).
+
+    ``x_planes`` [2, M, K] float16 (optional): the fp16 [hi | lo * 2^11] operand planes of ``x`` written by its producer
+    (``node_edge_features(planes=True)`` or a previous ``linear(out_planes=True)``); on the 3xFP16 engine the GEMM then
+    runs on the pre-split kernel (csrc/lin16p.cu, no in-kernel conversion of the activations).  ``out_planes=True``
+    returns ``(y, y_planes)`` — ``y_planes`` is None when the pre-split kernel was not used."""
     lib = _lib.load()
     w_obj = weight                 # the split cache is keyed by the caller's (long-lived) tensor object, not the detached view
-    x = _f32(x, 'x'); weight = _f32(weight, 'weight')
-    if x.dim() != 2 or weight.dim() != 2 or x.shape[1] != weight.shape[1]:
-        raise _lib.SggError('linear: x %s vs weight %s' % (tuple(x.shape), tuple(weight.shape)))
+    weight = _f32(weight, 'weight')
+    if x is None:                  # planes-only input (node_edge_features(planes='only'))
+        if x_planes is None or x_planes.dim() != 3:
+            raise _lib.SggError('linear: x is None and no x_planes [2, M, K] given')
+        if not (_use_tc() and lib.sgg_tc_get_mode() == 1 and x_planes.shape[2] % 8 == 0 and weight.shape[0] % 4 == 0):
+            raise _lib.SggError('linear: planes-only input needs the 3xFP16 engine, K % 8 == 0 and Nout % 4 == 0')
+        M, K = int(x_planes.shape[1]), int(x_planes.shape[2])
+        dev = x_planes.device
+        if weight.dim() != 2 or weight.shape[1] != K:
+            raise _lib.SggError('linear: x_planes %s vs weight %s' % (tuple(x_planes.shape), tuple(weight.shape)))
+    else:
+        x = _f32(x, 'x')
+        if x.dim() != 2 or weight.dim() != 2 or x.shape[1] != weight.shape[1]:
+            raise _lib.SggError('linear: x %s vs weight %s' % (tuple(x.shape), tuple(weight.shape)))
+        M, K = x.shape
+        dev = x.device
     if bias is not None:
         bias = _f32(bias, 'bias', (weight.shape[0],))
-    M, K = x.shape
     Nout = weight.shape[0]
-    y = torch.empty((M, Nout), dtype=torch.float32, device=x.device)
-    if _use_tc() and _tc_k_ok(K):
+    y = torch.empty((M, Nout), dtype=torch.float32, device=dev)
+    ypl = None
+    if (x_planes is not None and _use_tc() and lib.sgg_tc_get_mode() == 1 and K % 8 == 0 and Nout % 4 == 0 and M > 0):
+        if (x_planes.dtype != torch.float16 or tuple(x_planes.shape) != (2, M, K) or not x_planes.is_contiguous()
+                or x_planes.device != dev):
+            raise _lib.SggError('linear: x_planes must be a contiguous float16 [2, %d, %d] tensor on %s' % (M, K, dev))
+        sp = split_weight(w_obj)
+        if out_planes:
+            ypl = torch.empty((2, M, Nout), dtype=torch.float16, device=dev)
+        check(lib.sgg_tc16_linear_pre(_ptr(x_planes), _ptr(sp), _ptr(bias), _ptr(y), _ptr(ypl), M, Nout, K,
+                                      1 if relu else 0, _stream()), 'sgg_tc16_linear_pre')
+    elif _use_tc() and _tc_k_ok(K):
         sp = split_weight(w_obj)
         nb = lib.sgg_tc_linear_workspace_bytes(M, Nout, K)
         ws = torch.empty(nb, dtype=torch.uint8, device=x.device) if nb else None
@@ -371,7 +398,7 @@ def linear(x, weight, bias=None, relu=False):
     else:
         check(lib.sgg_linear_forward(_ptr(x), _ptr(weight), _ptr(bias), _ptr(y), M, Nout, K, 1 if relu else 0,
                                      _stream()), 'sgg_linear_forward')
-    return y
+    return (y, ypl) if out_planes else y
 
 
 class L1Plan(object):
@@ -570,19 +597,34 @@ def union_geom(rois, union_inds, params, union_pools=None, prefix='union_boxes.c
 
 
 def node_edge_features(fmap, rois, union_inds, spatial_scale=1.0 / 16, pool=7, sampling_ratio=2,
-                       want_node=True, want_edge=True, fast=True, edge_add=None):
+                       want_node=True, want_edge=True, fast=True, edge_add=None, planes=False):
     """RelModelBase.node_edge_features (rel_model_base.py:245-260).  ``edge_add`` [E,C] (optional): the union-box
-    geometry embedding, added to every bin of the edge rows in the same kernel (lib/get_union_boxes.py:101)."""
+    geometry embedding, added to every bin of the edge rows in the same kernel (lib/get_union_boxes.py:101).
+    ``planes=True`` also returns the fp16 operand planes of both outputs ([2, rows, C*pool*pool] float16 each) for
+    ``linear(..., x_planes=...)``: (node, edge, node_planes, edge_planes).  ``planes='only'``: the fp32 rows are not
+    written at all (node and edge are None) — the eval forward, where nothing but the fc6 layers reads them."""
     lib = _lib.load()
     fmap = _f32(fmap, 'fmap'); rois = _f32(rois, 'rois'); ui, stride = _i64_rows(union_inds, 'union_inds')
     B, Cc, Hf, Wf = fmap.shape
     N, E = rois.shape[0], ui.shape[0]
     if edge_add is not None:
         edge_add = _f32(edge_add, 'edge_add', (E, Cc))
-    node = torch.empty((N, Cc, pool, pool), dtype=torch.float32, device=fmap.device) if want_node else None
-    edge = torch.empty((E, Cc, pool, pool), dtype=torch.float32, device=fmap.device) if want_edge else None
+    rows32 = planes != 'only'
+    node = torch.empty((N, Cc, pool, pool), dtype=torch.float32, device=fmap.device) if (want_node and rows32) else None
+    edge = torch.empty((E, Cc, pool, pool), dtype=torch.float32, device=fmap.device) if (want_edge and rows32) else None
     nb = lib.sgg_node_edge_features_workspace_bytes(B, Cc, Hf, Wf) if fast else 0
     ws = torch.empty(nb, dtype=torch.uint8, device=fmap.device) if nb else None
+    if planes:
+        if not (fast and sampling_ratio == 2 and Cc % 4 == 0):
+            raise _lib.SggError('node_edge_features: planes need the channel-last path (fast, sampling_ratio 2, C % 4 == 0)')
+        per = Cc * pool * pool
+        npl = torch.empty((2, N, per), dtype=torch.float16, device=fmap.device) if want_node else None
+        epl = torch.empty((2, E, per), dtype=torch.float16, device=fmap.device) if want_edge else None
+        check(lib.sgg_node_edge_features_planes(_ptr(fmap), B, Cc, Hf, Wf, _ptr(rois), N, _ptr(ui), stride, 0, 1, E,
+                                                float(spatial_scale), pool, sampling_ratio, _ptr(edge_add), _ptr(node),
+                                                _ptr(edge), _ptr(npl), _ptr(epl), _ptr(ws), nb, _stream()),
+              'sgg_node_edge_features_planes')
+        return node, edge, npl, epl
     check(lib.sgg_node_edge_features_add(_ptr(fmap), B, Cc, Hf, Wf, _ptr(rois), N, _ptr(ui), stride, 0, 1, E,
                                          float(spatial_scale), pool, sampling_ratio, _ptr(edge_add), _ptr(node),
                                          _ptr(edge), _ptr(ws), nb, _stream()), 'sgg_node_edge_features_add')
