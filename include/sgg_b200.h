@@ -273,6 +273,9 @@ SGG_API int sgg_max4_backward(const float *dy, const unsigned char *idx, int E, 
  * sgg_bcast_add: out[r,s] = pools[r,s] + geom[r], r < rows = E*C, s < S = 49 (lib/get_union_boxes.py:101);
  * sgg_relu_backward: dx = y > 0 ? dy : 0;  sgg_group_sum: out[g] = sum_s x[g,s] (e.g. the 7x7 taps of fc6's weight). */
 SGG_API int sgg_bcast_add(const float *pools, const float *geom, long long rows, int S, float *out, void *stream);
+/* sgg_bcast_add + the fp16 [hi | lo * 2^11] operand planes of out (2 * rows * S halves) for sgg_tc16_linear_pre */
+SGG_API int sgg_bcast_add_planes(const float *pools, const float *geom, long long rows, int S, float *out, void *out_planes,
+                                 void *stream);
 SGG_API int sgg_relu_backward(const float *dy, const float *y, long long n, float *dx, void *stream);
 SGG_API int sgg_group_sum(const float *x, long long groups, int S, float *out, void *stream);
 

@@ -103,6 +103,7 @@ SIGNATURES = {
     'sgg_max4_forward': (C.c_int, [c_f, C.c_int, C.c_int, c_f, C.c_void_p, C.c_void_p]),
     'sgg_max4_backward': (C.c_int, [c_f, C.c_void_p, C.c_int, C.c_int, c_f, C.c_void_p]),
     'sgg_bcast_add': (C.c_int, [c_f, c_f, C.c_longlong, C.c_int, c_f, C.c_void_p]),
+    'sgg_bcast_add_planes': (C.c_int, [c_f, c_f, C.c_longlong, C.c_int, c_f, C.c_void_p, C.c_void_p]),
     'sgg_relu_backward': (C.c_int, [c_f, c_f, C.c_longlong, c_f, C.c_void_p]),
     'sgg_group_sum': (C.c_int, [c_f, C.c_longlong, C.c_int, c_f, C.c_void_p]),
     'sgg_mpf_debug_timing': (C.c_int, [C.POINTER(C.c_longlong), C.c_int, C.c_int]),

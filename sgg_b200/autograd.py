@@ -187,8 +187,16 @@ class _FcBroadcastFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, pools, geom, weight, bias):
         E = pools.shape[0]
-        x = ops.bcast_add(pools, geom).view(E, -1)
-        y = ops.linear(x, weight, bias, relu=True)
+        if ops._use_tc() and ops.tc_engine() == 'tc16' and pools.numel() % 4 == 0 and weight.shape[0] % 4 == 0:
+            # the add also emits the fp16 operand planes: the forward GEMM runs on the pre-split kernel (no in-kernel
+            # conversion of the 9600 x 25088 activations); the fp32 x stays for the weight gradient
+            x, xpl = ops.bcast_add(pools, geom, planes=True)
+            x = x.view(E, -1)
+            y = ops.linear(x, weight, bias, relu=True, x_planes=xpl)
+            del xpl
+        else:
+            x = ops.bcast_add(pools, geom).view(E, -1)
+            y = ops.linear(x, weight, bias, relu=True)
         ctx.S = pools.shape[2] * pools.shape[3]
         ctx.save_for_backward(x, weight, y)
         ctx.has_bias = bias is not None

@@ -6,6 +6,7 @@
 // forward and backward, the preceding ReLU folded in) and the 2x2 -> 1 max-pool, both as deterministic CUDA kernels
 // (fixed-order column reductions, no atomics).  Round 1 ran these through ATen.
 #include "common.cuh"
+#include "tc16_common.cuh"
 #include "kernels.h"
 
 namespace sgg {
@@ -148,9 +149,13 @@ __global__ void k_max4_bwd(const float *__restrict__ dy, const unsigned char *__
   }
 }
 
+__device__ unsigned int g_bcast_overflow = 0;   // sticky: an emitted operand plane left the fp16 range (sgg_tc16_overflow, bit 0)
 // out[e, c, s] = pools[e, c, s] + geom[e, c]   (lib/get_union_boxes.py:101, the broadcast add of the training path)
+// pl_hi / pl_lo (nullable): also the fp16 [hi | lo * 2^11] operand planes of `out` for the pre-split fc6 GEMM (lin16p.cu)
 __global__ void k_bcast_add(const float4 *__restrict__ pools, const float *__restrict__ geom, size_t n4, int S4,
-                            float4 *__restrict__ out) {
+                            float4 *__restrict__ out, uint2 *__restrict__ pl_hi, uint2 *__restrict__ pl_lo,
+                            unsigned int *__restrict__ ovf_flag) {
+  unsigned int ovf = 0;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
     float4 v = pools[i];
     // element 4i..4i+3 of [E*C, S]: row = (4i + k) / S
@@ -159,7 +164,14 @@ __global__ void k_bcast_add(const float4 *__restrict__ pools, const float *__res
     const float g0 = geom[base / S], g1 = geom[(base + 1) / S], g2 = geom[(base + 2) / S], g3 = geom[(base + 3) / S];
     v.x += g0; v.y += g1; v.z += g2; v.w += g3;
     out[i] = v;
+    if (pl_hi != nullptr) {
+      uint2 hi, lo;
+      tc16::split2(v.x, v.y, hi.x, lo.x); tc16::split2(v.z, v.w, hi.y, lo.y);
+      ovf |= tc16::f16x2_nonfinite(hi.x) | tc16::f16x2_nonfinite(hi.y);
+      pl_hi[i] = hi; pl_lo[i] = lo;
+    }
   }
+  if (ovf) atomicOr(ovf_flag, 1u);
 }
 // dx = dy where y > 0 else 0   (ReLU backward from the saved output)
 __global__ void k_relu_bwd(const float4 *__restrict__ dy, const float4 *__restrict__ y, size_t n4, float4 *__restrict__ dx) {
@@ -272,10 +284,39 @@ extern "C" int sgg_bcast_add(const float *pools, const float *geom, long long ro
   if (rows <= 0 || S <= 0) return 0;
   const size_t n = (size_t)rows * S;
   if (!pools || !geom || !out || (n & 3)) return sgg_set_err(SGG_E_BADARG, "bcast_add: bad argument");
-  sgg::k_bcast_add<<<sgg::ew_grid(n / 4), 256, 0, (cudaStream_t)stream>>>((const float4 *)pools, geom, n / 4, S, (float4 *)out);
+  sgg::k_bcast_add<<<sgg::ew_grid(n / 4), 256, 0, (cudaStream_t)stream>>>((const float4 *)pools, geom, n / 4, S, (float4 *)out,
+                                                                          nullptr, nullptr, nullptr);
   SGG_RETURN_IF_LAUNCH_FAILED("k_bcast_add");
   return 0;
 }
+/* Same, and the fp16 [hi | lo * 2^11] operand planes of out (2 * rows * S halves) for sgg_tc16_linear_pre: the train-mode
+ * fc6 forward of rel_model_stanford.py:100-101 then runs on pre-split operands while out (fp32) stays for the backward. */
+extern "C" int sgg_bcast_add_planes(const float *pools, const float *geom, long long rows, int S, float *out, void *out_planes,
+                                    void *stream) {
+  if (rows <= 0 || S <= 0) return 0;
+  const size_t n = (size_t)rows * S;
+  if (!pools || !geom || !out || !out_planes || (n & 3)) return sgg_set_err(SGG_E_BADARG, "bcast_add_planes: bad argument");
+  unsigned int *flag = nullptr;
+  SGG_CUDA_TRY(cudaGetSymbolAddress((void **)&flag, sgg::g_bcast_overflow));
+  uint2 *hi = (uint2 *)out_planes, *lo = (uint2 *)((__half *)out_planes + n);
+  sgg::k_bcast_add<<<sgg::ew_grid(n / 4), 256, 0, (cudaStream_t)stream>>>((const float4 *)pools, geom, n / 4, S, (float4 *)out, hi, lo,
+                                                                          flag);
+  SGG_RETURN_IF_LAUNCH_FAILED("k_bcast_add");
+  return 0;
+}
+namespace sgg {
+int bcast_overflow_flag(int reset, unsigned int *out) {
+  unsigned int v = 0;
+  if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+  if (cudaMemcpyFromSymbol(&v, g_bcast_overflow, sizeof(v)) != cudaSuccess) return -1;
+  if (reset) {
+    const unsigned int z = 0;
+    if (cudaMemcpyToSymbol(g_bcast_overflow, &z, sizeof(z)) != cudaSuccess) return -1;
+  }
+  *out = v;
+  return 0;
+}
+}  // namespace sgg
 extern "C" int sgg_relu_backward(const float *dy, const float *y, long long n, float *dx, void *stream) {
   if (n <= 0) return 0;
   if (!dy || !y || !dx || (n & 3)) return sgg_set_err(SGG_E_BADARG, "relu_backward: bad argument");

@@ -101,7 +101,7 @@ extern "C" int sgg_mpf_debug_timing(long long *host_out, int n_ctas, int which) 
   return sgg::mpf::debug_timing(host_out, n_ctas, which);
 }
 
-namespace sgg { namespace lin16p { int overflow_flag(int reset, unsigned int *out); } int roi_overflow_flag(int reset, unsigned int *out); }
+namespace sgg { namespace lin16p { int overflow_flag(int reset, unsigned int *out); } int roi_overflow_flag(int reset, unsigned int *out); int bcast_overflow_flag(int reset, unsigned int *out); }
 /* fp16 range guard of the 3xFP16 engine (|x| must stay below 65504): returns the sticky flag (0 = every operand was in
  * range since the last reset; bit 0 activations, bit 1 emitted planes, bit 2 weights), negative on error. */
 extern "C" int sgg_tc16_overflow(int reset) {
@@ -109,5 +109,7 @@ extern "C" int sgg_tc16_overflow(int reset) {
   int rc = sgg::tc16::overflow_flag(reset, &v);
   if (rc == 0) rc = sgg::lin16p::overflow_flag(reset, &v2);     // pre-split LINEAR (lin16p.cu): emitted planes
   if (rc == 0) rc = sgg::roi_overflow_flag(reset, &v3);         // RoIAlign rows emitted as operand planes
-  return rc ? -1 : (int)(v | v2 | v3);
+  unsigned int v4 = 0;
+  if (rc == 0) rc = sgg::bcast_overflow_flag(reset, &v4);       // pools + geom rows emitted as operand planes (train)
+  return rc ? -1 : (int)(v | v2 | v3 | v4);
 }

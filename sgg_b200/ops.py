@@ -534,12 +534,18 @@ def max4_backward(dy, idx):
     return dx
 
 
-def bcast_add(pools, geom):
-    """pools [E,C,P,P] + geom [E,C] broadcast over the P x P positions (lib/get_union_boxes.py:101)."""
+def bcast_add(pools, geom, planes=False):
+    """pools [E,C,P,P] + geom [E,C] broadcast over the P x P positions (lib/get_union_boxes.py:101).
+    ``planes=True``: returns (out, out_planes [2, E, C*P*P] float16) — the operand planes for ``linear(x_planes=...)``."""
     lib = _lib.load()
     pools = _f32(pools, 'pools'); geom = _f32(geom, 'geom', (pools.shape[0], pools.shape[1]))
     out = torch.empty_like(pools)
     S = pools.shape[2] * pools.shape[3]
+    if planes:
+        pl = torch.empty((2, pools.shape[0], pools.shape[1] * S), dtype=torch.float16, device=pools.device)
+        check(lib.sgg_bcast_add_planes(_ptr(pools), _ptr(geom), pools.shape[0] * pools.shape[1], S, _ptr(out), _ptr(pl),
+                                       _stream()), 'sgg_bcast_add_planes')
+        return out, pl
     check(lib.sgg_bcast_add(_ptr(pools), _ptr(geom), pools.shape[0] * pools.shape[1], S, _ptr(out), _stream()), 'sgg_bcast_add')
     return out
 

@@ -88,3 +88,15 @@ def test_planes_only_path_matches_the_fp32_path():
     assert torch.equal(ya, yb)
     ref = (e1.reshape(e1.shape[0], -1).double() @ w.detach().double().t()).clamp_min(0)
     assert float((yb.double() - ref).abs().max()) <= 1e-5 * float(ref.abs().max())
+
+
+def test_bcast_add_planes_are_the_split_of_the_sum():
+    from sgg_b200 import ops
+    g = torch.Generator(device='cuda').manual_seed(9)
+    pools = torch.rand(37, 16, 7, 7, device='cuda', generator=g) * 5
+    geom = torch.randn(37, 16, device='cuda', generator=g)
+    out0 = ops.bcast_add(pools, geom)
+    out, pl = ops.bcast_add(pools, geom, planes=True)
+    assert torch.equal(out, out0) and torch.equal(out, pools + geom[:, :, None, None])
+    exp = _planes(out.reshape(37, -1))
+    assert pl.shape == exp.shape and torch.equal(pl[0], exp[0]) and torch.equal(pl[1], exp[1])
