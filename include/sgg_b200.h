@@ -164,9 +164,10 @@ SGG_API int sgg_tc16_linear_scaled(const float *x, const void *w_split16, float 
 /* nn.Linear forward on tcgen05 with BOTH operands pre-split (lin16p.cu): x_planes = fp16 [hi | lo * 2^11] planes of
  * x [M,K] (2 * M * K halves, written by sgg_node_edge_features_planes or as y_planes of a previous call), w_split16 =
  * planes of w [Nout,K] (sgg_tc_split_weights, 3xFP16 layout).  y [M,Nout] fp32; y_planes nullable (2 * M * Nout halves).
- * K % 8 == 0, Nout % 4 == 0.  Replaces F.linear of rel_model_stanford.py:100-101 on RoIAlign rows. */
+ * K % 8 == 0, Nout % 4 == 0.  Replaces F.linear of rel_model_stanford.py:100-101 on RoIAlign rows.
+ * out_scale (nullable device scalar) multiplies x w^T before bias / ReLU: the 1/s of a scaled backward GEMM. */
 SGG_API int sgg_tc16_linear_pre(const void *x_planes, const void *w_split16, const float *bias, float *y, void *y_planes,
-                                int M, int Nout, int K, int relu, void *stream);
+                                int M, int Nout, int K, int relu, const float *out_scale, void *stream);
 
 /* ---- tensor-core (tcgen05 / TMEM / TMA) variants -----------------------------------------
  * fp32 in, fp32 out, fp32-grade accuracy through a 3-pass operand split.  Two engines:

@@ -93,7 +93,7 @@ SIGNATURES = {
     'sgg_tc16_linear_scaled': (C.c_int, [c_f, C.c_void_p, c_f, C.c_int, C.c_int, C.c_int, c_f, C.c_void_p, C.c_size_t,
                                          C.c_void_p]),
     'sgg_tc16_linear_pre': (C.c_int, [C.c_void_p, C.c_void_p, c_f, c_f, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
-                                      C.c_void_p]),
+                                      c_f, C.c_void_p]),
     'sgg_tc16_overflow': (C.c_int, [C.c_int]),
     'sgg_bn_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int]),
     'sgg_bn_train_forward': (C.c_int, [c_f, C.c_int, C.c_int, C.c_int, c_f, c_f, c_f, c_f, C.c_float, C.c_float, c_f, c_f,

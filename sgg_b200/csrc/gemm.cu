@@ -365,7 +365,7 @@ __global__ void __launch_bounds__(256) k_transpose16(const float *__restrict__ i
                                                      int Rpad, const float *__restrict__ sc) {
   __shared__ float tile[32][33];
   const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
-  const float s = (MODE == 0 && sc != nullptr) ? sc[0] : 1.f;
+  const float s = sc != nullptr ? sc[0] : 1.f;               // power-of-two scale of a gradient operand (exact)
   for (int i = threadIdx.y; i < 32; i += 8) {
     const int r = r0 + i, c = c0 + threadIdx.x;
     tile[i][threadIdx.x] = (r < R && c < C) ? in[(size_t)r * ldin + c] * s : 0.f;
@@ -417,7 +417,7 @@ extern "C" int sgg_pow2_scale(const float *x, long long n, float *sc, void *ws, 
   SGG_RETURN_IF_LAUNCH_FAILED("k_pow2_scale");
   return 0;
 }
-/* in [R,C] (row stride ldin) -> out [C,Rpad]: mode 0 = fp32, multiplied by sc[0] (sc nullable); mode 1 = fp16 [hi | lo] planes */
+/* in [R,C] (row stride ldin) -> out [C,Rpad], multiplied by sc[0] (sc nullable): mode 0 = fp32; mode 1 = fp16 [hi | lo] planes */
 extern "C" int sgg_bwd_transpose16(const float *in, long long ldin, int R, int C, void *out, int Rpad, int mode, const float *sc,
                                    void *stream) {
   if (!in || !out || R < 0 || C <= 0 || Rpad < R || ldin < C || ldin > 0x7fffffffLL || (mode != 0 && mode != 1))
@@ -425,7 +425,7 @@ extern "C" int sgg_bwd_transpose16(const float *in, long long ldin, int R, int C
   dim3 grid((Rpad + 31) / 32, (C + 31) / 32);
   if (grid.y > 65535) return sgg_set_err(SGG_E_BADARG, "bwd_transpose16: too many columns");
   if (mode == 0) sgg::k_transpose16<0><<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(in, (int)ldin, R, C, out, Rpad, sc);
-  else sgg::k_transpose16<1><<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(in, (int)ldin, R, C, out, Rpad, nullptr);
+  else sgg::k_transpose16<1><<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(in, (int)ldin, R, C, out, Rpad, sc);
   SGG_RETURN_IF_LAUNCH_FAILED("k_transpose16");
   return 0;
 }

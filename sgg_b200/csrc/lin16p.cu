@@ -27,6 +27,7 @@ __device__ unsigned int g_lin16p_overflow = 0;   // sticky: an emitted output pl
 struct LinParams {
   int M, K, Nout, relu;
   const float *bias;          // nullable
+  const float *out_scale;     // nullable device scalar multiplied into x w^T before bias / ReLU (scaled backward GEMMs)
   float *out;                 // [M, Nout]
   __half *out_hi, *out_lo;    // nullable: planes of the output
 };
@@ -146,12 +147,13 @@ k_lin16p(const LinParams p, const __grid_constant__ CUtensorMap tmAh, const __gr
     const int m = m0 + row, cbase = n0 + half * HC;
     if (m < p.M) {
       uint32_t ovf = 0;
+      const float osc = p.out_scale != nullptr ? __ldg(p.out_scale) : 1.0f;
       float *orow = p.out + (size_t)m * p.Nout;
 #pragma unroll
       for (int c = 0; c < HC; c += 4) {
         const int col = cbase + c;
         if (col < p.Nout) {                  // Nout % 4 == 0: a group of four is inside or outside
-          float4 v = make_float4(acc[c], acc[c + 1], acc[c + 2], acc[c + 3]);
+          float4 v = make_float4(acc[c] * osc, acc[c + 1] * osc, acc[c + 2] * osc, acc[c + 3] * osc);
           if (p.bias != nullptr) {
             const float4 bv = ldg4(p.bias + col);
             v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
@@ -193,9 +195,10 @@ int overflow_flag(int reset, unsigned int *out) {
 /* y [M,Nout] = act(x w^T + b) on tcgen05 with BOTH operands pre-split: x_planes = fp16 [hi | lo * 2^11] planes of x [M,K]
  * (2 * M * K halves: sgg_node_edge_features_planes, or y_planes of a previous call), w_split16 = planes of w [Nout,K]
  * (sgg_tc_split_weights, 3xFP16 layout).  y_planes nullable: also emit the planes of y (2 * M * Nout halves).
+ * out_scale nullable (device scalar multiplied into x w^T before bias / ReLU).
  * K % 8 == 0, Nout % 4 == 0; fp16 range of x is the producer's responsibility (sticky flag: sgg_tc16_overflow). */
 extern "C" int sgg_tc16_linear_pre(const void *x_planes, const void *w_split16, const float *bias, float *y, void *y_planes,
-                                   int M, int Nout, int K, int relu, void *stream) {
+                                   int M, int Nout, int K, int relu, const float *out_scale, void *stream) {
   using namespace sgg::lin16p;
   if (M <= 0 || Nout <= 0) return 0;
   if (!x_planes || !w_split16 || !y) return sgg_set_err(SGG_E_BADARG, "tc16_linear_pre: null pointer");
@@ -215,7 +218,7 @@ extern "C" int sgg_tc16_linear_pre(const void *x_planes, const void *w_split16, 
   if ((rc = sgg::tc16::make_tmap(&tm[2], wh, Nout, K, NC, 2))) return rc;
   if ((rc = sgg::tc16::make_tmap(&tm[3], wh + (size_t)Nout * K, Nout, K, NC, 2))) return rc;
   LinParams p{};
-  p.M = M; p.K = K; p.Nout = Nout; p.relu = relu; p.bias = bias; p.out = y;
+  p.M = M; p.K = K; p.Nout = Nout; p.relu = relu; p.bias = bias; p.out = y; p.out_scale = out_scale;
   p.out_hi = (__half *)y_planes; p.out_lo = y_planes ? (__half *)y_planes + (size_t)M * Nout : nullptr;
   // blockIdx.x = column tile: CTAs resident together share a row block's A tiles and walk k in lockstep
   dim3 grid((Nout + NC - 1) / NC, (M + sgg::tc16::BM - 1) / sgg::tc16::BM);

@@ -388,7 +388,7 @@ def linear(x, weight, bias=None, relu=False, x_planes=None, out_planes=False):
         if out_planes:
             ypl = torch.empty((2, M, Nout), dtype=torch.float16, device=dev)
         check(lib.sgg_tc16_linear_pre(_ptr(x_planes), _ptr(sp), _ptr(bias), _ptr(y), _ptr(ypl), M, Nout, K,
-                                      1 if relu else 0, _stream()), 'sgg_tc16_linear_pre')
+                                      1 if relu else 0, None, _stream()), 'sgg_tc16_linear_pre')
     elif _use_tc() and _tc_k_ok(K):
         sp = split_weight(w_obj)
         nb = lib.sgg_tc_linear_workspace_bytes(M, Nout, K)
@@ -730,7 +730,8 @@ def _pow2_scale(x):
 
 
 def _transpose16(inp, R, C, ldin, Rpad, planes, sc=None):
-    """inp [R, C] (row stride ldin) -> [C, Rpad]: planes=False: fp32 scaled by sc[0]; planes=True: fp16 [hi | lo] [2, C, Rpad]"""
+    """inp [R, C] (row stride ldin) -> [C, Rpad], scaled by sc[0] when given: planes=False: fp32; planes=True: fp16 [hi | lo]
+    planes [2, C, Rpad]"""
     lib = _lib.load()
     if planes:
         out = torch.empty((2, C, Rpad), dtype=torch.float16, device=inp.device)
@@ -808,9 +809,15 @@ def linear_backward(x, weight, dy, need_dx=True, need_dw=True, need_db=True):
         chunks = sink[2] if (sink is not None and sink[2]) else [(0, Nout)]
         if tc16 and sc is not None:
             xT = _transpose16(x, M, K, K, Mp, planes=True)                # fp16 planes [2, K, Mp], shared by every row chunk
+            pre = K % 4 == 0                                              # both operands pre-split: csrc/lin16p.cu
             for r0, r1 in chunks:
-                dyT = _transpose16(dy[:, r0:], M, r1 - r0, Nout, Mp, planes=False, sc=sc)    # (s dY)^T [r1-r0, Mp]
-                _tc16_linear_scaled(dyT, xT, r1 - r0, K, Mp, sc[1:], out=dw[r0:r1])
+                if pre:
+                    dyT = _transpose16(dy[:, r0:], M, r1 - r0, Nout, Mp, planes=True, sc=sc)   # planes of (s dY)^T [2, r1-r0, Mp]
+                    check(lib.sgg_tc16_linear_pre(_ptr(dyT), _ptr(xT), None, _ptr(dw[r0:r1]), None, r1 - r0, K, Mp, 0,
+                                                  _ptr(sc[1:]), _stream()), 'sgg_tc16_linear_pre')
+                else:
+                    dyT = _transpose16(dy[:, r0:], M, r1 - r0, Nout, Mp, planes=False, sc=sc)  # (s dY)^T [r1-r0, Mp]
+                    _tc16_linear_scaled(dyT, xT, r1 - r0, K, Mp, sc[1:], out=dw[r0:r1])
                 if sink is not None:
                     sink[3](sink[0](), r0, r1)
         else:
