@@ -363,6 +363,8 @@ extern "C" int sgg_mp_backward(const float *obj_rep, const float *rel_rep, const
     int r;
     if (use16) {
       if (scp == nullptr) { if ((r = scale16(dY, M))) return r; scp = s.sc; }
+      // (the pre-split kernel, lin16p.cu, was tried here: its 48 tiles of a [3H, H] output without split-K leave 100 SMs idle —
+      // L1 train step 3.99 -> 4.08 ms — so these GEMMs stay on the split-K LINEAR engine)
       r = sgg_bwd_transpose16(dY, 3 * H, M, 3 * H, s.xT, mp, 0, scp, st);                           // (s dY)^T  [3H, mp] fp32
       if (r == 0) r = sgg_bwd_transpose16(X, H, M, H, s.bT, mp, 1, nullptr, st);                     // X^T planes [H, mp]
       if (r == 0) r = tc16::linear_scaled(s.xT, s.bT, s.tmp, 3 * H, H, mp, scp + 1, s.lin, st);
