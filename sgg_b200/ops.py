@@ -809,9 +809,12 @@ def linear_backward(x, weight, dy, need_dx=True, need_dw=True, need_db=True):
         chunks = sink[2] if (sink is not None and sink[2]) else [(0, Nout)]
         if tc16 and sc is not None:
             xT = _transpose16(x, M, K, K, Mp, planes=True)                # fp16 planes [2, K, Mp], shared by every row chunk
-            pre = K % 4 == 0                                              # both operands pre-split: csrc/lin16p.cu
+            # both operands pre-split (csrc/lin16p.cu) when the output has enough 128 x 128 tiles to fill the GPU; small
+            # outputs (classifier heads: 4 tiles, 150 k-blocks each) stay on the split-K LINEAR engine
+            def pre_ok(rows):
+                return K % 4 == 0 and ((rows + 127) // 128) * ((K + 127) // 128) >= 96
             for r0, r1 in chunks:
-                if pre:
+                if pre_ok(r1 - r0):
                     dyT = _transpose16(dy[:, r0:], M, r1 - r0, Nout, Mp, planes=True, sc=sc)   # planes of (s dY)^T [2, r1-r0, Mp]
                     check(lib.sgg_tc16_linear_pre(_ptr(dyT), _ptr(xT), None, _ptr(dw[r0:r1]), None, r1 - r0, K, Mp, 0,
                                                   _ptr(sc[1:]), _stream()), 'sgg_tc16_linear_pre')
