@@ -4,14 +4,18 @@
 //
 //   out[pixel, cout] = sum_{tap, cin} in[pixel + tap, cin] * w[cout, tap, cin]
 //
-// with activations kept as NHWC fp16 planes [hi | lo * 2^11] (tc16_common.cuh: x = hi + 2^-11 lo, three MMA passes give
-// fp32-grade results), so the im2col operand never exists: for tap (dy, dx) and a block of 64 input channels, the A tile
-// of an 8 x 16 pixel output tile is ONE 4-D TMA box {64 c, 16 w, 8 h, 1 n} at (w0 + dx - 1, h0 + dy - 1) — the hardware's
-// out-of-bounds zero fill is the padding.  K = 9 * Cin is folded into TMEM 256 at a time (two ping-pong accumulator
-// pairs, the tensor core's fp32 accumulate truncates: DESIGN.md section 4); eight warps drain the chunks into registers.
-// Epilogue: bias + ReLU, optional fused 2x2 max-pool (the tile holds whole windows), output again as fp16 planes (NHWC)
-// or, for the last layer, fp32 NCHW (the layout RelModel.fmap has in the reference).
-// The first layer (Cin = 3, K = 27) is a small SIMT kernel that also converts NCHW fp32 images to planes.
+// with activations kept as NHWC fp16 planes [hi | lo * 2^11] (tc16_common.cuh: x = hi + 2^-11 lo, fp32-grade results), so
+// the im2col operand never exists and the hardware's out-of-bounds zero fill of the TMA boxes is the padding.
+// K = 9 * Cin is folded into TMEM 256 at a time (two ping-pong accumulator pairs, the tensor core's fp32 accumulate
+// truncates: DESIGN.md section 4); eight warps drain the chunks into registers.  Epilogue: bias + ReLU, optional fused
+// 2x2 max-pool, output again as fp16 planes (NHWC) or, for the last layer, fp32 NCHW (the layout RelModel.fmap has in the
+// reference).  Two kernels, chosen per layer:
+//   k_conv3x3     (v1): one 8 x 16 pixel tile per CTA; per tap and 64-channel block the A tile is ONE 4-D TMA box
+//                       {64 c, 16 w, 8 h, 1 n} at (w0 + dx - 1, h0 + dy - 1).  Used from 512 input channels.
+//   k_conv3x3_v2  (v2): persistent CTAs over 16 x 8 tiles; three column-shifted 18 x 8 slabs per channel block serve all
+//                       nine taps through shifted shared-memory descriptors.  Used up to 256 input channels.
+// Both have a cta_group::2 variant (CTA pairs, M = 256).  The first layer (Cin = 3, K = 27) is a SIMT kernel that also
+// converts NCHW fp32 images to planes.
 #include <stdlib.h>
 #include <stdio.h>
 #include "tc16_common.cuh"
@@ -228,7 +232,7 @@ k_conv3x3(const ConvParams p, const __grid_constant__ CUtensorMap tmAh, const __
             mma_f16_ss_pair(dc, ah + o, bl + o, idesc, 1u);
             mma_f16_ss_pair(dm, ah + o, bh + o, idesc, acc);
           } else {
-            // two instructions instead of three (tc16_common.cuh, "instruction floor"): the B_lo tile follows the B_hi
+            // two instructions instead of three (tc16_common.cuh, "fused pair"): the B_lo tile follows the B_hi
             // tile in shared memory, so ONE N = 2 NC MMA forms [main | a_hi b_lo] in the adjacent column ranges
             mma_f16_ss(dm, ah + o, bh + o, idesc2, acc);
             mma_f16_ss(dc, al + o, bh + o, idesc, 1u);
@@ -806,7 +810,8 @@ static int make_tmap_4d(CUtensorMap *m, const void *base, int B, int H, int W, i
 
 // SGG_CONV_CG = 1 | 2 (default 1): CTAs per UMMA tile.  The cta_group::2 variants are exact and halve the weight bytes each SM
 // stages, but measured no faster (profiles/r02_conv_experiments.md): these kernels are bound by the tensor pipe's
-// per-instruction floor, not by shared-memory or L2 bandwidth, and the pair cannot use the fused two-instruction pattern.
+// power cap and by instruction count, not by shared-memory or L2 bandwidth, and the pair cannot use the fused two-instruction
+// pattern (its 2 NC columns would interleave the two CTAs' halves).
 static int conv_cta_group() {
   static int v = -1;
   if (v < 0) {

@@ -1,6 +1,15 @@
 // Shared pieces of the 3xFP16 tcgen05 engine (tc16_gemm.cu) and the fused message-passing kernels (mp_fused.cu):
 // tile constants, UMMA descriptors, the fp16 [hi | lo*2^11] operand split, the GRUCell pointwise math and the
 // TMA tensor-map encoder.
+//
+// MMA pattern of a K16 step.  With x = hi + 2^-11 lo the three products are a_hi b_hi (MAIN) and a_lo b_hi + a_hi b_lo
+// (CORR, carries the 2^11 scale).  Where a tile has NC <= 128 columns the kernels issue TWO instructions, not three:
+// every stage stores the B_lo tile right behind the B_hi tile and every accumulator pair stores CORR right behind MAIN, so
+// ONE N = 2 NC instruction computes [a_hi b_hi | a_hi b_lo] and a second, N = NC, adds a_lo b_hi into CORR ("fused pair").
+// Same flops, one instruction and one A_hi fetch fewer per step; the issuing thread spends ~100 cycles per tcgen05.mma
+// when operands change per instruction (tools/ubench/umma_rate.cu), so narrow tiles are bound by instruction count.
+// The issuing loops run warp-uniformly and ONE ELECTED lane issues (elect.sync): under `if (lane == 0)` the compiler
+// wraps each UTCHMMA / UTMALDG in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop to move its operands to uniform registers.
 #pragma once
 #include <cuda_fp16.h>
 #include "tc_gemm.cuh"
