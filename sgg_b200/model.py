@@ -315,7 +315,9 @@ class RelModelStanford(RelModelBase):
             # embedding [E,C] is computed first and added inside the RoIAlign kernel: the [E,C,7,7] tensor is written
             # once instead of written, re-read and re-written (lib/get_union_boxes.py:101)
             geom = ops.union_geom(rois, rel_inds[:, 1:], K._conv_params(ub.conv))
-            use_planes = ops._use_tc() and ops.tc_engine() == 'tc16' and result.fmap.shape[1] % 4 == 0
+            # (planes-only activations cannot enter an autograd graph: without torch.no_grad() the fp32 path is kept)
+            use_planes = (ops._use_tc() and ops.tc_engine() == 'tc16' and result.fmap.shape[1] % 4 == 0
+                          and not torch.is_grad_enabled())
             # with planes, the 963 MB of fp32 union-box rows are not written either: only the fc6 layers read them
             feats = self.node_edge_features(result.fmap, rois, rel_inds[:, 1:], im_sizes=result.im_sizes, edge_add=geom,
                                             planes='only' if use_planes else False)

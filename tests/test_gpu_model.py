@@ -129,6 +129,29 @@ def test_l3_forward_eval_vs_golden(model, mode):
     assert same >= 0.9, same
 
 
+def test_l3_forward_eval_without_no_grad_matches_the_no_grad_path(model):
+    """model.eval(); model(batch) with autograd enabled (a caller who forgot torch.no_grad()) takes the fp32 activation
+    path — the pre-split fc6 / fc7 kernels cannot enter an autograd graph — and returns the same detections."""
+    seed = 4242
+    sizes, boxes, gt_classes, gt_rels = l3_case(seed)
+    imgs = synth.synth_images(sizes, seed)
+    model.mode = 'sgcls'
+    model.eval()
+    batch = [([torch.from_numpy(i)[None] for i in imgs], None, 0, torch.from_numpy(boxes), torch.from_numpy(gt_classes),
+              torch.from_numpy(gt_rels), None, ['a', 'b'])]
+    with torch.no_grad():
+        b0, oc0, osc0, rels0, ps0 = model(batch)
+    b1, oc1, osc1, rels1, ps1 = model(batch)
+    model.mode = 'predcls'
+    assert np.array_equal(b0, b1) and np.array_equal(oc0, oc1) and np.abs(osc0 - osc1).max() <= 1e-5
+    assert rels0.shape == rels1.shape and ps0.shape == ps1.shape
+    key = lambda r: {tuple(x): i for i, x in enumerate(r.tolist())}
+    m0, m1 = key(rels0), key(rels1)
+    assert set(m0) == set(m1)
+    for pair, i in m0.items():
+        assert np.abs(ps0[i] - ps1[m1[pair]]).max() <= 1e-4, pair
+
+
 def test_train_forward_backward_contract(model):
     """Training mode returns a Result with the reference's fields; loss.backward() yields gradients for every
     trainable (non-detector) tensor; detector stays frozen."""
