@@ -380,6 +380,10 @@ def linear(x, weight, bias=None, relu=False, x_planes=None, out_planes=False):
     Nout = weight.shape[0]
     y = torch.empty((M, Nout), dtype=torch.float32, device=dev)
     ypl = None
+    if M == 0:                     # pair-less batch: nothing to compute (and no fp32 x to fall back on when planes-only)
+        if out_planes:
+            return y, (torch.empty((2, 0, Nout), dtype=torch.float16, device=dev) if x_planes is not None else None)
+        return y
     if (x_planes is not None and _use_tc() and lib.sgg_tc_get_mode() == 1 and K % 8 == 0 and Nout % 4 == 0 and M > 0):
         if (x_planes.dtype != torch.float16 or tuple(x_planes.shape) != (2, M, K) or not x_planes.is_contiguous()
                 or x_planes.device != dev):
