@@ -23,3 +23,17 @@ def test_reference_arm_prints_the_contract_line():
     assert cb['kind'] in ('port', 'reference') and cb['cores'] >= 1 and cb['value'] == d['value']
     e = d['e2e']
     assert e['value'] == d['value'] and e['unit'] == d['unit'] and e['h2d_bytes_per_step'] == 0 and e['d2h_bytes_per_step'] == 0
+
+
+def test_reference_arm_under_torchrun_prints_once():
+    """Launched like the driver launches N > 1 (torchrun, one process per rank): rank 0 alone runs and prints the line,
+    the other rank exits 0 without work."""
+    out = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
+                          '--master-addr', '127.0.0.1', '--master-port', '29519', os.path.join(ROOT, 'bench.py'),
+                          '--impl', 'reference', '--gpus', '2', '--steps', '1', '--warmup', '1'],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip().startswith('{')]
+    assert len(lines) == 1, out.stdout[-2000:]
+    d = json.loads(lines[0])
+    assert d['impl'] == 'reference' and d['n_gpus'] == 2 and d['value'] > 0
