@@ -37,3 +37,16 @@ def test_reference_arm_under_torchrun_prints_once():
     assert len(lines) == 1, out.stdout[-2000:]
     d = json.loads(lines[0])
     assert d['impl'] == 'reference' and d['n_gpus'] == 2 and d['value'] > 0
+
+
+def test_native_arm_fails_loudly_without_a_gpu():
+    """No CPU fallback on the product path: without a CUDA device the native arm exits non-zero and prints no JSON line."""
+    import torch
+    if torch.cuda.is_available():
+        import pytest
+        pytest.skip('a CUDA device is present')
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--steps', '1', '--warmup', '1'],
+                         capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert out.returncode != 0
+    assert not [ln for ln in out.stdout.splitlines() if ln.strip().startswith('{')]
+    assert 'CUDA' in out.stderr
